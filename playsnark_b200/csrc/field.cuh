@@ -1,0 +1,214 @@
+// Montgomery prime-field arithmetic on 32-bit limbs for sm_100a (BLS12-381 Fp: 12 limbs, Fr: 8).
+//
+// Replaces, on the device, the third-party big-integer arithmetic the reference reaches through
+// kyber.Scalar / kyber.Point (reference call sites: algebra.go:92-105 Scalar.Mul/Add,
+// algebra.go:348-359 Point.Mul/Add; modules named in go.mod:6-8).  Values are kept in Montgomery
+// form x*R mod p with R = 2^(32N), always fully reduced to [0, p).
+//
+// The multiplier is a row-interleaved (CIOS) Montgomery product written as carry chains of
+// mad.lo.cc / madc.hi.cc on *alternating* limbs: the partial products of the even limbs of the
+// multiplicand land in one accumulator ("aligned"), those of the odd limbs in a second one that is
+// shifted by one limb.  Inside one chain consecutive 64-bit products do not overlap, so a single
+// carry flag ripples through it and ptxas can pair every lo/hi couple into one IMAD.WIDE.U32(.X).
+#pragma once
+#include <cstdint>
+#include "constants.cuh"
+
+namespace ps {
+
+#define PS_DEV __device__ __forceinline__
+
+// ---- PTX carry-chain primitives -------------------------------------------------------------
+PS_DEV uint32_t ptx_add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PS_DEV uint32_t ptx_addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PS_DEV uint32_t ptx_addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PS_DEV uint32_t ptx_sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PS_DEV uint32_t ptx_subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PS_DEV uint32_t ptx_subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+
+// acc[0..N) = sum over k of a[2k] * b * 2^(64k)   (no carries: products are disjoint)
+template <int N>
+PS_DEV void mul_chain(uint32_t* acc, const uint32_t* a, uint32_t b) {
+#pragma unroll
+  for (int j = 0; j < N; j += 2)
+    asm volatile("mul.lo.u32 %0,%2,%3; mul.hi.u32 %1,%2,%3;" : "=r"(acc[j]), "=r"(acc[j + 1]) : "r"(a[j]), "r"(b));
+}
+
+// acc[0..N) += sum over k of MOD[OFF+2k] * b * 2^(64k): the modulus limbs are immediates.
+template <class P, int OFF, bool CARRY_IN>
+PS_DEV void mad_chain_mod(uint32_t* acc, uint32_t b) {
+  constexpr int N = P::N;
+  if (CARRY_IN)
+    asm volatile("madc.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(P::MOD(OFF)), "r"(b));
+  else
+    asm volatile("mad.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(P::MOD(OFF)), "r"(b));
+#pragma unroll
+  for (int j = 2; j < N; j += 2)
+    asm volatile("madc.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(acc[j]), "+r"(acc[j + 1]) : "r"(P::MOD(OFF + j)), "r"(b));
+}
+
+// acc[0..N) += sum over k of a[2k] * b * 2^(64k); CARRY_IN consumes the pending carry flag at
+// limb 0; the carry out of limb N-1 is left in the flag.
+template <int N, bool CARRY_IN>
+PS_DEV void mad_chain(uint32_t* acc, const uint32_t* a, uint32_t b) {
+  if (CARRY_IN)
+    asm volatile("madc.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(a[0]), "r"(b));
+  else
+    asm volatile("mad.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(a[0]), "r"(b));
+#pragma unroll
+  for (int j = 2; j < N; j += 2)
+    asm volatile("madc.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(acc[j]), "+r"(acc[j + 1]) : "r"(a[j]), "r"(b));
+}
+
+// ---- field element ----------------------------------------------------------------------------
+template <class P>
+struct alignas(16) Fe {
+  static constexpr int N = P::N;
+  using Params = P;
+  uint32_t v[P::N];
+
+  PS_DEV static Fe zero() { Fe r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = 0;
+    return r; }
+  PS_DEV static Fe one() { Fe r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::ONE(i);
+    return r; }
+  template <class FN>
+  PS_DEV static Fe from_const(FN limb) { Fe r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = limb(i);
+    return r; }
+
+  PS_DEV bool is_zero() const { uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= v[i];
+    return o == 0; }
+  PS_DEV bool operator==(const Fe& b) const { uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= v[i] ^ b.v[i];
+    return o == 0; }
+  PS_DEV bool operator!=(const Fe& b) const { return !(*this == b); }
+
+  // r = a - p if a >= p (a < 2p on entry; `top` is the carry limb above v[N-1])
+  PS_DEV static void final_sub(Fe& a, uint32_t top) {
+    uint32_t t[N];
+    t[0] = ptx_sub_cc(a.v[0], P::MOD(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = ptx_subc_cc(a.v[i], P::MOD(i));
+    uint32_t borrow = ptx_subc(top, 0);  // 0 if a >= p, 0xffffffff otherwise
+#pragma unroll
+    for (int i = 0; i < N; i++) a.v[i] = borrow ? a.v[i] : t[i];
+  }
+
+  PS_DEV friend Fe operator+(const Fe& a, const Fe& b) {
+    Fe r;
+    r.v[0] = ptx_add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.v[i] = ptx_addc_cc(a.v[i], b.v[i]);
+    uint32_t top = ptx_addc(0, 0);
+    final_sub(r, top);
+    return r;
+  }
+  PS_DEV friend Fe operator-(const Fe& a, const Fe& b) {
+    Fe r;
+    r.v[0] = ptx_sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.v[i] = ptx_subc_cc(a.v[i], b.v[i]);
+    uint32_t borrow = ptx_subc(0, 0);  // 0xffffffff when a < b
+    uint32_t t[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = P::MOD(i) & borrow;
+    r.v[0] = ptx_add_cc(r.v[0], t[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = ptx_addc_cc(r.v[i], t[i]);
+    r.v[N - 1] = ptx_addc(r.v[N - 1], t[N - 1]);
+    return r;
+  }
+  PS_DEV Fe neg() const { return is_zero() ? *this : (Fe::zero() - *this); }
+  PS_DEV Fe dbl() const { return *this + *this; }
+
+  // Montgomery product a*b/R mod p.
+  PS_DEV friend Fe operator*(const Fe& a, const Fe& b) {
+    // T = X + 2^32 * Y.  X receives the products of even limbs, Y those of odd limbs.
+    uint32_t X[N], Y[N];
+    uint32_t pend;  // limb to be added at weight 1 (spilled out of X by the previous row's shift)
+    {
+      const uint32_t bi = b.v[0];
+      mul_chain<N>(X, a.v, bi);
+      mul_chain<N>(Y, a.v + 1, bi);
+      const uint32_t m = X[0] * P::INV;
+      mad_chain_mod<P, 0, false>(X, m);
+      uint32_t cx = ptx_addc(0, 0);
+      mad_chain_mod<P, 1, false>(Y, m);
+      // shift right one limb: X[0] == 0 now.
+      pend = X[1];
+#pragma unroll
+      for (int k = 0; k < N - 2; k++) X[k] = X[k + 2];
+      X[N - 2] = cx; X[N - 1] = 0;
+      // roles swap: new aligned accumulator is Y, new shifted one is X
+    }
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+      const uint32_t bi = b.v[i];
+      // even rows of the loop (i odd) have Y aligned / X shifted, and vice versa.
+      uint32_t* A = (i & 1) ? Y : X;  // aligned
+      uint32_t* S = (i & 1) ? X : Y;  // shifted
+      A[0] = ptx_add_cc(A[0], pend);                 // carry -> weight 2^32 == S[0]
+      mad_chain<N, true>(S, a.v + 1, bi);            // odd limbs, consumes that carry
+      mad_chain<N, false>(A, a.v, bi);               // even limbs
+      uint32_t cx = ptx_addc(0, 0);
+      const uint32_t m = A[0] * P::INV;
+      mad_chain_mod<P, 0, false>(A, m);
+      cx = ptx_addc(cx, 0);
+      mad_chain_mod<P, 1, false>(S, m);
+      pend = A[1];
+#pragma unroll
+      for (int k = 0; k < N - 2; k++) A[k] = A[k + 2];
+      A[N - 2] = cx; A[N - 1] = 0;
+    }
+    // after N rows (N even) the aligned accumulator is X again
+    uint32_t* A = (N & 1) ? Y : X;
+    uint32_t* S = (N & 1) ? X : Y;
+    Fe r;
+    r.v[0] = ptx_add_cc(A[0], pend);
+#pragma unroll
+    for (int k = 1; k < N; k++) r.v[k] = ptx_addc_cc(A[k], S[k - 1]);
+    uint32_t top = ptx_addc(S[N - 1], 0);
+    final_sub(r, top);
+    return r;
+  }
+  PS_DEV Fe sqr() const { return (*this) * (*this); }
+
+  PS_DEV Fe to_mont() const { return (*this) * from_const([] __device__ (int i) { return P::R2(i); }); }
+  PS_DEV Fe from_mont() const { Fe o = zero(); o.v[0] = 1; return (*this) * o; }
+
+  // this^e, e = nlimbs little-endian 32-bit limbs (readable at run time: constant or global memory)
+  __device__ __noinline__ Fe pow(const uint32_t* e, int nlimbs) const {
+    Fe acc = one();
+    bool started = false;
+    for (int i = nlimbs - 1; i >= 0; i--) {
+      uint32_t w = e[i];
+#pragma unroll 1
+      for (int b = 31; b >= 0; b--) {
+        if (started) acc = acc * acc;
+        if ((w >> b) & 1) {
+          if (started) acc = acc * (*this); else { acc = *this; started = true; }
+        }
+      }
+    }
+    return acc;
+  }
+};
+
+using Fp = Fe<FpParams>;
+using Fr = Fe<FrParams>;
+
+}  // namespace ps
+
+namespace ps {
+PS_DEV Fp fp_inv(const Fp& a) { return a.pow(c_FP_MOD_M2, 12); }   // 0 -> 0
+PS_DEV Fr fr_inv(const Fr& a) { return a.pow(c_FR_MOD_M2, 8); }
+PS_DEV Fp fp_sqrt_candidate(const Fp& a) { return a.pow(c_FP_SQRT_EXP, 12); }  // p = 3 mod 4
+}  // namespace ps
