@@ -1,0 +1,159 @@
+/* playsnark_b200 -- C ABI of the B200-native prover backend.
+ *
+ * Drop-in boundary for the proving path of nikkolasg/playsnark.  The reference has no FFI; its
+ * boundary is the pair of Go functions
+ *     Groth16Prove(tr Groth16Setup, q QAP, sol Vector) Groth16Proof      (groth16.go:122)
+ *     PHGR13Prove(ek PHGR13EvalKey, qap QAP, solution Vector) PHGR13Proof (pinochio.go:207)
+ * and the helpers they call (QAP.Quotient qap.go:151, Poly.BlindEval algebra.go:348).  A cgo shim
+ * inside package playsnark marshals its kyber values with MarshalBinary and calls the entry points
+ * below (INTEGRATION.md shows the shim).  Conventions:
+ *   - every function returns an int status (PS_OK == 0); the shim maps PS_ERR_REMAINDER to
+ *     panic("apocalypse") (qap.go:159, pinochio.go:215) and PS_ERR_LENGTH to the BlindEval length
+ *     panic (algebra.go:350-352);
+ *   - Fr scalars: 32 bytes, big-endian, canonical (< r)          (kyber Scalar.MarshalBinary);
+ *   - G1 / G2 points: 48 / 96 bytes zcash-compressed (PS_FMT_COMPRESSED; kyber Point.MarshalBinary)
+ *     or 96 / 192 bytes zcash-uncompressed (PS_FMT_AFFINE) for bulk keys already decompressed;
+ *   - handles are opaque, caller-owned, freed with the matching *_free; buffers are caller-owned;
+ *   - one ps_ctx per host thread and per GPU; no global state.
+ * There is no CPU fallback: every entry point needs a CUDA device.
+ */
+#ifndef PLAYSNARK_B200_H
+#define PLAYSNARK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  PS_OK = 0,
+  PS_ERR_ARG = 1,        /* null pointer, bad size or bad enum */
+  PS_ERR_LENGTH = 2,     /* len(p) != len(points): BlindEval's panic, algebra.go:350-352 */
+  PS_ERR_REMAINDER = 3,  /* (a*b - c) mod z != 0: panic("apocalypse"), qap.go:158-160 */
+  PS_ERR_ENCODING = 4,   /* point bytes do not decode to a curve point / scalar >= r */
+  PS_ERR_CUDA = 5,
+  PS_ERR_ALLOC = 6,
+  PS_ERR_UNSUPPORTED = 7
+};
+
+enum { PS_FMT_COMPRESSED = 0, PS_FMT_AFFINE = 1 };
+enum { PS_G1 = 1, PS_G2 = 2 };
+
+typedef struct ps_ctx ps_ctx;
+typedef struct ps_bases ps_bases;     /* resident MSM base set (G1 or G2)                      */
+typedef struct ps_qap ps_qap;         /* resident QAP (dense polynomials or sparse R1CS)        */
+typedef struct ps_g16_key ps_g16_key; /* resident Groth16 proving key                           */
+typedef struct ps_phgr13_key ps_phgr13_key;
+
+const char* ps_strerror(int status);
+const char* ps_version(void);
+
+/* ---- context ------------------------------------------------------------------------------ */
+int ps_ctx_create(int device, ps_ctx** out);
+/* run on a caller-provided CUDA stream (cudaStream_t passed as void*), e.g. torch's current one */
+int ps_ctx_set_stream(ps_ctx* ctx, void* cuda_stream);
+int ps_ctx_sync(ps_ctx* ctx);
+void ps_ctx_destroy(ps_ctx* ctx);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t ps_launch_count(void);
+
+/* ---- MSM bases: the []Commit argument of Poly.BlindEval (algebra.go:348) ------------------- */
+/* `window_bits` = 0 lets the library choose c per call; otherwise fixes the Pippenger window and,
+ * with `precompute_tables` = T > 1, stores 2^(c*t) * P_i for t < T so that T windows share one
+ * bucket set (T is clamped to the number of windows).                                          */
+int ps_bases_load(ps_ctx* ctx, int group, const uint8_t* points, size_t n, int format,
+                  int window_bits, int precompute_tables, ps_bases** out);
+size_t ps_bases_len(const ps_bases* b);
+void ps_bases_free(ps_bases* b);
+/* bases[i] = scalars[i] * generator (GeneratePowersCommit's Mul(s, nil), algebra.go:373,381);
+ * used by setup-side callers and the benchmarks to create large keys on the GPU.               */
+int ps_bases_from_scalars(ps_ctx* ctx, int group, const uint8_t* scalars_be, size_t n,
+                          int window_bits, int precompute_tables, ps_bases** out);
+/* copy points [first, first+count) out as compressed or affine bytes */
+int ps_bases_export(ps_ctx* ctx, const ps_bases* b, size_t first, size_t count, int format, uint8_t* out);
+
+/* ---- MSM: Poly.BlindEval(zero, blindedPoint) = sum_i p[i] * P[i] (algebra.go:348-359) -------- */
+/* n must equal ps_bases_len(b) (PS_ERR_LENGTH otherwise, like the reference's panic).
+ * out: 48 B (G1) / 96 B (G2) compressed.                                                       */
+int ps_msm(ps_ctx* ctx, const ps_bases* b, const uint8_t* scalars_be, size_t n, uint8_t* out);
+/* Partial-range / device-resident variant for sharding and benchmarking: scalars already on the
+ * device as 8 little-endian u32 limbs each, standard (non-Montgomery) form; sums bases
+ * [first, first+n) and leaves the partial as an XYZZ point (4 field elements, Montgomery limbs)
+ * in device memory `d_out_xyzz` (192 B G1 / 384 B G2).                                          */
+int ps_msm_device(ps_ctx* ctx, const ps_bases* b, size_t first, const void* d_scalars_le, size_t n,
+                  void* d_out_xyzz);
+/* sum `count` XYZZ partials (device memory, contiguous) and emit the compressed point: the single
+ * small gather of the multi-GPU MSM.                                                            */
+int ps_msm_combine(ps_ctx* ctx, int group, const void* d_partials_xyzz, size_t count, uint8_t* out);
+
+/* ---- Fr polynomial kernels --------------------------------------------------------------------- */
+/* in-place radix-2 NTT over Fr on `n = 2^log_n` big-endian scalars (host memory).  inverse != 0
+ * computes the inverse transform (scaled by 1/n).  coset (32 B, may be NULL) evaluates on
+ * coset * <omega> (forward) or interpolates from it (inverse).  omega = 7^((r-1)/2^log_n).      */
+int ps_ntt_fr(ps_ctx* ctx, uint8_t* data_be, unsigned log_n, int inverse, const uint8_t* coset_be);
+
+/* QAP as ToQAP produces it (qap.go:35-65): left/right/out are m polynomials of n coefficients
+ * each (row-major m x n, 32 B big-endian, low degree first), z has n+1 coefficients.           */
+int ps_qap_load_dense(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, const uint8_t* left,
+                      const uint8_t* right, const uint8_t* out, const uint8_t* z, ps_qap** qap);
+/* Sparse R1CS twin of the same object for sizes where the dense QAP cannot exist (3*m*n*32 B):
+ * CSR matrices over the gates (row_ptr[n+1], col[nnz], val[nnz] as 32 B big-endian Fr); the
+ * polynomials are implicit (interpolants on the domain {1..n}).                                */
+int ps_qap_load_r1cs(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io,
+                     const uint32_t* l_row_ptr, const uint32_t* l_col, const uint8_t* l_val,
+                     const uint32_t* r_row_ptr, const uint32_t* r_col, const uint8_t* r_val,
+                     const uint32_t* o_row_ptr, const uint32_t* o_col, const uint8_t* o_val,
+                     ps_qap** qap);
+void ps_qap_free(ps_qap* qap);
+
+/* QAP.Quotient (qap.go:151-162): witness = n_vars Fr values (Value.ToFieldElement, curve.go:17),
+ * out_h = n_gates-1 coefficients.  PS_ERR_REMAINDER when z does not divide a*b-c.
+ * out_abc (optional, may be NULL) receives computeAggregatePoly's three polynomials
+ * (qap.go:164-175), 3 * n_gates * 32 B.                                                         */
+int ps_quotient(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_be, uint8_t* out_h, uint8_t* out_abc);
+
+/* ---- Groth16 (groth16.go) ---------------------------------------------------------------------- */
+/* Proving part of Groth16Setup (groth16.go:30-61): Xi[n], Xi2[n] (G2), XiT[n-1], NioLP[n_nio],
+ * Alpha, Beta, Delta (G1), Beta2, Delta2 (G2).                                                   */
+int ps_g16_key_load(ps_ctx* ctx, size_t n_gates, size_t n_nio, int format, const uint8_t* xi,
+                    const uint8_t* xi2, const uint8_t* xit, const uint8_t* niolp, const uint8_t* alpha,
+                    const uint8_t* beta, const uint8_t* delta, const uint8_t* beta2,
+                    const uint8_t* delta2, ps_g16_key** key);
+void ps_g16_key_free(ps_g16_key* key);
+/* Groth16Prove (groth16.go:122-211) with the blinding scalars supplied by the caller (the shim
+ * samples them with Pick(random.New()) as groth16.go:148,158 and stores them in the proof).
+ * outA 48 B, outB 96 B, outC 48 B; out_h optional (n_gates-1 scalars).                          */
+int ps_g16_prove(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const uint8_t* witness_be,
+                 const uint8_t* r_be, const uint8_t* s_be, uint8_t* outA, uint8_t* outB, uint8_t* outC,
+                 uint8_t* out_h);
+
+/* ---- PHGR13 / Pinocchio (pinochio.go) ------------------------------------------------------------ */
+/* PHGR13EvalKey (pinochio.go:37-62): gsi[n-1]; vs, ys, vas, was, yas, vbs, wbs, ybs [n_mid] in G1
+ * (wbs is typed []G2 in the reference but holds G1 points, pinochio.go:114,136); ws [n_mid] G2. */
+int ps_phgr13_key_load(ps_ctx* ctx, size_t n_gates, size_t n_mid, int format, const uint8_t* gsi,
+                       const uint8_t* vs, const uint8_t* ws, const uint8_t* ys, const uint8_t* vas,
+                       const uint8_t* was, const uint8_t* yas, const uint8_t* vbs, const uint8_t* wbs,
+                       const uint8_t* ybs, ps_phgr13_key** key);
+void ps_phgr13_key_free(ps_phgr13_key* key);
+/* PHGR13Prove (pinochio.go:207-254).  out: hs, vss, yss, vass, wass, yass, gz (7 x 48 B, in this
+ * order) then wss (96 B) = 432 bytes.                                                           */
+int ps_phgr13_prove(ps_ctx* ctx, const ps_phgr13_key* key, const ps_qap* qap, const uint8_t* witness_be,
+                    uint8_t* out432, uint8_t* out_h);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------------- */
+/* Integer-multiply pipe microbenchmark: variant 0 = IMAD (mad.lo), 1 = IMAD.HI, 2 = IMAD.WIDE
+ * (independent), 3 = IMAD.WIDE.X carry chains as in the field multiplier; returns instructions/s
+ * over all SMs measured with CUDA events.                                                       */
+int ps_bench_intpipe(ps_ctx* ctx, int variant, int iters, double* inst_per_s, double* ms);
+/* chained Montgomery products per second (field 0 = Fr, 1 = Fp) */
+int ps_bench_fieldmul(ps_ctx* ctx, int field, int iters, double* mul_per_s, double* ms);
+/* device time in ms of the last ps_msm / ps_msm_device call on this context, by phase:
+ * [0] digits+sort, [1] bucket accumulate, [2] bucket reduce, [3] total                          */
+int ps_last_msm_timing(ps_ctx* ctx, float out_ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLAYSNARK_B200_H */

@@ -1,0 +1,358 @@
+"""Host-side mirror of the reference's proving interface.
+
+Names, argument meaning and error behaviour follow the Go package so that parity tests read like the
+reference's own tests:
+  Groth16Prove(tr, q, sol)          groth16.go:122
+  PHGR13Prove(ek, qap, solution)    pinochio.go:207
+  QAP.Quotient(sol) -> Quotient     qap.go:151         (raises ArithmeticError("apocalypse"))
+  Poly.BlindEval -> BlindEval       algebra.go:348     (raises ValueError on length mismatch)
+Scalars are Python ints mod r (the reference's kyber.Scalar); points are their MarshalBinary bytes
+(48 B G1 / 96 B G2, zcash-compressed), which is also what crosses the C ABI.  This module holds no
+arithmetic: every value is computed by the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import secrets
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+from . import _lib as L
+
+R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+
+Vector = List[int]
+Poly = List[int]
+
+
+def _fr_bytes(vals: Sequence[int]) -> bytes:
+    return b"".join((int(v) % R).to_bytes(32, "big") for v in vals)
+
+
+def _fr_list(buf: bytes) -> List[int]:
+    return [int.from_bytes(buf[i:i + 32], "big") for i in range(0, len(buf), 32)]
+
+
+class Bases:
+    """Device-resident []Commit (the blindedPoint argument of BlindEval)."""
+
+    def __init__(self, backend: "Backend", handle, group: int):
+        self.backend, self.handle, self.group = backend, handle, group
+
+    def __len__(self):
+        return self.backend.lib.ps_bases_len(self.handle)
+
+    def export(self, first=0, count=None, fmt=L.PS_FMT_COMPRESSED) -> List[bytes]:
+        n = len(self) - first if count is None else count
+        per = {(1, 0): 48, (1, 1): 96, (2, 0): 96, (2, 1): 192}[(self.group, fmt)]
+        buf = C.create_string_buffer(max(1, n * per))
+        self.backend._check(self.backend.lib.ps_bases_export(self.backend.ctx, self.handle, first, n, fmt, buf))
+        return [buf.raw[i * per:(i + 1) * per] for i in range(n)]
+
+    def close(self):
+        if self.handle:
+            self.backend.lib.ps_bases_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Backend:
+    """One context per process and GPU (ps_ctx)."""
+
+    def __init__(self, device: int = 0, lib=None):
+        self.lib = lib if lib is not None else L.load()
+        ctx = C.c_void_p()
+        self._check(self.lib.ps_ctx_create(device, C.byref(ctx)))
+        self.ctx = ctx
+        self.device = device
+
+    def _check(self, status):
+        L.check(self.lib, status)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.ps_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def sync(self):
+        self._check(self.lib.ps_ctx_sync(self.ctx))
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._check(self.lib.ps_ctx_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr)))
+
+    def launch_count(self) -> int:
+        return int(self.lib.ps_launch_count())
+
+    # ---- bases / MSM ----
+    def load_bases(self, group: int, points, fmt: int = L.PS_FMT_COMPRESSED, window_bits: int = 0, tables: int = 1) -> Bases:
+        per = {(1, 0): 48, (1, 1): 96, (2, 0): 96, (2, 1): 192}[(group, fmt)]
+        buf = points if isinstance(points, (bytes, bytearray)) else b"".join(points)
+        assert len(buf) % per == 0
+        h = C.c_void_p()
+        self._check(self.lib.ps_bases_load(self.ctx, group, bytes(buf), len(buf) // per, fmt, window_bits, tables, C.byref(h)))
+        return Bases(self, h, group)
+
+    def bases_from_scalars(self, group: int, scalars, window_bits: int = 0, tables: int = 1) -> Bases:
+        buf = scalars if isinstance(scalars, (bytes, bytearray)) else _fr_bytes(scalars)
+        h = C.c_void_p()
+        self._check(self.lib.ps_bases_from_scalars(self.ctx, group, bytes(buf), len(buf) // 32, window_bits, tables, C.byref(h)))
+        return Bases(self, h, group)
+
+    def msm(self, bases: Bases, scalars) -> bytes:
+        buf = scalars if isinstance(scalars, (bytes, bytearray)) else _fr_bytes(scalars)
+        n = len(buf) // 32
+        out = C.create_string_buffer(48 if bases.group == L.PS_G1 else 96)
+        st = self.lib.ps_msm(self.ctx, bases.handle, bytes(buf), n, out)
+        if st == L.PS_ERR_LENGTH:
+            raise ValueError("mismatch of length between poly %d and blinded eval points %d" % (n, len(bases)))
+        self._check(st)
+        return out.raw
+
+    def msm_timing(self):
+        t = (C.c_float * 4)()
+        self._check(self.lib.ps_last_msm_timing(self.ctx, t))
+        return {"sort_ms": t[0], "accumulate_ms": t[1], "reduce_ms": t[2], "total_ms": t[3]}
+
+    # ---- NTT ----
+    def ntt(self, values: Sequence[int], inverse: bool = False, coset: Optional[int] = None) -> List[int]:
+        n = len(values)
+        log_n = n.bit_length() - 1
+        if n != 1 << log_n:
+            raise ValueError("NTT size must be a power of two")
+        buf = C.create_string_buffer(_fr_bytes(values), n * 32)
+        cz = None if coset is None else (coset % R).to_bytes(32, "big")
+        self._check(self.lib.ps_ntt_fr(self.ctx, buf, log_n, 1 if inverse else 0, cz))
+        return _fr_list(buf.raw)
+
+
+_default: Optional[Backend] = None
+
+
+def default_backend() -> Backend:
+    global _default
+    if _default is None:
+        _default = Backend(0)
+    return _default
+
+
+def set_default_backend(b: Optional[Backend]):
+    global _default
+    _default = b
+
+
+def BlindEval(p: Poly, blinded: Bases, backend: Optional[Backend] = None) -> bytes:
+    """Poly.BlindEval (algebra.go:348-359) against a resident base set."""
+    return (backend or blinded.backend).msm(blinded, p)
+
+
+# ---- R1CS / QAP types (r1cs.go:81-102, qap.go:10-27) ------------------------------------------------
+@dataclass
+class R1CS:
+    """Dense 0/1(/const) gate matrices; variable order [const, inputs..., outputs..., intermediates...]
+    (r1cs.go:132-144)."""
+    inputs: List[str] = field(default_factory=list)
+    outputs: List[str] = field(default_factory=list)
+    intermediates: List[str] = field(default_factory=list)
+    left: List[List[int]] = field(default_factory=list)
+    right: List[List[int]] = field(default_factory=list)
+    out: List[List[int]] = field(default_factory=list)
+
+    @property
+    def vars(self) -> List[str]:
+        return ["const"] + self.inputs + self.outputs + self.intermediates
+
+    def nbIO(self) -> int:
+        return 1 + len(self.inputs) + len(self.outputs)
+
+
+@dataclass
+class QAP:
+    """qap.go:10-27: left/right/out are nbVars polynomials of nbGates coefficients (low degree
+    first); z has nbGates+1."""
+    nbVars: int
+    nbIO: int
+    nbGates: int
+    left: List[Poly]
+    right: List[Poly]
+    out: List[Poly]
+    z: Poly
+    _dev: object = None
+
+    def _resident(self, backend: Backend):
+        if self._dev is None or self._dev[0] is not backend:
+            n, m = self.nbGates, self.nbVars
+            if len(self.left) != m or len(self.right) != m or len(self.out) != m:
+                raise ValueError("different number of solution variables than polynomials")
+            for polys in (self.left, self.right, self.out):
+                for p in polys:
+                    if len(p) != n:
+                        raise ValueError("QAP polynomial with %d coefficients, expected %d" % (len(p), n))
+            if len(self.z) != n + 1:
+                raise ValueError("z must have nbGates+1 coefficients")
+            h = C.c_void_p()
+            flat = lambda polys: b"".join(_fr_bytes(p) for p in polys)
+            backend._check(backend.lib.ps_qap_load_dense(backend.ctx, n, m, self.nbIO, flat(self.left), flat(self.right),
+                                                         flat(self.out), _fr_bytes(self.z), C.byref(h)))
+            self._dev = (backend, h)
+        return self._dev[1]
+
+    def Quotient(self, sol: Vector, backend: Optional[Backend] = None) -> Poly:
+        return Quotient(self, sol, backend)
+
+
+def _sanity(q: QAP, sol: Vector):
+    """QAP.sanityCheck, qap.go:177-189."""
+    if len(sol) != q.nbVars:
+        raise ValueError("different number of solution variables than left polynomials")
+
+
+def Quotient(q: QAP, sol: Vector, backend: Optional[Backend] = None, return_abc: bool = False):
+    """QAP.Quotient, qap.go:151-162."""
+    b = backend or default_backend()
+    _sanity(q, sol)
+    h = q._resident(b)
+    n = q.nbGates
+    out = C.create_string_buffer(max(1, (n - 1) * 32))
+    abc = C.create_string_buffer(3 * n * 32) if return_abc else None
+    st = b.lib.ps_quotient(b.ctx, h, _fr_bytes(sol), out, abc)
+    if st == L.PS_ERR_REMAINDER:
+        raise ArithmeticError("apocalypse")
+    b._check(st)
+    hx = _fr_list(out.raw[:(n - 1) * 32])
+    if return_abc:
+        v = _fr_list(abc.raw)
+        return hx, (v[:n], v[n:2 * n], v[2 * n:])
+    return hx
+
+
+# ---- Groth16 (groth16.go:30-61, 106-118) --------------------------------------------------------------
+@dataclass
+class Groth16Setup:
+    """Prover-side fields of Groth16Setup; points as MarshalBinary bytes."""
+    Alpha: bytes
+    Beta: bytes
+    Delta: bytes
+    Xi: List[bytes]
+    NioLP: List[bytes]
+    XiT: List[bytes]
+    Beta2: bytes
+    Delta2: bytes
+    Xi2: List[bytes]
+    IoLP: List[bytes] = field(default_factory=list)   # verifier side, carried for completeness
+    Gamma: bytes = b""
+    _dev: object = None
+
+    def _resident(self, backend: Backend):
+        if self._dev is None or self._dev[0] is not backend:
+            n = len(self.Xi)
+            if len(self.Xi2) != n or len(self.XiT) != n - 1:
+                raise ValueError("mismatch of length between poly and blinded eval points")
+            h = C.c_void_p()
+            j = b"".join
+            backend._check(backend.lib.ps_g16_key_load(
+                backend.ctx, n, len(self.NioLP), L.PS_FMT_COMPRESSED, j(self.Xi), j(self.Xi2), j(self.XiT), j(self.NioLP),
+                self.Alpha, self.Beta, self.Delta, self.Beta2, self.Delta2, C.byref(h)))
+            self._dev = (backend, h)
+        return self._dev[1]
+
+
+@dataclass
+class Groth16ToxicProof:
+    R: int
+    S: int
+
+
+@dataclass
+class Groth16Proof:
+    tp: Groth16ToxicProof
+    A: bytes
+    B: bytes
+    C: bytes
+    h: Optional[Poly] = None
+
+
+def Groth16Prove(tr: Groth16Setup, q: QAP, sol: Vector, r: Optional[int] = None, s: Optional[int] = None,
+                 backend: Optional[Backend] = None, want_h: bool = False) -> Groth16Proof:
+    """Groth16Prove, groth16.go:122-211.  r, s default to fresh randomness (groth16.go:148,158) and
+    are kept in the proof's tp like the reference; tests inject them."""
+    b = backend or default_backend()
+    _sanity(q, sol)
+    if r is None:
+        r = secrets.randbelow(R - 1) + 1
+    if s is None:
+        s = secrets.randbelow(R - 1) + 1
+    kh, qh = tr._resident(b), q._resident(b)
+    A, Bp, Cp = C.create_string_buffer(48), C.create_string_buffer(96), C.create_string_buffer(48)
+    hb = C.create_string_buffer(max(1, (q.nbGates - 1) * 32)) if want_h else None
+    st = b.lib.ps_g16_prove(b.ctx, kh, qh, _fr_bytes(sol), _fr_bytes([r]), _fr_bytes([s]), A, Bp, Cp, hb)
+    if st == L.PS_ERR_REMAINDER:
+        raise ArithmeticError("apocalypse")
+    if st == L.PS_ERR_LENGTH:
+        raise ValueError("mismatch of length between poly and blinded eval points")
+    b._check(st)
+    return Groth16Proof(Groth16ToxicProof(r, s), A.raw, Bp.raw, Cp.raw,
+                        _fr_list(hb.raw[:(q.nbGates - 1) * 32]) if want_h else None)
+
+
+# ---- PHGR13 (pinochio.go:37-62, 180-203) -----------------------------------------------------------------
+@dataclass
+class PHGR13EvalKey:
+    vs: List[bytes]
+    ws: List[bytes]   # G2
+    ys: List[bytes]
+    vas: List[bytes]
+    was: List[bytes]
+    yas: List[bytes]
+    gsi: List[bytes]
+    vbs: List[bytes]
+    wbs: List[bytes]  # typed []G2 in the reference but holds G1 points (pinochio.go:114,136)
+    ybs: List[bytes]
+    _dev: object = None
+
+    def _resident(self, backend: Backend):
+        if self._dev is None or self._dev[0] is not backend:
+            h = C.c_void_p()
+            j = b"".join
+            backend._check(backend.lib.ps_phgr13_key_load(
+                backend.ctx, len(self.gsi) + 1, len(self.vs), L.PS_FMT_COMPRESSED, j(self.gsi), j(self.vs), j(self.ws),
+                j(self.ys), j(self.vas), j(self.was), j(self.yas), j(self.vbs), j(self.wbs), j(self.ybs), C.byref(h)))
+            self._dev = (backend, h)
+        return self._dev[1]
+
+
+@dataclass
+class PHGR13Proof:
+    vss: bytes
+    vass: bytes
+    wss: bytes
+    wass: bytes
+    yss: bytes
+    yass: bytes
+    hs: bytes
+    gz: bytes
+    h: Optional[Poly] = None
+
+
+def PHGR13Prove(ek: PHGR13EvalKey, qap: QAP, solution: Vector, backend: Optional[Backend] = None,
+                want_h: bool = False) -> PHGR13Proof:
+    """PHGR13Prove, pinochio.go:207-254."""
+    b = backend or default_backend()
+    _sanity(qap, solution)
+    kh, qh = ek._resident(b), qap._resident(b)
+    out = C.create_string_buffer(432)
+    hb = C.create_string_buffer(max(1, (qap.nbGates - 1) * 32)) if want_h else None
+    st = b.lib.ps_phgr13_prove(b.ctx, kh, qh, _fr_bytes(solution), out, hb)
+    if st == L.PS_ERR_REMAINDER:
+        raise ArithmeticError("apocalypse")
+    if st == L.PS_ERR_LENGTH:
+        raise ValueError("mismatch of length between poly and blinded eval points")
+    b._check(st)
+    o = out.raw
+    g1 = [o[i * 48:(i + 1) * 48] for i in range(7)]  # hs vss yss vass wass yass gz
+    return PHGR13Proof(hs=g1[0], vss=g1[1], yss=g1[2], vass=g1[3], wass=g1[4], yass=g1[5], gz=g1[6], wss=o[336:432],
+                       h=_fr_list(hb.raw[:(qap.nbGates - 1) * 32]) if want_h else None)

@@ -1,0 +1,35 @@
+// The per-GPU context behind the C ABI's opaque ps_ctx handle.
+#pragma once
+#include "backend.cuh"
+#include "ntt.cuh"
+
+struct ps_ctx {
+  int device = 0;
+  ps::ps_stream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  ps::Arena arena;                 // per-call scratch, persists across calls
+  ps::NttTables ntt_cache[31];     // twiddles by log2(size), built on first use
+  void* fixed_base[2] = {nullptr, nullptr};  // 32 x 255 affine multiples of the G1 / G2 generator
+  // phase events of the last MSM (cudaEvent_t): start, sorted, accumulated, reduced
+  void* ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+};
+
+namespace ps {
+inline int ctx_ntt_tables(ps_ctx* ctx, int log_n, const NttTables** out) {
+  if (log_n < 0 || log_n > 30) return PS_ERR_ARG;
+  NttTables& t = ctx->ntt_cache[log_n];
+  if (t.log_n != log_n) PS_TRY(ntt_tables_build(ctx->stream, log_n, &t));
+  *out = &t;
+  return PS_OK;
+}
+inline int ctx_event(ps_ctx* ctx, int i) {
+#if PS_GPU
+  if (ctx->ev[i]) PS_CUDA_TRY(cudaEventRecord((cudaEvent_t)ctx->ev[i], ctx->stream));
+#else
+  (void)ctx; (void)i;
+#endif
+  return PS_OK;
+}
+}  // namespace ps

@@ -1,0 +1,195 @@
+// BLS12-381 G1 / G2 group arithmetic for the prover's multi-scalar multiplications.
+//
+// Replaces kyber.Point.Add / Mul as the reference calls them inside Poly.BlindEval
+// (algebra.go:348-359), sumBlind (groth16.go:134-141) and computeSolCommit (pinochio.go:222-229).
+// Points are stored affine (bases) or in extended-Jacobian XYZZ form (accumulators):
+//   x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2;  ZZ == 0 encodes the point at infinity.
+// Affine infinity is encoded (0, 0), which is not on either curve (b != 0).
+// The same templates serve G1 (F = Fp) and G2 (F = Fp2 = Fp[u]/(u^2+1)).
+#pragma once
+#include "field.cuh"
+
+namespace ps {
+
+// ---- Fp2 ---------------------------------------------------------------------------------------
+struct alignas(16) Fp2 {
+  Fp c0, c1;
+  PS_DEV static Fp2 zero() { return Fp2{Fp::zero(), Fp::zero()}; }
+  PS_DEV static Fp2 one() { return Fp2{Fp::one(), Fp::zero()}; }
+  PS_DEV bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  PS_DEV bool operator==(const Fp2& b) const { return c0 == b.c0 && c1 == b.c1; }
+  PS_DEV bool operator!=(const Fp2& b) const { return !(*this == b); }
+  PS_DEV friend Fp2 operator+(const Fp2& a, const Fp2& b) { return Fp2{a.c0 + b.c0, a.c1 + b.c1}; }
+  PS_DEV friend Fp2 operator-(const Fp2& a, const Fp2& b) { return Fp2{a.c0 - b.c0, a.c1 - b.c1}; }
+  PS_DEV Fp2 neg() const { return Fp2{c0.neg(), c1.neg()}; }
+  PS_DEV Fp2 dbl() const { return Fp2{c0.dbl(), c1.dbl()}; }
+  // Karatsuba: 3 base-field products
+  PS_DEV friend Fp2 operator*(const Fp2& a, const Fp2& b) {
+    Fp t0 = fe_mul_call(a.c0, b.c0);
+    Fp t1 = fe_mul_call(a.c1, b.c1);
+    Fp t2 = fe_mul_call(a.c0 + a.c1, b.c0 + b.c1);
+    return Fp2{t0 - t1, t2 - t0 - t1};
+  }
+  // (c0 + c1 u)^2 = (c0+c1)(c0-c1) + 2 c0 c1 u: 2 base-field products
+  PS_DEV Fp2 sqr() const {
+    Fp s = c0 + c1, d = c0 - c1;
+    Fp m = fe_mul_call(c0, c1);
+    return Fp2{fe_mul_call(s, d), m.dbl()};
+  }
+};
+
+PS_DEV Fp2 fp2_inv(const Fp2& a) {
+  Fp d = fp_inv(fe_mul_call(a.c0, a.c0) + fe_mul_call(a.c1, a.c1));
+  return Fp2{fe_mul_call(a.c0, d), fe_mul_call(a.c1, d).neg()};
+}
+
+template <class F> struct FieldInv;
+template <> struct FieldInv<Fp> { PS_DEV static Fp inv(const Fp& a) { return fp_inv(a); } };
+template <> struct FieldInv<Fp2> { PS_DEV static Fp2 inv(const Fp2& a) { return fp2_inv(a); } };
+
+// ---- points --------------------------------------------------------------------------------------
+template <class F>
+struct alignas(16) Affine {
+  F x, y;
+  PS_DEV bool is_inf() const { return x.is_zero() && y.is_zero(); }
+  PS_DEV static Affine inf() { return Affine{F::zero(), F::zero()}; }
+  PS_DEV Affine neg() const { return Affine{x, y.neg()}; }
+};
+
+template <class F>
+struct alignas(16) XYZZ {
+  F x, y, zz, zzz;
+  PS_DEV bool is_inf() const { return zz.is_zero(); }
+  PS_DEV static XYZZ inf() { return XYZZ{F::zero(), F::zero(), F::zero(), F::zero()}; }
+  PS_DEV static XYZZ from_affine(const Affine<F>& p) {
+    if (p.is_inf()) return inf();
+    return XYZZ{p.x, p.y, F::one(), F::one()};
+  }
+  PS_DEV XYZZ neg() const { return XYZZ{x, y.neg(), zz, zzz}; }
+};
+
+// 2*P for affine P (mdbl-2008-s-1, a = 0)
+template <class F>
+PS_DEV XYZZ<F> xyzz_dbl_affine(const Affine<F>& p) {
+  if (p.is_inf() || p.y.is_zero()) return XYZZ<F>::inf();
+  F U = p.y.dbl();
+  F V = U.sqr();
+  F W = U * V;
+  F S = p.x * V;
+  F X2 = p.x.sqr();
+  F M = X2.dbl() + X2;
+  F X3 = M.sqr() - S.dbl();
+  F Y3 = M * (S - X3) - W * p.y;
+  return XYZZ<F>{X3, Y3, V, W};
+}
+
+// 2*P (dbl-2008-s-1, a = 0)
+template <class F>
+PS_DEV XYZZ<F> xyzz_dbl(const XYZZ<F>& p) {
+  if (p.is_inf() || p.y.is_zero()) return XYZZ<F>::inf();
+  F U = p.y.dbl();
+  F V = U.sqr();
+  F W = U * V;
+  F S = p.x * V;
+  F X2 = p.x.sqr();
+  F M = X2.dbl() + X2;
+  F X3 = M.sqr() - S.dbl();
+  F Y3 = M * (S - X3) - W * p.y;
+  return XYZZ<F>{X3, Y3, V * p.zz, W * p.zzz};
+}
+
+// out-of-line ("cold") versions, defined below: used on rare paths and in every kernel that is not
+// the bucket-accumulation hot loop, to keep code size and compile time down
+template <class F> PS_NOINLINE XYZZ<F> xyzz_dbl_c(const XYZZ<F>& p);
+template <class F> PS_NOINLINE XYZZ<F> xyzz_dbl_affine_c(const Affine<F>& p);
+
+// acc += q, q affine (madd-2008-s: 8M + 2S), all special cases handled
+template <class F>
+PS_DEV void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q) {
+  if (q.is_inf()) return;
+  if (acc.is_inf()) { acc = XYZZ<F>{q.x, q.y, F::one(), F::one()}; return; }
+  F U2 = q.x * acc.zz;
+  F S2 = q.y * acc.zzz;
+  F Pd = U2 - acc.x;
+  F Rd = S2 - acc.y;
+  if (Pd.is_zero()) {
+    if (Rd.is_zero()) acc = xyzz_dbl_affine_c(q); else acc = XYZZ<F>::inf();
+    return;
+  }
+  F PP = Pd.sqr();
+  F PPP = Pd * PP;
+  F Q = acc.x * PP;
+  F X3 = Rd.sqr() - PPP - Q.dbl();
+  F Y3 = Rd * (Q - X3) - acc.y * PPP;
+  acc.x = X3;
+  acc.y = Y3;
+  acc.zz = acc.zz * PP;
+  acc.zzz = acc.zzz * PPP;
+}
+
+// acc += q, both XYZZ (add-2008-s: 12M + 2S)
+template <class F>
+PS_DEV void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
+  if (q.is_inf()) return;
+  if (acc.is_inf()) { acc = q; return; }
+  F U1 = acc.x * q.zz;
+  F U2 = q.x * acc.zz;
+  F S1 = acc.y * q.zzz;
+  F S2 = q.y * acc.zzz;
+  F Pd = U2 - U1;
+  F Rd = S2 - S1;
+  if (Pd.is_zero()) {
+    if (Rd.is_zero()) acc = xyzz_dbl_c(acc); else acc = XYZZ<F>::inf();
+    return;
+  }
+  F PP = Pd.sqr();
+  F PPP = Pd * PP;
+  F Q = U1 * PP;
+  F X3 = Rd.sqr() - PPP - Q.dbl();
+  F Y3 = Rd * (Q - X3) - S1 * PPP;
+  acc.x = X3;
+  acc.y = Y3;
+  acc.zz = acc.zz * q.zz * PP;
+  acc.zzz = acc.zzz * q.zzz * PPP;
+}
+
+template <class F> PS_NOINLINE XYZZ<F> xyzz_dbl_c(const XYZZ<F>& p) { return xyzz_dbl(p); }
+template <class F> PS_NOINLINE XYZZ<F> xyzz_dbl_affine_c(const Affine<F>& p) { return xyzz_dbl_affine(p); }
+template <class F> PS_NOINLINE void xyzz_add_c(XYZZ<F>& acc, const XYZZ<F>& q) { xyzz_add(acc, q); }
+template <class F> PS_NOINLINE void xyzz_madd_c(XYZZ<F>& acc, const Affine<F>& q) { xyzz_madd(acc, q); }
+
+template <class F>
+PS_DEV Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
+  if (p.is_inf()) return Affine<F>::inf();
+  // one inversion gives both: ZZ^3 = ZZZ^2  =>  1/ZZ = (ZZ/ZZZ)^2
+  F zzz_inv = FieldInv<F>::inv(p.zzz);
+  F t = zzz_inv * p.zz;
+  F zz_inv = t.sqr();
+  return Affine<F>{p.x * zz_inv, p.y * zzz_inv};
+}
+
+// k * P by left-to-right double-and-add over `nbits` bits of a little-endian limb array.
+// Used for the handful of per-proof scalar multiplications (groth16.go:149,159,189-199) and as the
+// plain reference inside self-tests; k = 0 or P = inf give inf like the reference's bit-serial loop.
+template <class F>
+PS_DEV XYZZ<F> xyzz_scalar_mul(const XYZZ<F>& p, const uint32_t* k, int nlimbs) {
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int i = nlimbs - 1; i >= 0; i--) {
+    uint32_t w = k[i];
+#pragma unroll 1
+    for (int b = 31; b >= 0; b--) {
+      acc = xyzz_dbl_c(acc);
+      if ((w >> b) & 1) xyzz_add_c(acc, p);
+    }
+  }
+  return acc;
+}
+
+template <class F> PS_NOINLINE Affine<F> xyzz_to_affine_c(const XYZZ<F>& p) { return xyzz_to_affine(p); }
+
+using G1Affine = Affine<Fp>;
+using G2Affine = Affine<Fp2>;
+using G1XYZZ = XYZZ<Fp>;
+using G2XYZZ = XYZZ<Fp2>;
+
+}  // namespace ps

@@ -16,51 +16,80 @@
 
 namespace ps {
 
-#define PS_DEV __device__ __forceinline__
+#ifdef __CUDACC__
+#define PS_NOINLINE __host__ __device__ __noinline__
+#define PS_DEV __host__ __device__ __forceinline__
+#else
+#define PS_NOINLINE
+#define PS_DEV inline
+#endif
 
-// ---- PTX carry-chain primitives -------------------------------------------------------------
+// ---- carry-chain primitives -------------------------------------------------------------------
+// Device: PTX add.cc / madc.* (the carry lives in the hardware flag between asm statements).
+// Host (unit tests of the same templates, tests/host_check.cpp): a thread-local emulated flag.
+#ifdef __CUDA_ARCH__
 PS_DEV uint32_t ptx_add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 PS_DEV uint32_t ptx_addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 PS_DEV uint32_t ptx_addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 PS_DEV uint32_t ptx_sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 PS_DEV uint32_t ptx_subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 PS_DEV uint32_t ptx_subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// (hi:lo) = a*b + (hi:lo) [+ carry]; carry out in the flag.  Written as a lo/hi pair so that ptxas
+// fuses it into one IMAD.WIDE.U32(.X).
+PS_DEV void ptx_mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("mad.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b)); }
+PS_DEV void ptx_madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("madc.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b)); }
+PS_DEV void ptx_mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("mul.lo.u32 %0,%2,%3; mul.hi.u32 %1,%2,%3;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b)); }
+#else
+inline uint32_t& host_cc() { static thread_local uint32_t cc = 0; return cc; }
+inline uint32_t ptx_add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; host_cc() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t ptx_addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + host_cc(); host_cc() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t ptx_addc(uint32_t a, uint32_t b) { return a + b + host_cc(); }
+inline uint32_t ptx_sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; host_cc() = (uint32_t)(t >> 63); return (uint32_t)t; }
+inline uint32_t ptx_subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - host_cc(); host_cc() = (uint32_t)(t >> 63); return (uint32_t)t; }
+inline uint32_t ptx_subc(uint32_t a, uint32_t b) { return a - b - host_cc(); }
+inline void ptx_mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  unsigned __int128 t = (unsigned __int128)a * b + (((uint64_t)hi << 32) | lo);
+  lo = (uint32_t)t; hi = (uint32_t)(t >> 32); host_cc() = (uint32_t)(t >> 64); }
+inline void ptx_madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  unsigned __int128 t = (unsigned __int128)a * b + (((uint64_t)hi << 32) | lo) + host_cc();
+  lo = (uint32_t)t; hi = (uint32_t)(t >> 32); host_cc() = (uint32_t)(t >> 64); }
+inline void ptx_mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a * b; lo = (uint32_t)t; hi = (uint32_t)(t >> 32); }
+#endif
 
-// acc[0..N) = sum over k of a[2k] * b * 2^(64k)   (no carries: products are disjoint)
+// acc[0..N) = sum over k of a[2k] * b * 2^(64k)   (no carries: the products are disjoint)
 template <int N>
 PS_DEV void mul_chain(uint32_t* acc, const uint32_t* a, uint32_t b) {
 #pragma unroll
-  for (int j = 0; j < N; j += 2)
-    asm volatile("mul.lo.u32 %0,%2,%3; mul.hi.u32 %1,%2,%3;" : "=r"(acc[j]), "=r"(acc[j + 1]) : "r"(a[j]), "r"(b));
-}
-
-// acc[0..N) += sum over k of MOD[OFF+2k] * b * 2^(64k): the modulus limbs are immediates.
-template <class P, int OFF, bool CARRY_IN>
-PS_DEV void mad_chain_mod(uint32_t* acc, uint32_t b) {
-  constexpr int N = P::N;
-  if (CARRY_IN)
-    asm volatile("madc.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(P::MOD(OFF)), "r"(b));
-  else
-    asm volatile("mad.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(P::MOD(OFF)), "r"(b));
-#pragma unroll
-  for (int j = 2; j < N; j += 2)
-    asm volatile("madc.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(acc[j]), "+r"(acc[j + 1]) : "r"(P::MOD(OFF + j)), "r"(b));
+  for (int j = 0; j < N; j += 2) ptx_mul_wide(acc[j], acc[j + 1], a[j], b);
 }
 
 // acc[0..N) += sum over k of a[2k] * b * 2^(64k); CARRY_IN consumes the pending carry flag at
 // limb 0; the carry out of limb N-1 is left in the flag.
 template <int N, bool CARRY_IN>
 PS_DEV void mad_chain(uint32_t* acc, const uint32_t* a, uint32_t b) {
-  if (CARRY_IN)
-    asm volatile("madc.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(a[0]), "r"(b));
-  else
-    asm volatile("mad.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(a[0]), "r"(b));
+  if (CARRY_IN) ptx_madc_wide_cc(acc[0], acc[1], a[0], b);
+  else ptx_mad_wide_cc(acc[0], acc[1], a[0], b);
 #pragma unroll
-  for (int j = 2; j < N; j += 2)
-    asm volatile("madc.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(acc[j]), "+r"(acc[j + 1]) : "r"(a[j]), "r"(b));
+  for (int j = 2; j < N; j += 2) ptx_madc_wide_cc(acc[j], acc[j + 1], a[j], b);
+}
+
+// acc[0..N) += sum over k of MOD[OFF+2k] * b * 2^(64k): the modulus limbs become immediates.
+template <class P, int OFF>
+PS_DEV void mad_chain_mod(uint32_t* acc, uint32_t b) {
+  constexpr int N = P::N;
+  ptx_mad_wide_cc(acc[0], acc[1], P::MOD(OFF), b);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) ptx_madc_wide_cc(acc[j], acc[j + 1], P::MOD(OFF + j), b);
 }
 
 // ---- field element ----------------------------------------------------------------------------
+template <class P> struct Fe;
+template <class P> PS_NOINLINE Fe<P> fe_mul_call(const Fe<P>& a, const Fe<P>& b);
+
 template <class P>
 struct alignas(16) Fe {
   static constexpr int N = P::N;
@@ -75,10 +104,10 @@ struct alignas(16) Fe {
 #pragma unroll
     for (int i = 0; i < N; i++) r.v[i] = P::ONE(i);
     return r; }
-  template <class FN>
-  PS_DEV static Fe from_const(FN limb) { Fe r;
+  template <uint32_t (*LIMB)(int)>
+  PS_DEV static Fe from_const() { Fe r;
 #pragma unroll
-    for (int i = 0; i < N; i++) r.v[i] = limb(i);
+    for (int i = 0; i < N; i++) r.v[i] = LIMB(i);
     return r; }
 
   PS_DEV bool is_zero() const { uint32_t o = 0;
@@ -139,9 +168,9 @@ struct alignas(16) Fe {
       mul_chain<N>(X, a.v, bi);
       mul_chain<N>(Y, a.v + 1, bi);
       const uint32_t m = X[0] * P::INV;
-      mad_chain_mod<P, 0, false>(X, m);
+      mad_chain_mod<P, 0>(X, m);
       uint32_t cx = ptx_addc(0, 0);
-      mad_chain_mod<P, 1, false>(Y, m);
+      mad_chain_mod<P, 1>(Y, m);
       // shift right one limb: X[0] == 0 now.
       pend = X[1];
 #pragma unroll
@@ -160,9 +189,9 @@ struct alignas(16) Fe {
       mad_chain<N, false>(A, a.v, bi);               // even limbs
       uint32_t cx = ptx_addc(0, 0);
       const uint32_t m = A[0] * P::INV;
-      mad_chain_mod<P, 0, false>(A, m);
+      mad_chain_mod<P, 0>(A, m);
       cx = ptx_addc(cx, 0);
-      mad_chain_mod<P, 1, false>(S, m);
+      mad_chain_mod<P, 1>(S, m);
       pend = A[1];
 #pragma unroll
       for (int k = 0; k < N - 2; k++) A[k] = A[k + 2];
@@ -181,11 +210,11 @@ struct alignas(16) Fe {
   }
   PS_DEV Fe sqr() const { return (*this) * (*this); }
 
-  PS_DEV Fe to_mont() const { return (*this) * from_const([] __device__ (int i) { return P::R2(i); }); }
-  PS_DEV Fe from_mont() const { Fe o = zero(); o.v[0] = 1; return (*this) * o; }
+  PS_DEV Fe to_mont() const { return fe_mul_call(*this, from_const<P::R2>()); }
+  PS_DEV Fe from_mont() const { Fe o = zero(); o.v[0] = 1; return fe_mul_call(*this, o); }
 
   // this^e, e = nlimbs little-endian 32-bit limbs (readable at run time: constant or global memory)
-  __device__ __noinline__ Fe pow(const uint32_t* e, int nlimbs) const {
+  PS_NOINLINE Fe pow(const uint32_t* e, int nlimbs) const {
     Fe acc = one();
     bool started = false;
     for (int i = nlimbs - 1; i >= 0; i--) {
@@ -205,10 +234,27 @@ struct alignas(16) Fe {
 using Fp = Fe<FpParams>;
 using Fr = Fe<FrParams>;
 
+// Out-of-line product: one copy of the ~300-instruction multiplier per field instead of one per call
+// site.  Used wherever code size / compile time matters more than the call overhead (Fp2 towers,
+// cold paths); the hot G1 kernels use the inlined operator*.
+template <class P>
+PS_NOINLINE Fe<P> fe_mul_call(const Fe<P>& a, const Fe<P>& b) { return a * b; }
+
 }  // namespace ps
 
 namespace ps {
-PS_DEV Fp fp_inv(const Fp& a) { return a.pow(c_FP_MOD_M2, 12); }   // 0 -> 0
-PS_DEV Fr fr_inv(const Fr& a) { return a.pow(c_FR_MOD_M2, 8); }
-PS_DEV Fp fp_sqrt_candidate(const Fp& a) { return a.pow(c_FP_SQRT_EXP, 12); }  // p = 3 mod 4
+#ifdef __CUDA_ARCH__
+#define PS_CEXP(name) name
+#else
+// host copies of the constant-memory exponents
+#define PS_CEXP(name) host_##name()
+inline const uint32_t* host_c_FP_MOD_M2() { static uint32_t t[12]; for (int i = 0; i < 12; i++) t[i] = FpParams::MOD_M2(i); return t; }
+inline const uint32_t* host_c_FP_SQRT_EXP() { static uint32_t t[12]; for (int i = 0; i < 12; i++) t[i] = FpParams::SQRT_EXP(i); return t; }
+inline const uint32_t* host_c_FP_P_M3_D4() { static uint32_t t[12]; for (int i = 0; i < 12; i++) t[i] = FpParams::P_M3_D4(i); return t; }
+inline const uint32_t* host_c_FP_P_M1_D2() { static uint32_t t[12]; for (int i = 0; i < 12; i++) t[i] = FpParams::P_M1_D2(i); return t; }
+inline const uint32_t* host_c_FR_MOD_M2() { static uint32_t t[8]; for (int i = 0; i < 8; i++) t[i] = FrParams::MOD_M2(i); return t; }
+#endif
+PS_DEV Fp fp_inv(const Fp& a) { return a.pow(PS_CEXP(c_FP_MOD_M2), 12); }   // 0 -> 0
+PS_DEV Fr fr_inv(const Fr& a) { return a.pow(PS_CEXP(c_FR_MOD_M2), 8); }
+PS_DEV Fp fp_sqrt_candidate(const Fp& a) { return a.pow(PS_CEXP(c_FP_SQRT_EXP), 12); }  // p = 3 mod 4
 }  // namespace ps

@@ -1,0 +1,462 @@
+// Pippenger multi-scalar multiplication for G1 and G2 (sm_100a).
+//
+// Computes what the reference obtains with one scalar multiplication per term:
+//   Poly.BlindEval  (algebra.go:348-359)   acc += p[i] * blindedPoint[i]
+//   sumBlind        (groth16.go:134-141)   and computeSolCommit (pinochio.go:222-229)
+// i.e. the group element  sum_i k_i * P_i ; the affine result is identical whatever the schedule.
+//
+// Pipeline (all on the device, one stream):
+//   1. MsmCountK      signed-digit window decomposition of every scalar (k -> r-k with the point
+//                     negated when k > r/2, so small negative witnesses stay short); per-bucket
+//                     histogram with the atomic's return value kept as the rank inside the bucket
+//   2. exclusive scan bucket offsets
+//   3. MsmScatterK    counting-sort of (point index | sign) by bucket
+//   4. MsmAccumK      bucket accumulation: every thread owns L consecutive sorted entries (perfect
+//                     balance whatever the scalar distribution), adds the gathered affine bases into
+//                     an XYZZ accumulator (madd, 8M+2S), writes buckets that lie wholly inside its
+//                     range and emits at most two boundary partials
+//   5. MsmCombineK    log-depth merge of the boundary partials (XYZZ + XYZZ)
+//   6. MsmReduceFirstK / MsmReduceK   sum_d d * B_d per bucket set as a tree of (acc, run) pairs
+//   7. MsmFinalK      Horner over the bucket sets (c*T doublings between sets)
+// With T precomputed tables (2^(c t) * P_i, t < T) the windows w = s*T + t share bucket set s.
+#pragma once
+#include "context.cuh"
+#include "curve.cuh"
+
+namespace ps {
+
+struct MsmGeom {
+  uint32_t n;      // scalars / points in this call
+  uint32_t nbase;  // points per table (table stride)
+  uint32_t first;  // first point of the range inside each table
+  int c;           // window bits
+  int W;           // windows = ceil(255 / c)
+  int T;           // precomputed tables
+  int S;           // bucket sets = ceil(W / T)
+  uint32_t D;      // buckets per set = 2^(c-1)
+};
+
+// Loads scalar i (8 LE limbs), optionally leaves Montgomery form, folds k > (r-1)/2 to r-k.
+PS_DEV void msm_load_scalar(const uint32_t* scalars, uint32_t i, int mont, uint32_t k[8], bool& neg) {
+  Fr x;
+#pragma unroll
+  for (int j = 0; j < 8; j++) x.v[j] = scalars[(size_t)i * 8 + j];
+  if (mont) x = x.from_mont();
+  // borrow of HALF - k  <=>  k > HALF
+  uint32_t t = ptx_sub_cc(FrParams::HALF(0), x.v[0]);
+#pragma unroll
+  for (int j = 1; j < 8; j++) t = ptx_subc_cc(FrParams::HALF(j), x.v[j]);
+  uint32_t borrow = ptx_subc(0, 0);
+  neg = borrow != 0;
+  if (neg) {
+    uint32_t m[8];
+    m[0] = ptx_sub_cc(FrParams::MOD(0), x.v[0]);
+#pragma unroll
+    for (int j = 1; j < 8; j++) m[j] = ptx_subc_cc(FrParams::MOD(j), x.v[j]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) x.v[j] = m[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) k[j] = x.v[j];
+}
+
+// returns the low c bits and shifts the 256-bit value right by c (1 <= c <= 31)
+PS_DEV uint32_t msm_take_bits(uint32_t k[8], int c) {
+  uint32_t v = k[0] & ((1u << c) - 1);
+#pragma unroll
+  for (int j = 0; j < 7; j++) k[j] = (k[j] >> c) | (k[j + 1] << (32 - c));
+  k[7] >>= c;
+  return v;
+}
+
+// Signed digit of window w: d in [-2^(c-1)+1, 2^(c-1)]; returns bucket (|d|-1) and sign, or false for 0.
+PS_DEV bool msm_next_digit(uint32_t k[8], int c, uint32_t& carry, uint32_t& mag, bool& dneg) {
+  uint32_t v = msm_take_bits(k, c) + carry;
+  uint32_t half = 1u << (c - 1);
+  if (v > half) { mag = (1u << c) - v; dneg = true; carry = 1; }
+  else { mag = v; dneg = false; carry = 0; }
+  return mag != 0;
+}
+
+struct MsmCountK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, MsmGeom g, const uint32_t* scalars, int mont, uint32_t* count, uint32_t* ranks) {
+    uint32_t k[8]; bool neg;
+    msm_load_scalar(scalars, i, mont, k, neg);
+    uint32_t carry = 0;
+    for (int w = 0; w < g.W; w++) {
+      uint32_t mag; bool dneg;
+      uint32_t rank = 0xFFFFFFFFu;
+      if (msm_next_digit(k, g.c, carry, mag, dneg)) {
+        uint32_t b = (uint32_t)(w / g.T) * g.D + (mag - 1);
+        rank = ps_atomic_add(count + b, 1u);
+      }
+      ranks[(size_t)w * g.n + i] = rank;
+    }
+  }
+};
+
+struct MsmScatterK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, MsmGeom g, const uint32_t* scalars, int mont, const uint32_t* off,
+                         const uint32_t* ranks, uint32_t* ent) {
+    uint32_t k[8]; bool neg;
+    msm_load_scalar(scalars, i, mont, k, neg);
+    uint32_t carry = 0;
+    for (int w = 0; w < g.W; w++) {
+      uint32_t mag; bool dneg;
+      if (msm_next_digit(k, g.c, carry, mag, dneg)) {
+        uint32_t b = (uint32_t)(w / g.T) * g.D + (mag - 1);
+        uint32_t pos = off[b] + ranks[(size_t)w * g.n + i];
+        uint32_t idx = (uint32_t)(w % g.T) * g.nbase + g.first + i;
+        ent[pos] = idx | ((neg != dneg) ? 0x80000000u : 0u);
+      }
+    }
+  }
+};
+
+// last index b in [0, nb) with off[b] <= pos  (off is non-decreasing, off[0] = 0, pos < off[nb])
+PS_DEV uint32_t msm_find_bucket(const uint32_t* off, uint32_t nb, uint32_t pos) {
+  uint32_t lo = 0, hi = nb;  // invariant: off[lo] <= pos < off[hi]
+  while (hi - lo > 1) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    if (off[mid] <= pos) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <class F>
+PS_DEV Affine<F> msm_load_point(const Affine<F>* tab, uint32_t e) {
+  Affine<F> p = tab[e & 0x7FFFFFFFu];
+  if (e >> 31) p.y = p.y.neg();
+  return p;
+}
+
+// slot flags: bit0 = the bucket has partials to the left, bit1 = to the right
+template <class F>
+struct MsmAccumK {
+  static constexpr int BLOCK = 128;
+  PS_DEV static void run(uint32_t tid, uint32_t nb, uint32_t L, const Affine<F>* tab, const uint32_t* ent,
+                         const uint32_t* off, XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid,
+                         uint8_t* slot_fl) {
+    const uint32_t M = off[nb];
+    const uint32_t head = 2 * tid, tail = 2 * tid + 1;
+    slot_bid[head] = -1; slot_bid[tail] = -1;
+    uint64_t p0 = (uint64_t)tid * L;
+    if (p0 >= M) return;
+    uint32_t cur = (uint32_t)p0;
+    uint32_t end = (M - cur > L) ? cur + L : M;
+    uint32_t b = msm_find_bucket(off, nb, cur);
+    bool head_open = off[b] < cur;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (;;) {
+      uint32_t bend = off[b + 1];
+      uint32_t lim = bend < end ? bend : end;
+      for (; cur < lim; cur++) xyzz_madd(acc, msm_load_point(tab, ent[cur]));
+      bool closed = bend <= end;
+      if (closed && !head_open) {
+        buckets[b] = acc;
+      } else {
+        uint32_t s = head_open ? head : tail;
+        slot_pt[s] = acc;
+        slot_bid[s] = (int32_t)b;
+        slot_fl[s] = (uint8_t)((head_open ? 1 : 0) | (closed ? 0 : 2));
+      }
+      if (cur >= end) break;
+      acc = XYZZ<F>::inf();
+      head_open = false;
+      b++;
+      while (off[b + 1] <= cur) b++;
+    }
+  }
+};
+
+template <class F>
+struct MsmCombineK {
+  static constexpr int BLOCK = 128;
+  PS_DEV static void flush(int32_t bid, const XYZZ<F>& acc, bool cl, bool cr, int final_pass, uint32_t tid,
+                           XYZZ<F>* buckets, XYZZ<F>* out_pt, int32_t* out_bid, uint8_t* out_fl) {
+    if (bid < 0) return;
+    if (final_pass || (!cl && !cr)) { buckets[bid] = acc; return; }
+    uint32_t s = cl ? 2 * tid : 2 * tid + 1;
+    out_pt[s] = acc; out_bid[s] = bid; out_fl[s] = (uint8_t)((cl ? 1 : 0) | (cr ? 2 : 0));
+  }
+  PS_DEV static void run(uint32_t tid, uint32_t n_in, uint32_t f, const XYZZ<F>* in_pt, const int32_t* in_bid,
+                         const uint8_t* in_fl, XYZZ<F>* buckets, XYZZ<F>* out_pt, int32_t* out_bid,
+                         uint8_t* out_fl, int final_pass) {
+    out_bid[2 * tid] = -1; out_bid[2 * tid + 1] = -1;
+    int32_t cur = -1; bool cl = false, cr = false;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t i = 0; i < f; i++) {
+      uint64_t j = (uint64_t)tid * f + i;
+      if (j >= n_in) break;
+      int32_t bid = in_bid[j];
+      if (bid < 0) continue;
+      uint8_t fl = in_fl[j];
+      if (bid != cur) {
+        flush(cur, acc, cl, cr, final_pass, tid, buckets, out_pt, out_bid, out_fl);
+        cur = bid; acc = in_pt[j]; cl = fl & 1; cr = (fl & 2) != 0;
+      } else {
+        xyzz_add_c(acc, in_pt[j]); cr = (fl & 2) != 0;
+      }
+    }
+    flush(cur, acc, cl, cr, final_pass, tid, buckets, out_pt, out_bid, out_fl);
+  }
+};
+
+// First level of sum_{d=1..D} d * B_d : thread (s, j) covers buckets [j*g, (j+1)*g) of set s and
+// emits acc = sum_{i<g} (i+1) * B_{jg+i}, run = sum_i B_{jg+i}.
+template <class F>
+struct MsmReduceFirstK {
+  static constexpr int BLOCK = 128;
+  PS_DEV static void run(uint32_t tid, uint32_t D, uint32_t G, uint32_t g, const XYZZ<F>* buckets, XYZZ<F>* acc_out,
+                         XYZZ<F>* run_out) {
+    uint32_t s = tid / G, j = tid % G;
+    const XYZZ<F>* B = buckets + (size_t)s * D + (size_t)j * g;
+    XYZZ<F> rr = XYZZ<F>::inf(), ww = XYZZ<F>::inf();
+    for (uint32_t i = g; i-- > 0;) {
+      xyzz_add_c(rr, B[i]);
+      xyzz_add_c(ww, rr);
+    }
+    acc_out[tid] = ww; run_out[tid] = rr;
+  }
+};
+
+// Next levels: thread (s, j) merges f consecutive (acc, run) elements, each spanning 2^log_len
+// buckets:  acc = sum_i acc_i + 2^log_len * sum_i i * run_i ,  run = sum_i run_i.
+template <class F>
+struct MsmReduceK {
+  static constexpr int BLOCK = 64;
+  PS_DEV static void run(uint32_t tid, uint32_t n_in, uint32_t n_out, uint32_t f, int log_len, const XYZZ<F>* acc_in,
+                         const XYZZ<F>* run_in, XYZZ<F>* acc_out, XYZZ<F>* run_out) {
+    uint32_t s = tid / n_out, j = tid % n_out;
+    const XYZZ<F>* A = acc_in + (size_t)s * n_in + (size_t)j * f;
+    const XYZZ<F>* R = run_in + (size_t)s * n_in + (size_t)j * f;
+    XYZZ<F> asum = XYZZ<F>::inf(), rr = XYZZ<F>::inf(), ww = XYZZ<F>::inf();
+    for (uint32_t i = f; i-- > 0;) {
+      if ((size_t)j * f + i >= n_in) continue;
+      xyzz_add_c(asum, A[i]);
+      xyzz_add_c(rr, R[i]);
+      if (i > 0) xyzz_add_c(ww, rr);
+    }
+    for (int d = 0; d < log_len; d++) ww = xyzz_dbl_c(ww);
+    xyzz_add_c(asum, ww);
+    acc_out[tid] = asum; run_out[tid] = rr;
+  }
+};
+
+// Horner over the bucket sets: R = sum_s 2^(shift*s) * set[s]; optionally adds into *out.
+template <class F>
+struct MsmFinalK {
+  static constexpr int BLOCK = 32;
+  PS_DEV static void run(uint32_t tid, int S, int shift, const XYZZ<F>* sets, XYZZ<F>* out) {
+    if (tid != 0) return;
+    XYZZ<F> r = XYZZ<F>::inf();
+    for (int s = S - 1; s >= 0; s--) {
+      for (int d = 0; d < shift; d++) r = xyzz_dbl_c(r);
+      xyzz_add_c(r, sets[s]);
+    }
+    *out = r;
+  }
+};
+
+// sums `count` XYZZ points (multi-GPU partials) into out
+template <class F>
+struct MsmSumK {
+  static constexpr int BLOCK = 32;
+  PS_DEV static void run(uint32_t tid, uint32_t count, const XYZZ<F>* in, XYZZ<F>* out) {
+    if (tid != 0) return;
+    XYZZ<F> r = XYZZ<F>::inf();
+    for (uint32_t i = 0; i < count; i++) xyzz_add_c(r, in[i]);
+    *out = r;
+  }
+};
+
+// ---- exclusive scan of uint32 counters --------------------------------------------------------------
+#if PS_GPU
+static constexpr int SCAN_THREADS = 256;
+static constexpr int SCAN_ITEMS = 8;
+static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* in, uint32_t* out, uint32_t* tile_sums, uint32_t n) {
+  __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t local = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = (base + i < n) ? in[base + i] : 0; local += v[i]; }
+  uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t ws = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ws, d); if (lane >= d) ws += t; }
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = ws;
+  }
+  __syncthreads();
+  uint32_t excl = inc - local + (wid ? warp_sums[wid - 1] : 0);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) out[base + i] = excl; excl += v[i]; }
+  if (threadIdx.x == SCAN_THREADS - 1) tile_sums[blockIdx.x] = warp_sums[SCAN_THREADS / 32 - 1];
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* sums, uint32_t n) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < n; base += 1024) {
+    uint32_t idx = base + threadIdx.x;
+    uint32_t v = idx < n ? sums[idx] : 0;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t ws = warp_sums[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ws, d); if (lane >= d) ws += t; }
+      warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    uint32_t carry = carry_s;
+    uint32_t excl = carry + inc - v + (wid ? warp_sums[wid - 1] : 0);
+    if (idx < n) sums[idx] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* out, const uint32_t* tile_sums, uint32_t n) {
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t add = tile_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < n) out[base + i] += add;
+}
+#endif
+
+// out[i] = sum_{j<i} in[i], i < n (in and out may not alias); tile_sums: scratch of ceil(n/2048)+1
+inline int exclusive_scan_u32(ps_stream_t st, const uint32_t* in, uint32_t* out, uint32_t* tile_sums, uint32_t n) {
+#if PS_GPU
+  uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  k_scan_tiles<<<tiles, SCAN_THREADS, 0, st>>>(in, out, tile_sums, n);
+  k_scan_sums<<<1, 1024, 0, st>>>(tile_sums, tiles);
+  k_scan_add<<<tiles, SCAN_THREADS, 0, st>>>(out, tile_sums, n);
+  PS_CUDA_TRY(cudaGetLastError());
+  launch_counter() += 3;
+#else
+  (void)st; (void)tile_sums;
+  uint32_t acc = 0;
+  for (uint32_t i = 0; i < n; i++) { uint32_t v = in[i]; out[i] = acc; acc += v; }
+#endif
+  return PS_OK;
+}
+
+// ---- planning ------------------------------------------------------------------------------------------
+inline int msm_windows(int c) { return (255 + c - 1) / c; }
+
+// cost model (field multiplications) used to pick c when the bases carry no precomputed tables
+inline int msm_pick_window(size_t n) {
+  int best = 4; double best_cost = 1e300;
+  for (int c = 4; c <= 22; c++) {
+    double W = msm_windows(c);
+    double buckets = W * (double)(1u << (c - 1));
+    double cost = (double)n * W * 10.0 + buckets * (2.0 * 14.0 + 10.0);
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
+// Runs the pipeline; result (XYZZ) written to d_out (device).  `tab` holds g.T tables of g.nbase points.
+template <class F>
+int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scalars, int mont, XYZZ<F>* d_out) {
+  ps_stream_t st = ctx->stream;
+  Arena& ar = ctx->arena;
+  if (g.n == 0) return dev_memset(d_out, 0, sizeof(XYZZ<F>), st);
+  const uint32_t nb = (uint32_t)g.S * g.D;
+  const size_t max_ent = (size_t)g.n * g.W;
+  if (max_ent >= 0xFFFFFFFFull) return PS_ERR_UNSUPPORTED;
+
+  // entries per accumulate thread: keep >= ~8 waves of threads when the problem is large enough
+  uint32_t L = 32;
+  while (L > 2 && max_ent / L < (size_t)ctx->sm_count * 1024) L >>= 1;
+  const size_t T1 = (max_ent + L - 1) / L;
+  const uint32_t CF = 16;  // slots merged per combine thread
+
+  uint32_t* count = ar.take<uint32_t>((size_t)nb + 1);
+  uint32_t* off = ar.take<uint32_t>((size_t)nb + 1);
+  uint32_t* tile_sums = ar.take<uint32_t>((size_t)nb / 2048 + 2);
+  uint32_t* ranks = ar.take<uint32_t>(max_ent);
+  uint32_t* ent = ar.take<uint32_t>(max_ent);
+  XYZZ<F>* buckets = ar.take<XYZZ<F>>(nb);
+  size_t slots_a = 2 * T1, slots_b = 2 * ((slots_a + CF - 1) / CF);
+  XYZZ<F>* sp[2] = {ar.take<XYZZ<F>>(slots_a), ar.take<XYZZ<F>>(slots_b)};
+  int32_t* sb[2] = {ar.take<int32_t>(slots_a), ar.take<int32_t>(slots_b)};
+  uint8_t* sf[2] = {ar.take<uint8_t>(slots_a), ar.take<uint8_t>(slots_b)};
+  if (!count || !off || !tile_sums || !ranks || !ent || !buckets || !sp[0] || !sp[1] || !sb[0] || !sb[1] || !sf[0] || !sf[1])
+    return PS_ERR_ALLOC;
+
+  ctx->ev_valid = false;
+  PS_TRY(ctx_event(ctx, 0));
+  PS_TRY(dev_memset(count, 0, ((size_t)nb + 1) * 4, st));
+  PS_TRY(dev_memset(buckets, 0, (size_t)nb * sizeof(XYZZ<F>), st));
+  PS_LAUNCH(MsmCountK, st, g.n, g, d_scalars, mont, count, ranks);
+  PS_TRY(exclusive_scan_u32(st, count, off, tile_sums, nb + 1));
+  PS_LAUNCH(MsmScatterK, st, g.n, g, d_scalars, mont, (const uint32_t*)off, (const uint32_t*)ranks, ent);
+  PS_TRY(ctx_event(ctx, 1));
+  PS_LAUNCH(MsmAccumK<F>, st, T1, nb, L, tab, (const uint32_t*)ent, (const uint32_t*)off, buckets, sp[0], sb[0], sf[0]);
+  {
+    size_t n_in = slots_a;
+    int cur = 0;
+    for (;;) {
+      size_t threads = (n_in + CF - 1) / CF;
+      int final_pass = threads == 1;
+      PS_LAUNCH(MsmCombineK<F>, st, threads, (uint32_t)n_in, CF, (const XYZZ<F>*)sp[cur], (const int32_t*)sb[cur],
+                (const uint8_t*)sf[cur], buckets, sp[cur ^ 1], sb[cur ^ 1], sf[cur ^ 1], final_pass);
+      if (final_pass) break;
+      n_in = 2 * threads;
+      cur ^= 1;
+    }
+  }
+  PS_TRY(ctx_event(ctx, 2));
+  // bucket reduction
+  {
+    // first level: aim at >= 64K threads, group size a power of two
+    uint32_t gsz = 1;
+    while ((uint64_t)g.S * (g.D / gsz) > 131072 && gsz < g.D) gsz <<= 1;
+    if (gsz < 2 && g.D >= 2) gsz = 2;
+    if (gsz > g.D) gsz = g.D;
+    uint32_t G = g.D / gsz;
+    size_t e0 = (size_t)g.S * G;
+    XYZZ<F>* accv[2] = {ar.take<XYZZ<F>>(e0), ar.take<XYZZ<F>>(e0 / 2 + g.S)};
+    XYZZ<F>* runv[2] = {ar.take<XYZZ<F>>(e0), ar.take<XYZZ<F>>(e0 / 2 + g.S)};
+    if (!accv[0] || !accv[1] || !runv[0] || !runv[1]) return PS_ERR_ALLOC;
+    PS_LAUNCH(MsmReduceFirstK<F>, st, e0, g.D, G, gsz, (const XYZZ<F>*)buckets, accv[0], runv[0]);
+    uint32_t n_in = G;
+    int log_len = 0;
+    while ((1u << log_len) < gsz) log_len++;
+    int cur = 0;
+    while (n_in > 1) {
+      uint32_t f = n_in < 16 ? n_in : 16;
+      uint32_t n_out = n_in / f;  // both powers of two
+      PS_LAUNCH(MsmReduceK<F>, st, (size_t)g.S * n_out, n_in, n_out, f, log_len, (const XYZZ<F>*)accv[cur],
+                (const XYZZ<F>*)runv[cur], accv[cur ^ 1], runv[cur ^ 1]);
+      int lf = 0;
+      while ((1u << lf) < f) lf++;
+      log_len += lf;
+      n_in = n_out;
+      cur ^= 1;
+    }
+    PS_LAUNCH(MsmFinalK<F>, st, 1, g.S, g.c * g.T, (const XYZZ<F>*)accv[cur], d_out);
+  }
+  PS_TRY(ctx_event(ctx, 3));
+  ctx->ev_valid = true;
+  return PS_OK;
+}
+
+}  // namespace ps

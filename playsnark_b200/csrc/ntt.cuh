@@ -1,0 +1,175 @@
+// Radix-2 number-theoretic transforms over Fr and the element-wise polynomial kernels around them.
+//
+// They replace the reference's schoolbook Poly.Mul (algebra.go:92-105) and long division Poly.Div2
+// (algebra.go:140-159) inside QAP.Quotient (qap.go:151-162); see poly.cuh for how.
+// Forward transforms are decimation-in-frequency (natural order in, bit-reversed out), inverse
+// transforms decimation-in-time (bit-reversed in, natural out), so no permutation pass is needed
+// between them; each launch fuses R <= 3 butterfly stages in registers (2^R elements per thread).
+// omega_n = 7^((r-1)/n); Fr has 2-adicity 32.
+#pragma once
+#include "backend.cuh"
+
+namespace ps {
+
+PS_DEV Fr fr_load(const Fr* p) { return *p; }
+
+// out[i] = scale * base^i   (square-and-multiply per element; tables are built once per size)
+struct FrPowTableK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, Fr base, Fr scale, Fr* out) {
+    Fr acc = scale, b = base;
+    uint32_t e = i;
+    while (e) {
+      if (e & 1) acc = acc * b;
+      b = b * b;
+      e >>= 1;
+    }
+    out[i] = acc;
+  }
+};
+
+// a[i] *= t[i]
+struct FrMulTableK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, Fr* a, const Fr* t) { a[i] = a[i] * t[i]; }
+};
+
+template <int R>
+struct NttDifK {
+  static constexpr int BLOCK = 256;
+  // one launch = R stages on sub-transforms of size B (B >= 2^R); n/2^R threads
+  PS_DEV static void run(uint32_t tid, Fr* a, uint32_t n, uint32_t B, const Fr* tw) {
+    const uint32_t q = B >> R;
+    const uint32_t blk = tid / q, j = tid % q;
+    Fr* base = a + (size_t)blk * B + j;
+    Fr x[1 << R];
+#pragma unroll
+    for (int k = 0; k < (1 << R); k++) x[k] = base[(size_t)k * q];
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+      const int hl = 1 << (R - 1 - t);           // half size in units of k
+      const uint32_t tw_mul = (n / B) << t;      // n / (2*half_t)
+#pragma unroll
+      for (int grp = 0; grp < (1 << t); grp++) {
+#pragma unroll
+        for (int i = 0; i < hl; i++) {
+          const int k = grp * 2 * hl + i, k2 = k + hl;
+          uint32_t p = j + (uint32_t)i * q;
+          Fr u = x[k], v = x[k2];
+          x[k] = u + v;
+          x[k2] = (u - v) * tw[(size_t)p * tw_mul];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < (1 << R); k++) base[(size_t)k * q] = x[k];
+  }
+};
+
+template <int R>
+struct NttDitK {
+  static constexpr int BLOCK = 256;
+  // one launch = R stages that grow finished sub-transforms of size B0 to B0 * 2^R
+  PS_DEV static void run(uint32_t tid, Fr* a, uint32_t n, uint32_t B0, const Fr* tw_inv) {
+    const uint32_t blk = tid / B0, j = tid % B0;
+    Fr* base = a + ((size_t)blk * B0 << R) + j;
+    Fr x[1 << R];
+#pragma unroll
+    for (int k = 0; k < (1 << R); k++) x[k] = base[(size_t)k * B0];
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+      const int hl = 1 << t;
+      const uint32_t tw_mul = n / ((2 * B0) << t);  // n / (2*half_t)
+#pragma unroll
+      for (int grp = 0; grp < (1 << (R - 1 - t)); grp++) {
+#pragma unroll
+        for (int i = 0; i < hl; i++) {
+          const int k = grp * 2 * hl + i, k2 = k + hl;
+          uint32_t p = j + (uint32_t)i * B0;
+          Fr u = x[k], v = x[k2] * tw_inv[(size_t)p * tw_mul];
+          x[k] = u + v;
+          x[k2] = u - v;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < (1 << R); k++) base[(size_t)k * B0] = x[k];
+  }
+};
+
+struct BitRevK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, const Fr* in, Fr* out, int log_n) {
+    uint32_t r = 0, v = i;
+    for (int b = 0; b < log_n; b++) { r = (r << 1) | (v & 1); v >>= 1; }
+    out[r] = in[i];
+  }
+};
+
+inline Fr fr_host_from_u64(uint64_t v) {
+  Fr x = Fr::zero();
+  x.v[0] = (uint32_t)v; x.v[1] = (uint32_t)(v >> 32);
+  return x.to_mont();
+}
+inline Fr fr_host_pow(Fr b, uint64_t e) {
+  Fr acc = Fr::one();
+  while (e) { if (e & 1) acc = acc * b; b = b * b; e >>= 1; }
+  return acc;
+}
+// primitive 2^log_n-th root of unity (Montgomery form), computed on the host from the 2^32-th root
+inline Fr fr_root_of_unity(int log_n) {
+  Fr w = Fr::from_const<FrParams::ROOT_2_32>();
+  for (int i = log_n; i < 32; i++) w = w * w;
+  return w;
+}
+
+// forward DIF on n = 2^log_n elements (natural -> bit-reversed); tw[i] = omega_n^i, i < n/2
+inline int ntt_forward(ps_stream_t st, Fr* a, int log_n, const Fr* tw) {
+  uint32_t n = 1u << log_n;
+  int done = 0;
+  while (done < log_n) {
+    int r = log_n - done >= 3 ? 3 : log_n - done;
+    uint32_t B = n >> done;
+    if (r == 3) PS_LAUNCH(NttDifK<3>, st, n >> 3, a, n, B, tw);
+    else if (r == 2) PS_LAUNCH(NttDifK<2>, st, n >> 2, a, n, B, tw);
+    else PS_LAUNCH(NttDifK<1>, st, n >> 1, a, n, B, tw);
+    done += r;
+  }
+  return PS_OK;
+}
+// inverse DIT (bit-reversed -> natural), WITHOUT the 1/n factor; tw_inv[i] = omega_n^-i
+inline int ntt_inverse_unscaled(ps_stream_t st, Fr* a, int log_n, const Fr* tw_inv) {
+  uint32_t n = 1u << log_n;
+  int done = 0;
+  while (done < log_n) {
+    int r = log_n - done >= 3 ? 3 : log_n - done;
+    uint32_t B0 = 1u << done;
+    if (r == 3) PS_LAUNCH(NttDitK<3>, st, n >> 3, a, n, B0, tw_inv);
+    else if (r == 2) PS_LAUNCH(NttDitK<2>, st, n >> 2, a, n, B0, tw_inv);
+    else PS_LAUNCH(NttDitK<1>, st, n >> 1, a, n, B0, tw_inv);
+    done += r;
+  }
+  return PS_OK;
+}
+
+// Twiddle tables for one transform size, resident on the device.
+struct NttTables {
+  int log_n = -1;
+  Fr* tw = nullptr;      // omega^i, i < max(n/2, 1)
+  Fr* tw_inv = nullptr;  // omega^-i
+  void release() { dev_free(tw); dev_free(tw_inv); tw = tw_inv = nullptr; log_n = -1; }
+};
+inline int ntt_tables_build(ps_stream_t st, int log_n, NttTables* t) {
+  if (log_n < 0 || log_n > 30) return PS_ERR_ARG;
+  t->log_n = log_n;
+  size_t half = log_n ? (size_t)1 << (log_n - 1) : 1;
+  PS_TRY(dev_alloc((void**)&t->tw, half * sizeof(Fr)));
+  PS_TRY(dev_alloc((void**)&t->tw_inv, half * sizeof(Fr)));
+  Fr w = fr_root_of_unity(log_n);
+  Fr wi = fr_host_pow(w, ((uint64_t)1 << log_n) - 1);  // w^-1 = w^(n-1)
+  PS_LAUNCH(FrPowTableK, st, half, w, Fr::one(), t->tw);
+  PS_LAUNCH(FrPowTableK, st, half, wi, Fr::one(), t->tw_inv);
+  return PS_OK;
+}
+
+}  // namespace ps

@@ -1,0 +1,262 @@
+"""Parity cases shared by the host-emulation suite (CPU, small sizes) and the GPU suite (through the
+product C ABI, larger sizes).  Each takes a playsnark_b200.Backend and compares with the oracle."""
+from __future__ import annotations
+
+import json
+import os
+import random
+
+from oracle import ps_oracle as O
+from playsnark_b200 import _lib as L, api
+from tests import helpers as H
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gold(name):
+    with open(os.path.join(GOLD, name + ".json")) as f:
+        return json.load(f)
+
+
+def _grp(group):
+    if group == L.PS_G1:
+        return O.F1, O.G1_GEN, O.g1_compress, O.g1_decompress
+    return O.F2, O.G2_GEN, O.g2_compress, O.g2_decompress
+
+
+def scalars_of(kind, n, rng):
+    if kind == "rand":
+        return [rng.randrange(O.R) for _ in range(n)]
+    if kind == "ones":
+        return [1] * n
+    if kind == "neg":          # Value(-1).ToFieldElement() = r-1 (curve.go:17-19)
+        return [O.R - 1] * n
+    if kind == "small":        # witness-like: small signed ints
+        return [rng.randrange(-40, 41) % O.R for _ in range(n)]
+    if kind == "zero":
+        return [0] * n
+    if kind == "edge":
+        base = [0, 1, 2, O.R - 1, O.R - 2, (O.R - 1) // 2, (O.R + 1) // 2, 1 << 254, (1 << 128) - 1]
+        return [base[i % len(base)] for i in range(n)]
+    raise ValueError(kind)
+
+
+def msm_exponent_check(be, group, n, kind="rand", window_bits=0, tables=1, seed=0):
+    """bases k_i*G built on the device; the MSM must equal (sum k_i s_i)*G (exponent-level check in
+    the style of groth16_test.go:32-107 -- needs one scalar-mul, so it scales to any n)."""
+    F, gen, comp, _ = _grp(group)
+    rng = random.Random((seed << 8) ^ n ^ (group << 30))
+    ks = [rng.randrange(1, O.R) for _ in range(n)]
+    sc = scalars_of(kind, n, rng)
+    bases = be.bases_from_scalars(group, ks, window_bits, tables)
+    got = be.msm(bases, sc)
+    want = comp(O.pt_mul(F, sum(k * s for k, s in zip(ks, sc)) % O.R, gen))
+    assert got == want, (group, n, kind, window_bits, tables)
+    bases.close()
+
+
+def msm_vs_naive(be, group, n, seed=1):
+    """against the reference's own algorithm (BlindEval: one scalar-mul per term)."""
+    F, gen, comp, _ = _grp(group)
+    rng = random.Random(seed)
+    pts = [O.pt_mul(F, rng.randrange(1, O.R), gen) for _ in range(n)]
+    sc = [rng.randrange(O.R) for _ in range(n)]
+    bases = be.load_bases(group, [comp(p) for p in pts])
+    assert be.msm(bases, sc) == comp(O.msm_naive(F, sc, pts))
+
+
+def msm_golden(be):
+    g = gold("msm")
+    for name, group in (("g1", L.PS_G1), ("g2", L.PS_G2)):
+        v = g[name]
+        bases = be.load_bases(group, [bytes.fromhex(p) for p in v["points"]])
+        assert be.msm(bases, [int(s, 16) for s in v["scalars"]]).hex() == v["result"]
+        # the same bases through the uncompressed format
+        aff = bases.export(fmt=L.PS_FMT_AFFINE)
+        b2 = be.load_bases(group, aff, fmt=L.PS_FMT_AFFINE)
+        assert b2.export() == [bytes.fromhex(p) for p in v["points"]]
+        assert be.msm(b2, [int(s, 16) for s in v["scalars"]]).hex() == v["result"]
+
+
+def msm_errors(be):
+    import pytest
+    bases = be.bases_from_scalars(L.PS_G1, [1, 2, 3])
+    with pytest.raises(ValueError):      # BlindEval length panic, algebra.go:350-352
+        be.msm(bases, [1, 2])
+    with pytest.raises(api.L.PlaysnarkError) as e:   # non-canonical scalar
+        be.msm(bases, b"\xff" * 96)
+    assert e.value.status == L.PS_ERR_ENCODING
+    with pytest.raises(api.L.PlaysnarkError) as e:   # x not on the curve
+        be.load_bases(L.PS_G1, [bytes([0x80]) + bytes(46) + b"\x01"])
+    assert e.value.status == L.PS_ERR_ENCODING
+    # empty MSM = identity
+    empty = be.load_bases(L.PS_G1, b"")
+    assert be.msm(empty, []) == O.g1_compress(None)
+
+
+def codec_roundtrip(be, n=24):
+    rng = random.Random(3)
+    for group in (L.PS_G1, L.PS_G2):
+        F, gen, comp, _ = _grp(group)
+        pts = [O.pt_mul(F, rng.randrange(1, O.R), gen) for _ in range(n)] + [None]
+        enc = [comp(p) for p in pts]
+        b = be.load_bases(group, enc)
+        assert b.export() == enc
+        affb = O.g1_affine_bytes if group == L.PS_G1 else O.g2_affine_bytes
+        assert b.export(fmt=L.PS_FMT_AFFINE) == [affb(p) for p in pts]
+    c = gold("constants")
+    g = be.bases_from_scalars(L.PS_G1, [1, 2, 0])
+    assert [x.hex() for x in g.export()] == [c["g1_generator_compressed"], c["g1_two_g"], c["g1_infinity_compressed"]]
+    g = be.bases_from_scalars(L.PS_G2, [1, 2, 0])
+    assert [x.hex() for x in g.export()] == [c["g2_generator_compressed"], c["g2_two_g"], c["g2_infinity_compressed"]]
+
+
+def ntt_cases(be, max_log=7):
+    g = gold("ntt")
+    v = [int(x, 16) for x in g["input"]]
+    assert be.ntt(v) == [int(x, 16) for x in g["forward"]]
+    assert be.ntt(v, coset=int(g["coset"], 16)) == [int(x, 16) for x in g["coset_forward"]]
+    rng = random.Random(11)
+    for log_n in range(0, max_log + 1):
+        n = 1 << log_n
+        v = [rng.randrange(O.R) for _ in range(n)]
+        got = be.ntt(v)
+        if n <= 64:
+            w = O.fr_root_of_unity(log_n)
+            assert got == [sum(v[j] * pow(w, i * j, O.R) for j in range(n)) % O.R for i in range(n)]
+        assert be.ntt(got, inverse=True) == v
+        c = rng.randrange(2, O.R)
+        assert be.ntt(be.ntt(v, coset=c), inverse=True, coset=c) == v
+
+
+def ntt_properties(be, log_n):
+    """size-independent properties: evaluation at a few points, linearity, round trip."""
+    n = 1 << log_n
+    rng = random.Random(log_n)
+    v = [rng.randrange(O.R) for _ in range(n)]
+    u = [rng.randrange(O.R) for _ in range(n)]
+    fv, fu = be.ntt(v), be.ntt(u)
+    w = O.fr_root_of_unity(log_n)
+    for i in (0, 1, 2, n // 2, n - 1, rng.randrange(n)):
+        assert fv[i] == O.poly_eval(v, pow(w, i, O.R))
+    k = rng.randrange(O.R)
+    assert be.ntt([(a + k * b) % O.R for a, b in zip(v, u)]) == [(a + k * b) % O.R for a, b in zip(fv, fu)]
+    assert be.ntt(fv, inverse=True) == v
+
+
+def readme_quotient(be):
+    g = gold("readme_circuit")
+    I = lambda xs: [int(x, 16) for x in xs]
+    q = api.QAP(g["nb_vars"], g["nb_io"], g["nb_gates"], [I(p) for p in g["left"]], [I(p) for p in g["right"]],
+                [I(p) for p in g["out"]], I(g["z"]))
+    h, (a, b, c) = api.Quotient(q, g["witness"], backend=be, return_abc=True)
+    assert h == I(g["h"]) and a == I(g["a"]) and b == I(g["b"]) and c == I(g["c"])
+    assert len(h) == g["nb_gates"] - 1          # TestGroth16TrustedSetup, groth16_test.go:16-19
+    import pytest
+    bad = list(g["witness"]); bad[3] += 1
+    with pytest.raises(ArithmeticError, match="apocalypse"):   # qap.go:158-160
+        api.Quotient(q, bad, backend=be)
+    with pytest.raises(ValueError):                              # sanityCheck, qap.go:177-189
+        api.Quotient(q, g["witness"][:-1], backend=be)
+    return q
+
+
+def quotient_vs_div2(be, n, seed=0, circuit="chain"):
+    rng = random.Random(seed)
+    if circuit == "chain":
+        r, w = H.squaring_chain(n, rng.randrange(O.R))
+    else:
+        r, w = H.mixed_circuit(n, seed, max(1, n // 2))
+    oq = O.to_qap(r)
+    q = H.mirror_qap(oq)
+    h, (a, b, c) = api.Quotient(q, w, backend=be, return_abc=True)
+    oa, ob, oc = oq.compute_aggregate_poly(w)
+    assert (a, b, c) == (oa, ob, oc)
+    assert h == oq.quotient(w)        # Poly.Div2 restatement
+    import pytest
+    bad = list(w); bad[-1] = (bad[-1] + 1) % O.R
+    with pytest.raises(ArithmeticError):
+        api.Quotient(q, bad, backend=be)
+    return r, w, oq, q
+
+
+def readme_groth16(be):
+    g = gold("readme_circuit")
+    I = lambda xs: [int(x, 16) for x in xs]
+    q = api.QAP(g["nb_vars"], g["nb_io"], g["nb_gates"], [I(p) for p in g["left"]], [I(p) for p in g["right"]],
+                [I(p) for p in g["out"]], I(g["z"]))
+    k = g["groth16"]
+    B = bytes.fromhex
+    tr = api.Groth16Setup(Alpha=B(k["Alpha"]), Beta=B(k["Beta"]), Delta=B(k["Delta"]), Xi=[B(x) for x in k["Xi"]],
+                          NioLP=[B(x) for x in k["NioLP"]], XiT=[B(x) for x in k["XiT"]], Beta2=B(k["Beta2"]),
+                          Delta2=B(k["Delta2"]), Xi2=[B(x) for x in k["Xi2"]])
+    pr = api.Groth16Prove(tr, q, g["witness"], int(k["r"], 16), int(k["s"], 16), backend=be, want_h=True)
+    assert (pr.A.hex(), pr.B.hex(), pr.C.hex()) == (k["A"], k["B"], k["C"])
+    assert pr.h == I(g["h"])
+    assert pr.tp.R == int(k["r"], 16) and pr.tp.S == int(k["s"], 16)
+    # fresh randomness path (groth16.go:148,158): proof must still verify
+    c = O.create_r1cs(); w = O.create_witness(c); oq = O.to_qap(c)
+    otr = O.groth16_setup(oq, O.Sampler(0))
+    pr2 = api.Groth16Prove(tr, q, w, backend=be)
+    dec = {"A": O.g1_decompress(pr2.A), "B": O.g2_decompress(pr2.B), "C": O.g1_decompress(pr2.C)}
+    assert O.groth16_verify(otr, oq, dec, w[:oq.nb_vars - oq.nb_io])          # TestGroth16Verify
+    ea, eb, ec = O.groth16_expected_from_toxic(otr, oq, w, pr2.tp.R, pr2.tp.S)  # TestGroth16ProofGen
+    assert (dec["A"], dec["B"], dec["C"]) == (ea, eb, ec)
+
+
+def readme_phgr13(be):
+    g = gold("readme_circuit")
+    I = lambda xs: [int(x, 16) for x in xs]
+    q = api.QAP(g["nb_vars"], g["nb_io"], g["nb_gates"], [I(p) for p in g["left"]], [I(p) for p in g["right"]],
+                [I(p) for p in g["out"]], I(g["z"]))
+    k = g["phgr13"]
+    ek = api.PHGR13EvalKey(**{name: [bytes.fromhex(x) for x in v] for name, v in k["ek"].items()})
+    pp = api.PHGR13Prove(ek, q, g["witness"], backend=be, want_h=True)
+    for f in O.PHGR13_FIELDS:
+        assert getattr(pp, f).hex() == k["proof"][f], f
+    assert pp.h == I(g["h"])
+    # verifier acceptance + the mutation rejects of pinocchio_test.go:243-276
+    c = O.create_r1cs(); w = O.create_witness(c); oq = O.to_qap(c)
+    st = O.phgr13_setup(oq, O.Sampler(1))
+    dec = H.decode_phgr13(pp)
+    io = w[:oq.nb_vars - oq.nb_io]
+    assert O.phgr13_verify(st["VK"], oq, dec, io)
+    for f in ("hs", "vss", "vass", "yass", "gz"):
+        bad = dict(dec); bad[f] = O.g1_add(dec[f], O.G1_GEN)
+        assert not O.phgr13_verify(st["VK"], oq, bad, io), f
+
+
+def groth16_circuit(be, n, seed, circuit="mixed", verify=True):
+    """full prove on a synthetic circuit: bit-exact vs the oracle prover (closed form), exponent-level
+    recomputation from the toxic waste, and the oracle's pairing verifier."""
+    rng = random.Random(seed)
+    if circuit == "chain":
+        r, w = H.squaring_chain(n, rng.choice([O.R - 1, rng.randrange(O.R)]))
+    else:
+        r, w = H.mixed_circuit(n, seed, max(1, n // 2))
+    oq = O.to_qap(r)
+    smp = O.Sampler(seed)
+    tr = O.groth16_setup(oq, smp)
+    rr, ss = smp.fr(), smp.fr()
+    pr = api.Groth16Prove(H.mirror_g16_setup(tr), H.mirror_qap(oq), w, rr, ss, backend=be, want_h=True)
+    want = O.groth16_prove(tr, oq, w, rr, ss)
+    assert pr.h == want["h"]
+    assert pr.A == O.g1_compress(want["A"]) and pr.B == O.g2_compress(want["B"]) and pr.C == O.g1_compress(want["C"])
+    ea, eb, ec = O.groth16_expected_from_toxic(tr, oq, w, rr, ss)
+    assert (want["A"], want["B"], want["C"]) == (ea, eb, ec)
+    if verify:
+        assert O.groth16_verify(tr, oq, want, w[:oq.nb_vars - oq.nb_io])
+
+
+def phgr13_circuit(be, n, seed, verify=True):
+    r, w = H.mixed_circuit(n, seed, max(1, n // 2))
+    oq = O.to_qap(r)
+    st = O.phgr13_setup(oq, O.Sampler(seed))
+    pp = api.PHGR13Prove(H.mirror_phgr13_ek(st["EK"]), H.mirror_qap(oq), w, backend=be, want_h=True)
+    want = O.phgr13_prove(st["EK"], oq, w)
+    for f in O.PHGR13_FIELDS:
+        enc = O.g2_compress if f == "wss" else O.g1_compress
+        assert getattr(pp, f) == enc(want[f]), f
+    assert pp.h == want["h"]
+    if verify:
+        assert O.phgr13_verify(st["VK"], oq, want, w[:oq.nb_vars - oq.nb_io])

@@ -1,0 +1,65 @@
+"""The complete C ABI, compiled with -DPS_HOST_EMU (kernel bodies driven by serial loops on the CPU),
+against the oracle.  Covers the host orchestration, index arithmetic and data formats that the GPU
+suite (test_gpu_parity.py) re-checks on the device through the product library."""
+import os
+
+import pytest
+
+from playsnark_b200 import _lib as L, api, build as B
+from tests import parity_cases as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def be():
+    so = B.build_host_emulation(os.path.join(ROOT, "tests", "_build"))
+    lib = L.bind(so)
+    assert b"HOST EMULATION" in lib.ps_version()
+    b = api.Backend(0, lib=lib)
+    yield b
+    b.close()
+
+
+def test_codec(be): P.codec_roundtrip(be, 6)
+def test_msm_golden(be): P.msm_golden(be)
+def test_msm_errors(be): P.msm_errors(be)
+
+
+@pytest.mark.parametrize("kind", ["rand", "ones", "neg", "small", "zero", "edge"])
+def test_msm_g1_kinds(be, kind): P.msm_exponent_check(be, L.PS_G1, 41, kind)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 100, 257])
+def test_msm_g1_sizes(be, n): P.msm_exponent_check(be, L.PS_G1, n)
+
+
+@pytest.mark.parametrize("wb,tables", [(4, 1), (5, 3), (7, 100), (9, 2), (13, 1)])
+def test_msm_g1_windows(be, wb, tables): P.msm_exponent_check(be, L.PS_G1, 50, "rand", wb, tables)
+
+
+def test_msm_g1_skewed_large(be): P.msm_exponent_check(be, L.PS_G1, 600, "ones")
+def test_msm_g1_vs_naive(be): P.msm_vs_naive(be, L.PS_G1, 9)
+def test_msm_g2_vs_naive(be): P.msm_vs_naive(be, L.PS_G2, 5)
+
+
+@pytest.mark.parametrize("kind", ["rand", "small", "edge"])
+def test_msm_g2(be, kind): P.msm_exponent_check(be, L.PS_G2, 19, kind)
+
+
+def test_msm_g2_tables(be): P.msm_exponent_check(be, L.PS_G2, 19, "rand", 6, 4)
+def test_ntt(be): P.ntt_cases(be, 7)
+def test_ntt_properties(be): P.ntt_properties(be, 9)
+def test_readme_quotient(be): P.readme_quotient(be)
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 8, 13, 16, 33])
+def test_quotient_chain(be, n): P.quotient_vs_div2(be, n, seed=n)
+
+
+def test_quotient_mixed(be): P.quotient_vs_div2(be, 12, seed=5, circuit="mixed")
+def test_readme_groth16(be): P.readme_groth16(be)
+def test_readme_phgr13(be): P.readme_phgr13(be)
+def test_groth16_mixed(be): P.groth16_circuit(be, 10, seed=3)
+def test_groth16_chain_negative_witness(be): P.groth16_circuit(be, 8, seed=4, circuit="chain", verify=False)
+def test_phgr13_mixed(be): P.phgr13_circuit(be, 9, seed=6)

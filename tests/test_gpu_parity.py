@@ -1,0 +1,108 @@
+"""Parity tests proper: the CUDA path, called through the product C ABI (libplaysnark_b200.so),
+against the oracle / golden fixtures, plus size-independent properties at BASELINE.json's sizes."""
+import random
+
+import pytest
+
+from oracle import ps_oracle as O
+from playsnark_b200 import _lib as L, api
+from tests import parity_cases as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def be():
+    lib = L.load()
+    assert b"sm_100a" in lib.ps_version()      # the product build, not the host emulation
+    b = api.Backend(0)
+    before = b.launch_count()
+    yield b
+    assert b.launch_count() > before           # kernels really ran
+    b.close()
+
+
+def test_codec(be): P.codec_roundtrip(be, 40)
+def test_msm_golden(be): P.msm_golden(be)
+def test_msm_errors(be): P.msm_errors(be)
+
+
+@pytest.mark.parametrize("kind", ["rand", "ones", "neg", "small", "zero", "edge"])
+def test_msm_g1_kinds(be, kind): P.msm_exponent_check(be, L.PS_G1, 1000, kind)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 257, 4096, 1 << 14])
+def test_msm_g1_sizes(be, n): P.msm_exponent_check(be, L.PS_G1, n)
+
+
+@pytest.mark.parametrize("wb,tables", [(4, 1), (5, 3), (7, 100), (9, 2), (13, 1), (16, 1), (16, 16)])
+def test_msm_g1_windows(be, wb, tables): P.msm_exponent_check(be, L.PS_G1, 3000, "rand", wb, tables)
+
+
+def test_msm_g1_skewed_large(be): P.msm_exponent_check(be, L.PS_G1, 1 << 16, "ones")
+def test_msm_g1_small_scalars_large(be): P.msm_exponent_check(be, L.PS_G1, 1 << 16, "small")
+def test_msm_g1_vs_naive(be): P.msm_vs_naive(be, L.PS_G1, 48)
+def test_msm_g2_vs_naive(be): P.msm_vs_naive(be, L.PS_G2, 24)
+
+
+@pytest.mark.parametrize("kind", ["rand", "small", "edge", "ones"])
+def test_msm_g2(be, kind): P.msm_exponent_check(be, L.PS_G2, 700, kind)
+
+
+@pytest.mark.parametrize("n", [1, 5, 4096])
+def test_msm_g2_sizes(be, n): P.msm_exponent_check(be, L.PS_G2, n)
+
+
+def test_msm_g2_tables(be): P.msm_exponent_check(be, L.PS_G2, 500, "rand", 8, 4)
+
+
+def test_msm_large_g1(be):
+    # config C4 scale: 2^20 points, checked in the exponent
+    P.msm_exponent_check(be, L.PS_G1, 1 << 20, "rand")
+
+
+def test_msm_large_g2(be):
+    P.msm_exponent_check(be, L.PS_G2, 1 << 17, "rand")
+
+
+def test_msm_linearity(be):
+    """MSM(s+t) = MSM(s) + MSM(t), MSM(k*s) = k*MSM(s) on a fixed base set."""
+    rng = random.Random(42)
+    n = 5000
+    bases = be.bases_from_scalars(L.PS_G1, [rng.randrange(1, O.R) for _ in range(n)])
+    s = [rng.randrange(O.R) for _ in range(n)]
+    t = [rng.randrange(O.R) for _ in range(n)]
+    k = rng.randrange(O.R)
+    ms, mt = O.g1_decompress(be.msm(bases, s)), O.g1_decompress(be.msm(bases, t))
+    mst = O.g1_decompress(be.msm(bases, [(a + b) % O.R for a, b in zip(s, t)]))
+    assert mst == O.g1_add(ms, mt)
+    assert O.g1_decompress(be.msm(bases, [a * k % O.R for a in s])) == O.g1_mul(k, ms)
+
+
+def test_ntt(be): P.ntt_cases(be, 10)
+
+
+@pytest.mark.parametrize("log_n", [11, 16, 20])
+def test_ntt_properties(be, log_n): P.ntt_properties(be, log_n)
+
+
+def test_readme_quotient(be): P.readme_quotient(be)
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 8, 13, 16, 33, 64, 100])
+def test_quotient_chain(be, n): P.quotient_vs_div2(be, n, seed=n)
+
+
+def test_quotient_mixed(be): P.quotient_vs_div2(be, 48, seed=5, circuit="mixed")
+def test_readme_groth16(be): P.readme_groth16(be)
+def test_readme_phgr13(be): P.readme_phgr13(be)
+def test_groth16_mixed(be): P.groth16_circuit(be, 24, seed=3)
+def test_groth16_chain_negative_witness(be): P.groth16_circuit(be, 32, seed=4, circuit="chain", verify=False)
+def test_phgr13_mixed(be): P.phgr13_circuit(be, 20, seed=6)
+
+
+def test_no_device_is_loud():
+    lib = L.load()
+    import ctypes as C
+    ctx = C.c_void_p()
+    assert lib.ps_ctx_create(9999, C.byref(ctx)) == L.PS_ERR_CUDA

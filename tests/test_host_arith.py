@@ -1,0 +1,135 @@
+"""Device field / curve templates, compiled for the host with an emulated carry flag, against the
+oracle.  Catches arithmetic mistakes without a GPU; the same templates are what the kernels run."""
+import ctypes
+import random
+
+import pytest
+
+from oracle import ps_oracle as O
+
+U32 = ctypes.c_uint32
+
+
+def limbs(x, n):
+    return (U32 * n)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+
+
+def unl(a):
+    return sum(int(v) << (32 * i) for i, v in enumerate(a))
+
+
+def fp_vals(rng, k):
+    edge = [0, 1, 2, O.P - 1, O.P - 2, (1 << 384) % O.P, (1 << 380), (O.P - 1) // 2, 0xFFFFFFFF, 1 << 32]
+    return edge + [rng.randrange(O.P) for _ in range(k)]
+
+
+def fr_vals(rng, k):
+    edge = [0, 1, 2, O.R - 1, O.R - 2, (1 << 256) % O.R, 1 << 254, 0xFFFFFFFF, 1 << 32]
+    return edge + [rng.randrange(O.R) for _ in range(k)]
+
+
+def test_fp_ops(host_check):
+    rng = random.Random(1)
+    vals = fp_vals(rng, 40)
+    out = (U32 * 12)()
+    for a in vals:
+        for b in vals[:14] + vals[-6:]:
+            host_check.hc_fp_mul(limbs(a, 12), limbs(b, 12), out); assert unl(out) == a * b % O.P
+            host_check.hc_fp_add(limbs(a, 12), limbs(b, 12), out); assert unl(out) == (a + b) % O.P
+            host_check.hc_fp_sub(limbs(a, 12), limbs(b, 12), out); assert unl(out) == (a - b) % O.P
+    rinv = pow(1 << 384, -1, O.P)
+    for a in vals:
+        for b in vals[:12]:
+            host_check.hc_fp_montmul_raw(limbs(a, 12), limbs(b, 12), out)
+            assert unl(out) == a * b * rinv % O.P
+    for a in vals[1:20]:
+        host_check.hc_fp_inv(limbs(a, 12), out); assert unl(out) * a % O.P == 1
+    host_check.hc_fp_inv(limbs(0, 12), out); assert unl(out) == 0
+    for a in vals[:20]:
+        sq = a * a % O.P
+        host_check.hc_fp_sqrt(limbs(sq, 12), out); assert unl(out) in (a, (O.P - a) % O.P)
+
+
+def test_fr_ops(host_check):
+    rng = random.Random(2)
+    vals = fr_vals(rng, 40)
+    out = (U32 * 8)()
+    rinv = pow(1 << 256, -1, O.R)
+    for a in vals:
+        for b in vals[:14] + vals[-6:]:
+            host_check.hc_fr_mul(limbs(a, 8), limbs(b, 8), out); assert unl(out) == a * b % O.R
+            host_check.hc_fr_add(limbs(a, 8), limbs(b, 8), out); assert unl(out) == (a + b) % O.R
+            host_check.hc_fr_sub(limbs(a, 8), limbs(b, 8), out); assert unl(out) == (a - b) % O.R
+            host_check.hc_fr_montmul_raw(limbs(a, 8), limbs(b, 8), out); assert unl(out) == a * b * rinv % O.R
+    for a in vals[1:20]:
+        host_check.hc_fr_inv(limbs(a, 8), out); assert unl(out) * a % O.R == 1
+
+
+def f2l(a):
+    return limbs(a[0] | (a[1] << 384), 24)
+
+
+def unf2(a):
+    v = unl(a)
+    return (v & ((1 << 384) - 1), v >> 384)
+
+
+def test_fp2_ops(host_check):
+    rng = random.Random(3)
+    vals = [(0, 0), (1, 0), (0, 1), (O.P - 1, O.P - 1)] + [(rng.randrange(O.P), rng.randrange(O.P)) for _ in range(20)]
+    out = (U32 * 24)()
+    for a in vals:
+        for b in vals:
+            host_check.hc_fp2_mul(f2l(a), f2l(b), out); assert unf2(out) == O.F2.mul(a, b)
+        host_check.hc_fp2_sqr(f2l(a), out); assert unf2(out) == O.F2.sqr(a)
+        if a != (0, 0):
+            host_check.hc_fp2_inv(f2l(a), out); assert O.F2.mul(unf2(out), a) == (1, 0)
+
+
+def g1l(p):
+    return limbs(0 if p is None else p[0] | (p[1] << 384), 24)
+
+
+def ung1(a):
+    v = unl(a)
+    x, y = v & ((1 << 384) - 1), v >> 384
+    return None if (x, y) == (0, 0) else (x, y)
+
+
+def g2l(p):
+    if p is None:
+        return limbs(0, 48)
+    (x0, x1), (y0, y1) = p
+    return limbs(x0 | (x1 << 384) | (y0 << 768) | (y1 << 1152), 48)
+
+
+def ung2(a):
+    v = unl(a)
+    m = (1 << 384) - 1
+    c = [(v >> (384 * i)) & m for i in range(4)]
+    return None if c == [0, 0, 0, 0] else ((c[0], c[1]), (c[2], c[3]))
+
+
+@pytest.mark.parametrize("grp", ["g1", "g2"])
+def test_group_law(host_check, grp):
+    rng = random.Random(4)
+    F = O.F1 if grp == "g1" else O.F2
+    gen = O.G1_GEN if grp == "g1" else O.G2_GEN
+    enc, dec = (g1l, ung1) if grp == "g1" else (g2l, ung2)
+    out = (U32 * (24 if grp == "g1" else 48))()
+    madd = getattr(host_check, "hc_%s_madd" % grp)
+    add = getattr(host_check, "hc_%s_add" % grp)
+    mul = getattr(host_check, "hc_%s_mul" % grp)
+    ks = [1, 2, 3, 5, O.R - 1, O.R - 2] + [rng.randrange(1, O.R) for _ in range(4)]
+    pts = [None] + [O.pt_mul(F, k, gen) for k in ks]
+    for p in pts:
+        for q in pts:
+            for pre in (1, 2, 3):
+                want = O.pt_add(F, O.pt_mul(F, pre, p), q)
+                madd(enc(p), enc(q), pre, out); assert dec(out) == want, (grp, "madd", pre)
+            for pre in (1, 2):
+                want = O.pt_add(F, O.pt_mul(F, pre, p), O.pt_mul(F, pre, q))
+                add(enc(p), enc(q), pre, out); assert dec(out) == want, (grp, "add", pre)
+    for k in [0, 1, 2, O.R - 1, O.R, rng.randrange(O.R), rng.randrange(1 << 64)]:
+        for p in pts[:4]:
+            mul(enc(p), limbs(k, 8), out); assert dec(out) == O.pt_mul(F, k, p)
