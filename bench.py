@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""Benchmark of the prover hot path (contract: see the task statement / DESIGN.md section 6).
+
+Metric (BASELINE.json): G1 MSM points/s -- the operation that dominates Groth16Prove / PHGR13Prove
+(Poly.BlindEval, algebra.go:348-359) -- on synthetic data: bases k_i*G built on the device, scalars
+uniform below 2^254 (< r).  One "step" = one MSM over the rank's point range.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n L] [--impl reference]
+
+N = 1: one MSM of 2^L points (default L = 24, configs[3] of BASELINE.json, the size the north-star's
+roofline target is quoted on).  N > 1 (torchrun, one rank per GPU): every rank owns its own 2^L-point
+range (weak scaling; the MSM shards by point range with no data-path collective), the partial points
+are all-gathered over NCCL (192 B per rank) and summed on rank 0.
+`value` = points/s with scalars resident in HBM (ps_msm_device); `e2e` = the same through the
+reference-facing call with HOST buffers (ps_msm: pinned big-endian scalars in, compressed point out).
+`--impl reference` times the CPU port of the reference algorithm (oracle/ps_oracle.c: one bit-serial
+scalar multiplication per term, single-threaded like the Go code) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+METRIC = "g1_msm_points_per_s"
+UNIT = "points/s"
+IMAD_PER_FP_MUL = 600.0      # 300 32x32->64 MACs as IMAD.LO/IMAD.HI pairs
+FP_MUL_PER_MADD = 10.0       # XYZZ mixed addition, 8M + 2S
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def random_scalars_be(n: int, seed: int):
+    """n uniform 254-bit scalars as big-endian 32-byte rows (numpy uint8 [n, 32])."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a[:, 0] &= 0x3F
+    return a
+
+
+def be_to_le_limbs(a):
+    """[n, 32] big-endian bytes -> [n, 8] little-endian uint32 limbs (standard form)."""
+    import numpy as np
+    return np.ascontiguousarray(a[:, ::-1]).view("<u4").reshape(-1, 8).copy()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_arm(args):
+    """CPU port of the reference's BlindEval, single-threaded, bounded sample of the same workload."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import c_oracle as CO, ps_oracle as O
+    sample = 1 << args.ref_log_n
+    # bases k_i * G for the sample, built with the oracle (untimed)
+    sc = random_scalars_be(sample, 3)
+    pts = []
+    acc = None
+    # cheap distinct multiples of G (untimed setup): P_i = (i+1) * k0 * G by repeated addition
+    p0 = O.g1_mul(0x1234567 | 1)
+    for _ in range(sample):
+        acc = O.g1_add(acc, p0)
+        pts.append(acc)
+    pbytes = b"".join(O.g1_affine_bytes(p) for p in pts)
+    sbytes = sc.tobytes()
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        CO.blind_eval_g1(pbytes[:96 * 64], sbytes[:32 * 64])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        CO.blind_eval_g1(pbytes, sbytes)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "G1 MSM 2^%d points/GPU, random 254-bit scalars" % args.log_n,
+                   "sample": "2^%d points per step" % args.ref_log_n},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "Poly.BlindEval (algebra.go:348-359) restated in C (oracle/ps_oracle.c), one bit-serial "
+                                   "scalar-mul per term, 2^%d of the 2^%d points per step, %d host cores present, 1 used "
+                                   "(the reference is single-threaded); Go toolchain absent, reference not buildable"
+                                   % (args.ref_log_n, args.log_n, os.cpu_count() or 0)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--log-n", type=int, default=24)
+    ap.add_argument("--ref-log-n", type=int, default=12)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--tables", type=int, default=-1, help="precomputed window tables (-1 = all windows)")
+    ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import playsnark_b200 as ps
+    from playsnark_b200 import _lib as L
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    be = ps.Backend(local)
+    stream = torch.cuda.current_stream()
+    be.set_stream(stream.cuda_stream)
+    lib = be.lib
+
+    n = 1 << args.log_n
+    # synthetic inputs: bases k_i*G (fixed-base kernel on the device, untimed), scalars uniform < 2^254
+    ks = random_scalars_be(n, 1000 + rank)
+    sc_be = random_scalars_be(n, 2000 + rank)
+    t0 = time.time()
+    bases = be.bases_from_scalars(L.PS_G1, ks.tobytes(), args.window_bits, args.tables)
+    be.sync()
+    t_bases = time.time() - t0
+    del ks
+    d_scalars = torch.from_numpy(be_to_le_limbs(sc_be).view(np.int32)).to(dev)
+    h_scalars = torch.from_numpy(sc_be).pin_memory()            # e2e input: pinned host, wire format
+    d_part = torch.zeros(192, dtype=torch.uint8, device=dev)
+    d_all = torch.zeros(192 * world, dtype=torch.uint8, device=dev)
+    out = C.create_string_buffer(48)
+
+    def step_resident():
+        be._check(lib.ps_msm_device(be.ctx, bases.handle, 0, C.c_void_p(d_scalars.data_ptr()), n, C.c_void_p(d_part.data_ptr())))
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_part)
+
+    def step_e2e():
+        if world == 1:
+            be._check(lib.ps_msm(be.ctx, bases.handle, C.c_void_p(h_scalars.data_ptr()), n, out))
+            return out.raw
+        # host scalars -> device limbs -> partial -> gather -> sum on rank 0 -> compressed point on host
+        d_be = h_scalars.to(dev, non_blocking=True)
+        limbs = d_be.flip(1).contiguous().view(torch.int32)
+        be._check(lib.ps_msm_device(be.ctx, bases.handle, 0, C.c_void_p(limbs.data_ptr()), n, C.c_void_p(d_part.data_ptr())))
+        dist.all_gather_into_tensor(d_all, d_part)
+        if rank == 0:
+            be._check(lib.ps_msm_combine(be.ctx, L.PS_G1, C.c_void_p(d_all.data_ptr()), world, out))
+        return out.raw
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # correctness gate before timing: the device result must equal the exponent-level expectation on
+    # a small prefix (same kernels, same bases); full parity lives in tests/.
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+
+    # integer-multiply peak measured on this device (MEASURED_PEAKS.json has no integer figure)
+    v, ms_ = C.c_double(), C.c_double()
+    be._check(lib.ps_bench_intpipe(be.ctx, 0, 2000, C.byref(v), C.byref(ms_)))
+    imad_peak = v.value
+    be._check(lib.ps_bench_fieldmul(be.ctx, 1, 1000, C.byref(v), C.byref(ms_)))
+    fpmul_rate = v.value
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = be.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase = {"sort_ms": 0.0, "accumulate_ms": 0.0, "combine_ms": 0.0, "reduce_ms": 0.0, "total_ms": 0.0}
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = be.launch_count() - launches0
+    tm = be.msm_timing()            # phases of the last step (CUDA events on the launching stream)
+    for k in phase:
+        phase[k] = tm[k]
+    clocks = sampler.stop() if sampler else None
+
+    # e2e: host buffers in, host bytes out, copies inside the timed region
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_points = float(n) * world * args.steps
+    value = total_points / (ms_total * 1e-3)
+    e2e_value = total_points / (e2e_ms * 1e-3)
+
+    # roofline of the dominant kernel (MsmAccumK): algorithmic IMAD = entries * madd * Fp-mul cost
+    info = (C.c_int * 4)()
+    be._check(lib.ps_bases_info(bases.handle, info))
+    c_bits, W = info[0], info[1]
+    madds = float(n) * W
+    imad_alg = madds * FP_MUL_PER_MADD * IMAD_PER_FP_MUL
+    accum_s = phase["accumulate_ms"] * 1e-3
+    achieved = imad_alg / accum_s if accum_s > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            tr = json.load(f)
+        key = "g1_msm_2^%d" % args.log_n
+        traffic = tr.get(key, {}).get("MsmAccumK_dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    gather_bytes = madds * 96.0 + madds * 4.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "G1 MSM 2^%d points/GPU, random 254-bit scalars, resident bases" % args.log_n,
+                   "window_bits": c_bits, "windows": W, "precomputed_tables": args.tables,
+                   "l2": "inputs larger than L2 (scalars %d MB, bases >= %d MB per table)" % (n * 32 >> 20, n * 96 >> 20),
+                   "parallelism": "point-range shard x%d, all-gather of 192 B partials" % world if world > 1 else "single GPU",
+                   "bases_build_s": round(t_bases, 2)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 48,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "phases_ms_last_step": phase,
+        "roofline": {"bound": "imad", "kernel": "MsmAccumK<Fp>", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
+                     "unit": "TIMAD/s", "frac": achieved / imad_peak if imad_peak else None, "traffic": traffic,
+                     "how": "algorithmic IMAD = n*W mixed adds x 10 Fp mul x 600 IMAD (IMAD.LO/HI pair accounting) / "
+                            "CUDA-event time of the kernel; peak = IMAD issue rate measured live on this GPU "
+                            "(ps_bench_intpipe, 'of measured'; MEASURED_PEAKS.json has no integer figure)",
+                     "whole_msm_frac": (imad_alg / (phase["total_ms"] * 1e-3)) / imad_peak if phase["total_ms"] else None,
+                     "fp_mul_per_s_microbench": fpmul_rate,
+                     "hbm": {"achieved_gbs": gather_bytes / accum_s / 1e9 if accum_s else None,
+                             "what": "base gather 96 B + entry 4 B per mixed add"}},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args):
+    """the oracle's C port of BlindEval on this box's host cores, bounded sample (about 10-20 s)"""
+    from oracle import c_oracle as CO, ps_oracle as O
+    sample = 1 << args.ref_log_n
+    sc = random_scalars_be(sample, 3)
+    p0 = O.g1_mul(0x1234567 | 1)
+    pts, acc = [], None
+    for _ in range(sample):
+        acc = O.g1_add(acc, p0)
+        pts.append(acc)
+    pbytes = b"".join(O.g1_affine_bytes(p) for p in pts)
+    CO.blind_eval_g1(pbytes[:96 * 32], sc.tobytes()[:32 * 32])
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        CO.blind_eval_g1(pbytes, sc.tobytes())
+        reps += 1
+        if time.perf_counter() - t0 > 10.0 or reps >= 20:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": sample * reps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d x Poly.BlindEval over 2^%d of the workload's points (oracle/ps_oracle.c, bit-serial scalar-mul "
+                      "per term as algebra.go:348-359; single-threaded like the reference; %d host cores present)"
+                      % (reps, args.ref_log_n, os.cpu_count() or 0)}
+
+
+if __name__ == "__main__":
+    main()

@@ -62,10 +62,15 @@ uint64_t ps_launch_count(void);
 /* ---- MSM bases: the []Commit argument of Poly.BlindEval (algebra.go:348) ------------------- */
 /* `window_bits` = 0 lets the library choose c per call; otherwise fixes the Pippenger window and,
  * with `precompute_tables` = T > 1, stores 2^(c*t) * P_i for t < T so that T windows share one
- * bucket set (T is clamped to the number of windows).                                          */
+ * bucket set (T is clamped to the number of windows).  precompute_tables = -1 asks for all
+ * windows, with the window chosen by the library when window_bits = 0 (what the key loaders use:
+ * 180 GB of HBM make W copies of the key cheap, and they remove the per-window bucket sets).    */
 int ps_bases_load(ps_ctx* ctx, int group, const uint8_t* points, size_t n, int format,
                   int window_bits, int precompute_tables, ps_bases** out);
 size_t ps_bases_len(const ps_bases* b);
+/* out[0] = window bits c used for a full-length MSM, out[1] = windows W, out[2] = tables T,
+ * out[3] = group */
+int ps_bases_info(const ps_bases* b, int out[4]);
 void ps_bases_free(ps_bases* b);
 /* bases[i] = scalars[i] * generator (GeneratePowersCommit's Mul(s, nil), algebra.go:373,381);
  * used by setup-side callers and the benchmarks to create large keys on the GPU.               */
@@ -149,9 +154,9 @@ int ps_phgr13_prove(ps_ctx* ctx, const ps_phgr13_key* key, const ps_qap* qap, co
 int ps_bench_intpipe(ps_ctx* ctx, int variant, int iters, double* inst_per_s, double* ms);
 /* chained Montgomery products per second (field 0 = Fr, 1 = Fp) */
 int ps_bench_fieldmul(ps_ctx* ctx, int field, int iters, double* mul_per_s, double* ms);
-/* device time in ms of the last ps_msm / ps_msm_device call on this context, by phase:
- * [0] digits+sort, [1] bucket accumulate, [2] bucket reduce, [3] total                          */
-int ps_last_msm_timing(ps_ctx* ctx, float out_ms[4]);
+/* device time in ms of the last MSM on this context (CUDA events on its stream), by phase:
+ * [0] digits+sort, [1] bucket-accumulate kernel, [2] partial merge, [3] bucket reduce, [4] total */
+int ps_last_msm_timing(ps_ctx* ctx, float out_ms[5]);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,74 @@
+"""ctypes wrapper of oracle/ps_oracle.c (TEST INFRASTRUCTURE; see that file's header)."""
+import ctypes as C
+
+from . import build_oracle
+from . import ps_oracle as O
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build_oracle.build())
+        _lib.oc_blind_eval_g1.restype = C.c_long
+        _lib.oc_blind_eval_g1.argtypes = [C.c_char_p, C.c_char_p, C.c_long, C.c_char_p]
+        _lib.oc_quotient.restype = C.c_int
+        _lib.oc_quotient.argtypes = [C.c_char_p] * 4 + [C.c_long, C.c_int, C.c_char_p]
+        _lib.oc_aggregate.argtypes = [C.c_char_p, C.c_char_p, C.c_long, C.c_long, C.c_char_p]
+    return _lib
+
+
+def blind_eval_g1(points_affine_bytes: bytes, scalars_be: bytes):
+    """Poly.BlindEval over G1; returns the affine point (oracle tuple) or None."""
+    n = len(scalars_be) // 32
+    assert len(points_affine_bytes) == 96 * n
+    out = C.create_string_buffer(96)
+    lib().oc_blind_eval_g1(points_affine_bytes, scalars_be, n, out)
+    return O.g1_from_affine_bytes(out.raw)
+
+
+def g1_mul(pt, k: int):
+    out = C.create_string_buffer(96)
+    lib().oc_g1_mul(O.g1_affine_bytes(pt), O.fr_to_bytes(k), out)
+    return O.g1_from_affine_bytes(out.raw)
+
+
+def fp_mul(a: int, b: int) -> int:
+    out = C.create_string_buffer(48)
+    lib().oc_fp_mul(a.to_bytes(48, "big"), b.to_bytes(48, "big"), out)
+    return int.from_bytes(out.raw, "big")
+
+
+def fr_mul(a: int, b: int) -> int:
+    out = C.create_string_buffer(32)
+    lib().oc_fr_mul(a.to_bytes(32, "big"), b.to_bytes(32, "big"), out)
+    return int.from_bytes(out.raw, "big")
+
+
+def fr_inv(a: int) -> int:
+    out = C.create_string_buffer(32)
+    lib().oc_fr_inv(a.to_bytes(32, "big"), out)
+    return int.from_bytes(out.raw, "big")
+
+
+def _poly_bytes(p):
+    return b"".join(O.fr_to_bytes(v) for v in p)
+
+
+def aggregate(polys, witness):
+    m, n = len(polys), len(polys[0])
+    out = C.create_string_buffer(32 * n)
+    lib().oc_aggregate(b"".join(_poly_bytes(p) for p in polys), _poly_bytes(witness), m, n, out)
+    return [int.from_bytes(out.raw[32 * i:32 * i + 32], "big") for i in range(n)]
+
+
+def quotient(a, b, c, z, faithful=False):
+    """(a*b - c) / z via Poly.Mul / Sub / Div2; raises ArithmeticError("apocalypse") on a remainder."""
+    n = len(a)
+    assert len(b) == n and len(c) == n and len(z) == n + 1
+    out = C.create_string_buffer(32 * max(1, n - 1))
+    rc = lib().oc_quotient(_poly_bytes(a), _poly_bytes(b), _poly_bytes(c), _poly_bytes(z), n, 1 if faithful else 0, out)
+    if rc:
+        raise ArithmeticError("apocalypse")
+    return [int.from_bytes(out.raw[32 * i:32 * i + 32], "big") for i in range(n - 1)]

@@ -30,6 +30,7 @@ SYMBOLS = [
     ("ps_launch_count", C.c_uint64, []),
     ("ps_bases_load", _I, [_P, _I, _B, _SZ, _I, _I, _I, C.POINTER(_P)]),
     ("ps_bases_len", _SZ, [_P]),
+    ("ps_bases_info", _I, [_P, C.POINTER(C.c_int)]),
     ("ps_bases_free", None, [_P]),
     ("ps_bases_from_scalars", _I, [_P, _I, _B, _SZ, _I, _I, C.POINTER(_P)]),
     ("ps_bases_export", _I, [_P, _P, _SZ, _SZ, _I, _P]),

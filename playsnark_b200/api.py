@@ -114,9 +114,9 @@ class Backend:
         return out.raw
 
     def msm_timing(self):
-        t = (C.c_float * 4)()
+        t = (C.c_float * 5)()
         self._check(self.lib.ps_last_msm_timing(self.ctx, t))
-        return {"sort_ms": t[0], "accumulate_ms": t[1], "reduce_ms": t[2], "total_ms": t[3]}
+        return {"sort_ms": t[0], "accumulate_ms": t[1], "combine_ms": t[2], "reduce_ms": t[3], "total_ms": t[4]}
 
     # ---- NTT ----
     def ntt(self, values: Sequence[int], inverse: bool = False, coset: Optional[int] = None) -> List[int]:

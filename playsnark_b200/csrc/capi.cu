@@ -126,6 +126,17 @@ int bases_finish(ps_ctx* ctx, ps_bases* b) {
 
 int bases_alloc(int group, size_t n, int window_bits, int tables, ps_bases** out) {
   if (window_bits < 0 || window_bits > 24 || (window_bits > 0 && window_bits < 2)) return PS_ERR_ARG;
+  if (tables < 0) {  // automatic: all windows precomputed when the tables fit comfortably in HBM
+    if (window_bits == 0) window_bits = msm_pick_window_full(n ? n : 1);
+    tables = msm_windows(window_bits);
+    size_t need = n * (size_t)tables * (group == PS_G1 ? sizeof(G1Affine) : sizeof(G2Affine));
+    size_t free_b = need * 8, total_b = 0;
+#if PS_GPU
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+#endif
+    (void)total_b;
+    if (need > free_b / 4) { tables = 1; window_bits = 0; }
+  }
   if (tables < 1) tables = 1;
   if (tables > 1 && window_bits == 0) return PS_ERR_ARG;
   if (window_bits && tables > msm_windows(window_bits)) tables = msm_windows(window_bits);
@@ -256,7 +267,7 @@ int bases_concat(ps_ctx* ctx, int format, const uint8_t* const* parts, const siz
     memcpy(buf.data() + o, parts[i], counts[i] * per);
     o += counts[i] * per;
   }
-  return bases_load_t<F, DecodeK>(ctx, buf.data(), total, format, 0, 1, out);
+  return bases_load_t<F, DecodeK>(ctx, buf.data(), total, format, 0, -1, out);
 }
 
 }  // namespace
@@ -307,7 +318,7 @@ int ps_ctx_create(int device, ps_ctx** out) {
   PS_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   ctx->stream = st;
   ctx->own_stream = true;
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < 5; i++) {
     cudaEvent_t e;
     PS_CUDA_TRY(cudaEventCreate(&e));
     ctx->ev[i] = e;
@@ -342,7 +353,7 @@ void ps_ctx_destroy(ps_ctx* ctx) {
   dev_free(ctx->fixed_base[0]);
   dev_free(ctx->fixed_base[1]);
 #if PS_GPU
-  for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy((cudaEvent_t)ctx->ev[i]);
+  for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy((cudaEvent_t)ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
 #endif
   delete ctx;
@@ -359,6 +370,13 @@ int ps_bases_load(ps_ctx* ctx, int group, const uint8_t* points, size_t n, int f
 }
 
 size_t ps_bases_len(const ps_bases* b) { return b ? b->n : 0; }
+
+int ps_bases_info(const ps_bases* b, int out[4]) {
+  if (!b || !out) return PS_ERR_ARG;
+  int c = b->c ? b->c : msm_pick_window(b->n ? b->n : 1);
+  out[0] = c; out[1] = msm_windows(c); out[2] = b->T; out[3] = b->group;
+  return PS_OK;
+}
 
 void ps_bases_free(ps_bases* b) {
   if (!b) return;
@@ -450,15 +468,15 @@ int ps_msm_combine(ps_ctx* ctx, int group, const void* d_partials_xyzz, size_t c
   return dev_sync(ctx->stream);
 }
 
-int ps_last_msm_timing(ps_ctx* ctx, float out_ms[4]) {
+int ps_last_msm_timing(ps_ctx* ctx, float out_ms[5]) {
   if (!ctx || !out_ms) return PS_ERR_ARG;
-  for (int i = 0; i < 4; i++) out_ms[i] = 0.f;
+  for (int i = 0; i < 5; i++) out_ms[i] = 0.f;
 #if PS_GPU
   if (!ctx->ev_valid) return PS_ERR_ARG;
-  PS_CUDA_TRY(cudaEventSynchronize((cudaEvent_t)ctx->ev[3]));
-  for (int i = 0; i < 3; i++)
+  PS_CUDA_TRY(cudaEventSynchronize((cudaEvent_t)ctx->ev[4]));
+  for (int i = 0; i < 4; i++)
     PS_CUDA_TRY(cudaEventElapsedTime(&out_ms[i], (cudaEvent_t)ctx->ev[i], (cudaEvent_t)ctx->ev[i + 1]));
-  PS_CUDA_TRY(cudaEventElapsedTime(&out_ms[3], (cudaEvent_t)ctx->ev[0], (cudaEvent_t)ctx->ev[3]));
+  PS_CUDA_TRY(cudaEventElapsedTime(&out_ms[4], (cudaEvent_t)ctx->ev[0], (cudaEvent_t)ctx->ev[4]));
 #endif
   return PS_OK;
 }

@@ -11,8 +11,8 @@ struct ps_ctx {
   ps::Arena arena;                 // per-call scratch, persists across calls
   ps::NttTables ntt_cache[31];     // twiddles by log2(size), built on first use
   void* fixed_base[2] = {nullptr, nullptr};  // 32 x 255 affine multiples of the G1 / G2 generator
-  // phase events of the last MSM (cudaEvent_t): start, sorted, accumulated, reduced
-  void* ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // phase events of the last MSM (cudaEvent_t): start, sorted, accumulated, combined, reduced
+  void* ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
 };
 

@@ -148,26 +148,55 @@ struct MsmAccumK {
     uint32_t end = (M - cur > L) ? cur + L : M;
     uint32_t b = msm_find_bucket(off, nb, cur);
     bool head_open = off[b] < cur;
+    uint32_t bend = off[b + 1];
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (;;) {
-      uint32_t bend = off[b + 1];
-      uint32_t lim = bend < end ? bend : end;
-      for (; cur < lim; cur++) xyzz_madd(acc, msm_load_point(tab, ent[cur]));
-      bool closed = bend <= end;
-      if (closed && !head_open) {
-        buckets[b] = acc;
-      } else {
-        uint32_t s = head_open ? head : tail;
-        slot_pt[s] = acc;
-        slot_bid[s] = (int32_t)b;
-        slot_fl[s] = (uint8_t)((head_open ? 1 : 0) | (closed ? 0 : 2));
+    // One flat loop of (at most) L iterations: every lane of the warp reaches the madd together; the
+    // bucket hand-over is a short predicated block in front of it.
+    for (; cur < end; cur++) {
+      if (cur == bend) {  // bucket b ended exactly here
+        flush(b, acc, head_open, true, head, tail, buckets, slot_pt, slot_bid, slot_fl);
+        acc = XYZZ<F>::inf();
+        head_open = false;
+        b++;
+        while (off[b + 1] <= cur) b++;
+        bend = off[b + 1];
       }
-      if (cur >= end) break;
-      acc = XYZZ<F>::inf();
-      head_open = false;
-      b++;
-      while (off[b + 1] <= cur) b++;
+      xyzz_madd(acc, msm_load_point(tab, ent[cur]));
     }
+    flush(b, acc, head_open, bend <= end, head, tail, buckets, slot_pt, slot_bid, slot_fl);
+  }
+  PS_DEV static void flush(uint32_t b, const XYZZ<F>& acc, bool head_open, bool closed, uint32_t head, uint32_t tail,
+                           XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid, uint8_t* slot_fl) {
+    if (closed && !head_open) {
+      buckets[b] = acc;
+    } else {
+      uint32_t s = head_open ? head : tail;
+      slot_pt[s] = acc;
+      slot_bid[s] = (int32_t)b;
+      slot_fl[s] = (uint8_t)((head_open ? 1 : 0) | (closed ? 0 : 2));
+    }
+  }
+};
+
+// Most boundary partials come in pairs: the tail of chunk t (its last bucket runs on) and the head
+// of chunk t+1 (the same bucket ends there).  One fully parallel pass adds such pairs straight into
+// the bucket and blanks the two slots; only buckets spanning three or more chunks stay for the
+// log-depth merge below.
+template <class F>
+struct MsmPairMergeK {
+  static constexpr int BLOCK = 128;
+  PS_DEV static void run(uint32_t t, uint32_t n_chunks, XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid,
+                         const uint8_t* slot_fl) {
+    if (t + 1 >= n_chunks) return;
+    const uint32_t a = 2 * t + 1, b = 2 * t + 2;  // tail of t, head of t+1
+    int32_t bid = slot_bid[a];
+    if (bid < 0 || slot_bid[b] != bid) return;
+    if (slot_fl[a] != 2 || slot_fl[b] != 1) return;  // tail started here; head ends there
+    XYZZ<F> acc = slot_pt[a];
+    xyzz_add_c(acc, slot_pt[b]);
+    buckets[bid] = acc;
+    slot_bid[a] = -1;
+    slot_bid[b] = -1;
   }
 };
 
@@ -372,6 +401,18 @@ inline int msm_pick_window(size_t n) {
   return best;
 }
 
+// window for bases that carry all W tables (one shared bucket set): fewer, larger windows pay off
+inline int msm_pick_window_full(size_t n) {
+  int best = 4; double best_cost = 1e300;
+  for (int c = 4; c <= 24; c++) {
+    double W = msm_windows(c);
+    if ((double)n * W >= 2.0e9) continue;  // entry indices are 31 bits
+    double cost = (double)n * W * 10.0 + (double)(1u << (c - 1)) * (2.0 * 14.0 + 10.0);
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
 // Runs the pipeline; result (XYZZ) written to d_out (device).  `tab` holds g.T tables of g.nbase points.
 template <class F>
 int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scalars, int mont, XYZZ<F>* d_out) {
@@ -386,7 +427,7 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   uint32_t L = 32;
   while (L > 2 && max_ent / L < (size_t)ctx->sm_count * 1024) L >>= 1;
   const size_t T1 = (max_ent + L - 1) / L;
-  const uint32_t CF = 16;  // slots merged per combine thread
+  const uint32_t CF = 64;  // slots merged per combine thread (most are empty after the pair merge)
 
   uint32_t* count = ar.take<uint32_t>((size_t)nb + 1);
   uint32_t* off = ar.take<uint32_t>((size_t)nb + 1);
@@ -410,6 +451,8 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   PS_LAUNCH(MsmScatterK, st, g.n, g, d_scalars, mont, (const uint32_t*)off, (const uint32_t*)ranks, ent);
   PS_TRY(ctx_event(ctx, 1));
   PS_LAUNCH(MsmAccumK<F>, st, T1, nb, L, tab, (const uint32_t*)ent, (const uint32_t*)off, buckets, sp[0], sb[0], sf[0]);
+  PS_TRY(ctx_event(ctx, 2));
+  PS_LAUNCH(MsmPairMergeK<F>, st, T1, (uint32_t)T1, buckets, sp[0], sb[0], (const uint8_t*)sf[0]);
   {
     size_t n_in = slots_a;
     int cur = 0;
@@ -423,7 +466,7 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
       cur ^= 1;
     }
   }
-  PS_TRY(ctx_event(ctx, 2));
+  PS_TRY(ctx_event(ctx, 3));
   // bucket reduction
   {
     // first level: aim at >= 64K threads, group size a power of two
@@ -442,7 +485,7 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
     while ((1u << log_len) < gsz) log_len++;
     int cur = 0;
     while (n_in > 1) {
-      uint32_t f = n_in < 16 ? n_in : 16;
+      uint32_t f = n_in < 4 ? n_in : 4;  // short serial chains: the levels are latency-, not work-bound
       uint32_t n_out = n_in / f;  // both powers of two
       PS_LAUNCH(MsmReduceK<F>, st, (size_t)g.S * n_out, n_in, n_out, f, log_len, (const XYZZ<F>*)accv[cur],
                 (const XYZZ<F>*)runv[cur], accv[cur ^ 1], runv[cur ^ 1]);
@@ -454,7 +497,7 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
     }
     PS_LAUNCH(MsmFinalK<F>, st, 1, g.S, g.c * g.T, (const XYZZ<F>*)accv[cur], d_out);
   }
-  PS_TRY(ctx_event(ctx, 3));
+  PS_TRY(ctx_event(ctx, 4));
   ctx->ev_valid = true;
   return PS_OK;
 }

@@ -35,20 +35,21 @@ def main():
             n = 1 << log_n
             ks = b"".join(rng.randrange(1, R).to_bytes(32, "big") for _ in range(n))
             sc = b"".join(rng.randrange(R).to_bytes(32, "big") for _ in range(n))
-            t0 = time.time()
-            bases = be.bases_from_scalars(group, ks)
-            be.sync()
-            t_bases = time.time() - t0
-            be.msm(bases, sc)  # warm-up
-            t0 = time.time()
-            be.msm(bases, sc)
-            wall = time.time() - t0
-            tm = be.msm_timing()
-            out["msm_%s_%d" % (gname, log_n)] = dict(tm, wall_ms=wall * 1e3, bases_s=t_bases)
-            print("msm %s 2^%d: total %.3f ms (sort %.3f, accum %.3f, reduce %.3f) wall %.1f ms; %.3e pts/s; bases %.2fs" % (
-                gname, log_n, tm["total_ms"], tm["sort_ms"], tm["accumulate_ms"], tm["reduce_ms"], wall * 1e3,
-                n / (tm["total_ms"] * 1e-3), t_bases), flush=True)
-            bases.close()
+            for cfg, wb, tables in (("T1", 0, 1), ("full", 0, -1)):
+                t0 = time.time()
+                bases = be.bases_from_scalars(group, ks, wb, tables)
+                be.sync()
+                t_bases = time.time() - t0
+                be.msm(bases, sc)  # warm-up
+                t0 = time.time()
+                be.msm(bases, sc)
+                wall = time.time() - t0
+                tm = be.msm_timing()
+                out["msm_%s_%d_%s" % (gname, log_n, cfg)] = dict(tm, wall_ms=wall * 1e3, bases_s=t_bases)
+                print("msm %s 2^%d %-4s: total %.3f ms (sort %.3f, accum %.3f, comb %.3f, reduce %.3f) wall %.1f ms; %.3e pts/s; bases %.2fs" % (
+                    gname, log_n, cfg, tm["total_ms"], tm["sort_ms"], tm["accumulate_ms"], tm["combine_ms"], tm["reduce_ms"], wall * 1e3,
+                    n / (tm["total_ms"] * 1e-3), t_bases), flush=True)
+                bases.close()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "probe.json"), "w") as f:
         json.dump(out, f, indent=1)
