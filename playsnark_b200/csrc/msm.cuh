@@ -15,7 +15,8 @@
 //                     balance whatever the scalar distribution), adds the gathered affine bases into
 //                     an XYZZ accumulator (madd, 8M+2S), writes buckets that lie wholly inside its
 //                     range and emits at most two boundary partials
-//   5. MsmCombineK    log-depth merge of the boundary partials (XYZZ + XYZZ)
+//   5. MsmRunMergeK / MsmCombineK   merge of the boundary partials (XYZZ + XYZZ): short runs in one
+//                     parallel pass, the rest log-depth
 //   6. MsmReduceFirstK / MsmReduceK   sum_d d * B_d per bucket set as a tree of (acc, run) pairs
 //   7. MsmFinalK      Horner over the bucket sets (c*T doublings between sets)
 // With T precomputed tables (2^(c t) * P_i, t < T) the windows w = s*T + t share bucket set s.
@@ -178,25 +179,32 @@ struct MsmAccumK {
   }
 };
 
-// Most boundary partials come in pairs: the tail of chunk t (its last bucket runs on) and the head
-// of chunk t+1 (the same bucket ends there).  One fully parallel pass adds such pairs straight into
-// the bucket and blanks the two slots; only buckets spanning three or more chunks stay for the
-// log-depth merge below.
+// Boundary partials of one bucket sit in consecutive chunks: the tail of the chunk where the bucket
+// starts, the heads of the chunks it covers entirely, and the head of the chunk where it ends.  The
+// thread that owns the starting tail walks that run (up to RUN_MAX chunks), adds it up into the
+// bucket and blanks the slots; every run is owned by exactly one thread, so the pass is fully
+// parallel.  Longer runs (heavily repeated scalars) are left to the log-depth merge below.
 template <class F>
-struct MsmPairMergeK {
+struct MsmRunMergeK {
   static constexpr int BLOCK = 128;
+  static constexpr uint32_t RUN_MAX = 8;
   PS_DEV static void run(uint32_t t, uint32_t n_chunks, XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid,
                          const uint8_t* slot_fl) {
-    if (t + 1 >= n_chunks) return;
-    const uint32_t a = 2 * t + 1, b = 2 * t + 2;  // tail of t, head of t+1
+    const uint32_t a = 2 * t + 1;  // tail of chunk t
     int32_t bid = slot_bid[a];
-    if (bid < 0 || slot_bid[b] != bid) return;
-    if (slot_fl[a] != 2 || slot_fl[b] != 1) return;  // tail started here; head ends there
+    if (bid < 0 || slot_fl[a] != 2) return;  // not the start of a run
+    uint32_t len = 0;                         // number of following chunks in the run
+    for (uint32_t j = 1; j <= RUN_MAX && t + j < n_chunks; j++) {
+      uint32_t h = 2 * (t + j);
+      if (slot_bid[h] != bid) return;         // malformed / not ours: leave untouched
+      if (slot_fl[h] == 1) { len = j; break; }
+    }
+    if (!len) return;
     XYZZ<F> acc = slot_pt[a];
-    xyzz_add_c(acc, slot_pt[b]);
+    for (uint32_t j = 1; j <= len; j++) xyzz_add_c(acc, slot_pt[2 * (t + j)]);
     buckets[bid] = acc;
     slot_bid[a] = -1;
-    slot_bid[b] = -1;
+    for (uint32_t j = 1; j <= len; j++) slot_bid[2 * (t + j)] = -1;
   }
 };
 
@@ -424,7 +432,9 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   if (max_ent >= 0xFFFFFFFFull) return PS_ERR_UNSUPPORTED;
 
   // entries per accumulate thread: keep >= ~8 waves of threads when the problem is large enough
+  // about a million accumulate threads for large inputs (fewer boundary partials), never below 8 waves
   uint32_t L = 32;
+  while (L < 256 && max_ent / L > ((size_t)1 << 20)) L <<= 1;
   while (L > 2 && max_ent / L < (size_t)ctx->sm_count * 1024) L >>= 1;
   const size_t T1 = (max_ent + L - 1) / L;
   const uint32_t CF = 64;  // slots merged per combine thread (most are empty after the pair merge)
@@ -452,7 +462,7 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   PS_TRY(ctx_event(ctx, 1));
   PS_LAUNCH(MsmAccumK<F>, st, T1, nb, L, tab, (const uint32_t*)ent, (const uint32_t*)off, buckets, sp[0], sb[0], sf[0]);
   PS_TRY(ctx_event(ctx, 2));
-  PS_LAUNCH(MsmPairMergeK<F>, st, T1, (uint32_t)T1, buckets, sp[0], sb[0], (const uint8_t*)sf[0]);
+  PS_LAUNCH(MsmRunMergeK<F>, st, T1, (uint32_t)T1, buckets, sp[0], sb[0], (const uint8_t*)sf[0]);
   {
     size_t n_in = slots_a;
     int cur = 0;
