@@ -51,6 +51,7 @@ SYMBOLS = [
     ("ps_bench_intpipe", _I, [_P, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("ps_bench_fieldmul", _I, [_P, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("ps_last_msm_timing", _I, [_P, C.POINTER(C.c_float)]),
+    ("ps_last_prove_timing", _I, [_P, C.POINTER(C.c_float)]),
 ]
 
 

@@ -25,12 +25,25 @@ Vector = List[int]
 Poly = List[int]
 
 
-def _fr_bytes(vals: Sequence[int]) -> bytes:
+def _fr_bytes(vals) -> bytes:
+    """Fr values (ints, reduced mod r like Value.ToFieldElement) -> 32-byte big-endian rows; byte strings
+    that are already in wire format pass through."""
+    if isinstance(vals, (bytes, bytearray, memoryview)):
+        return bytes(vals)
     return b"".join((int(v) % R).to_bytes(32, "big") for v in vals)
 
 
 def _fr_list(buf: bytes) -> List[int]:
     return [int.from_bytes(buf[i:i + 32], "big") for i in range(0, len(buf), 32)]
+
+
+def _join(x) -> bytes:
+    """a list of per-point byte strings or one contiguous blob"""
+    return bytes(x) if isinstance(x, (bytes, bytearray, memoryview)) else b"".join(x)
+
+
+def _count(x, per: int) -> int:
+    return len(x) // per if isinstance(x, (bytes, bytearray, memoryview)) else len(x)
 
 
 class Bases:
@@ -42,12 +55,13 @@ class Bases:
     def __len__(self):
         return self.backend.lib.ps_bases_len(self.handle)
 
-    def export(self, first=0, count=None, fmt=L.PS_FMT_COMPRESSED) -> List[bytes]:
+    def export(self, first=0, count=None, fmt=L.PS_FMT_COMPRESSED, blob: bool = False):
         n = len(self) - first if count is None else count
         per = {(1, 0): 48, (1, 1): 96, (2, 0): 96, (2, 1): 192}[(self.group, fmt)]
         buf = C.create_string_buffer(max(1, n * per))
         self.backend._check(self.backend.lib.ps_bases_export(self.backend.ctx, self.handle, first, n, fmt, buf))
-        return [buf.raw[i * per:(i + 1) * per] for i in range(n)]
+        raw = buf.raw[:n * per]
+        return raw if blob else [raw[i * per:(i + 1) * per] for i in range(n)]
 
     def close(self):
         if self.handle:
@@ -112,6 +126,11 @@ class Backend:
             raise ValueError("mismatch of length between poly %d and blinded eval points %d" % (n, len(bases)))
         self._check(st)
         return out.raw
+
+    def prove_timing(self):
+        t = (C.c_float * 6)()
+        self._check(self.lib.ps_last_prove_timing(self.ctx, t))
+        return {"quotient_ms": t[0], "msm_a_ms": t[1], "msm_c_ms": t[2], "msm_b_g2_ms": t[3], "encode_ms": t[4], "total_ms": t[5]}
 
     def msm_timing(self):
         t = (C.c_float * 5)()
@@ -205,9 +224,59 @@ class QAP:
         return Quotient(self, sol, backend)
 
 
-def _sanity(q: QAP, sol: Vector):
+@dataclass
+class SparseQAP:
+    """The same object as QAP for circuits whose dense polynomials cannot be materialised
+    (3*nbVars*nbGates*32 bytes): the R1CS gate matrices in CSR form (r1cs.go:96-101 holds them
+    dense); the per-variable polynomials stay implicit as interpolants on {1..nbGates}
+    (qap.go:67-93).  nbGates must be a power of two.  Each matrix is (row_ptr, col, val) with
+    val as Fr integers."""
+    nbVars: int
+    nbIO: int
+    nbGates: int
+    left: tuple
+    right: tuple
+    out: tuple
+    _dev: object = None
+
+    @staticmethod
+    def from_dense_rows(nbVars, nbIO, left, right, out):
+        """rows of Go ints (Matrix, algebra.go:15) -> CSR; Value.ToFieldElement on the entries"""
+        def csr(m):
+            rp, col, val = [0], [], []
+            for row in m:
+                for j, v in enumerate(row):
+                    if v:
+                        col.append(j); val.append(int(v) % R)
+                rp.append(len(col))
+            return rp, col, val
+        return SparseQAP(nbVars, nbIO, len(left), csr(left), csr(right), csr(out))
+
+    def _resident(self, backend: Backend):
+        if self._dev is None or self._dev[0] is not backend:
+            import array
+            h = C.c_void_p()
+            keep, args = [], []
+            for rp, col, val in (self.left, self.right, self.out):
+                if len(rp) != self.nbGates + 1:
+                    raise ValueError("row_ptr must have nbGates+1 entries")
+                a_rp = (C.c_uint32 * len(rp))(*rp)
+                a_col = (C.c_uint32 * max(1, len(col)))(*col)
+                b_val = _fr_bytes(val) or b"\0"
+                keep += [a_rp, a_col, b_val]
+                args += [C.cast(a_rp, C.c_void_p), C.cast(a_col, C.c_void_p), C.cast(C.c_char_p(b_val), C.c_void_p)]
+            backend._check(backend.lib.ps_qap_load_r1cs(backend.ctx, self.nbGates, self.nbVars, self.nbIO, *args, C.byref(h)))
+            self._dev = (backend, h)
+        return self._dev[1]
+
+    def Quotient(self, sol: Vector, backend: Optional[Backend] = None) -> Poly:
+        return Quotient(self, sol, backend)
+
+
+def _sanity(q, sol):
     """QAP.sanityCheck, qap.go:177-189."""
-    if len(sol) != q.nbVars:
+    nsol = len(sol) // 32 if isinstance(sol, (bytes, bytearray, memoryview)) else len(sol)
+    if nsol != q.nbVars:
         raise ValueError("different number of solution variables than left polynomials")
 
 
@@ -245,17 +314,19 @@ class Groth16Setup:
     Xi2: List[bytes]
     IoLP: List[bytes] = field(default_factory=list)   # verifier side, carried for completeness
     Gamma: bytes = b""
+    fmt: int = L.PS_FMT_COMPRESSED    # PS_FMT_AFFINE for bulk keys (every point field then uncompressed)
     _dev: object = None
 
     def _resident(self, backend: Backend):
         if self._dev is None or self._dev[0] is not backend:
-            n = len(self.Xi)
-            if len(self.Xi2) != n or len(self.XiT) != n - 1:
+            g1b, g2b = (48, 96) if self.fmt == L.PS_FMT_COMPRESSED else (96, 192)
+            n = _count(self.Xi, g1b)
+            if _count(self.Xi2, g2b) != n or _count(self.XiT, g1b) != n - 1:
                 raise ValueError("mismatch of length between poly and blinded eval points")
             h = C.c_void_p()
-            j = b"".join
+            j = _join
             backend._check(backend.lib.ps_g16_key_load(
-                backend.ctx, n, len(self.NioLP), L.PS_FMT_COMPRESSED, j(self.Xi), j(self.Xi2), j(self.XiT), j(self.NioLP),
+                backend.ctx, n, _count(self.NioLP, g1b), self.fmt, j(self.Xi), j(self.Xi2), j(self.XiT), j(self.NioLP) or b"\0",
                 self.Alpha, self.Beta, self.Delta, self.Beta2, self.Delta2, C.byref(h)))
             self._dev = (backend, h)
         return self._dev[1]

@@ -5,6 +5,7 @@
 #include "microbench.cuh"
 #include "msm.cuh"
 #include "poly.cuh"
+#include "interp.cuh"
 
 #include <new>
 
@@ -233,8 +234,32 @@ int check_err_flag(ps_ctx* ctx, const uint32_t* d_err, int code) {
 
 // witness -> device Montgomery; a, b, c, h on the device (n' entries each)
 struct QuotientBufs { Fr *w, *a, *b, *c, *h; uint32_t* flag; uint32_t* enc_err; };
+int run_quotient_sparse(ps_ctx* ctx, const ps_qap* q, const uint8_t* witness_be, QuotientBufs* o) {
+  const SparseQap* sq = (const SparseQap*)q->sparse;
+  const uint32_t n = (uint32_t)q->n;
+  ps_stream_t st = ctx->stream;
+  uint32_t* d_w = nullptr;
+  PS_TRY(stage_scalars(ctx, witness_be, q->m, 1, &d_w, &o->enc_err));
+  o->w = (Fr*)d_w;
+  Fr* ev = ctx->arena.take<Fr>((size_t)3 * n);
+  Fr* coef = ctx->arena.take<Fr>((size_t)3 * n);
+  o->h = ctx->arena.take<Fr>(n);
+  o->flag = ctx->arena.take<uint32_t>(1);
+  uint32_t* flag2 = ctx->arena.take<uint32_t>(1);
+  if (!ev || !coef || !o->h || !o->flag || !flag2) return PS_ERR_ALLOC;
+  PS_TRY(dev_memset(o->flag, 0, 4, st));
+  PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
+            (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
+            (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, (const Fr*)o->w, ev);
+  PS_LAUNCH(GateCheckK, st, n, n, (const Fr*)ev, o->flag);
+  PS_TRY(interpolate3(ctx, sq, n, q->log_np, ev, coef));
+  o->a = coef; o->b = coef + n; o->c = coef + 2 * (size_t)n;
+  PS_TRY(quotient_from_abc(ctx, q, o->a, o->b, o->c, o->h, flag2, false));
+  return PS_OK;
+}
+
 int run_quotient(ps_ctx* ctx, const ps_qap* q, const uint8_t* witness_be, QuotientBufs* o) {
-  if (!q->dense) return PS_ERR_UNSUPPORTED;
+  if (!q->dense) return run_quotient_sparse(ctx, q, witness_be, o);
   const uint32_t np = 1u << q->log_np;
   uint32_t* d_w = nullptr;
   PS_TRY(stage_scalars(ctx, witness_be, q->m, 1, &d_w, &o->enc_err));
@@ -323,6 +348,11 @@ int ps_ctx_create(int device, ps_ctx** out) {
     PS_CUDA_TRY(cudaEventCreate(&e));
     ctx->ev[i] = e;
   }
+  for (int i = 0; i < 6; i++) {
+    cudaEvent_t e;
+    PS_CUDA_TRY(cudaEventCreate(&e));
+    ctx->evp[i] = e;
+  }
 #endif
   ctx->arena.stream = ctx->stream;
   *out = ctx;
@@ -354,6 +384,7 @@ void ps_ctx_destroy(ps_ctx* ctx) {
   dev_free(ctx->fixed_base[1]);
 #if PS_GPU
   for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy((cudaEvent_t)ctx->ev[i]);
+  for (int i = 0; i < 6; i++) if (ctx->evp[i]) cudaEventDestroy((cudaEvent_t)ctx->evp[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
 #endif
   delete ctx;
@@ -481,6 +512,19 @@ int ps_last_msm_timing(ps_ctx* ctx, float out_ms[5]) {
   return PS_OK;
 }
 
+int ps_last_prove_timing(ps_ctx* ctx, float out_ms[6]) {
+  if (!ctx || !out_ms) return PS_ERR_ARG;
+  for (int i = 0; i < 6; i++) out_ms[i] = 0.f;
+#if PS_GPU
+  if (!ctx->evp_valid) return PS_ERR_ARG;
+  PS_CUDA_TRY(cudaEventSynchronize((cudaEvent_t)ctx->evp[5]));
+  for (int i = 0; i < 5; i++)
+    PS_CUDA_TRY(cudaEventElapsedTime(&out_ms[i], (cudaEvent_t)ctx->evp[i], (cudaEvent_t)ctx->evp[i + 1]));
+  PS_CUDA_TRY(cudaEventElapsedTime(&out_ms[5], (cudaEvent_t)ctx->evp[0], (cudaEvent_t)ctx->evp[5]));
+#endif
+  return PS_OK;
+}
+
 // ---- NTT --------------------------------------------------------------------------------------------
 int ps_ntt_fr(ps_ctx* ctx, uint8_t* data_be, unsigned log_n, int inverse, const uint8_t* coset_be) {
   if (!data_be || log_n > 28) return PS_ERR_ARG;
@@ -555,13 +599,60 @@ int ps_qap_load_dense(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, c
   return PS_OK;
 }
 
-int ps_qap_load_r1cs(ps_ctx*, size_t, size_t, size_t, const uint32_t*, const uint32_t*, const uint8_t*,
-                     const uint32_t*, const uint32_t*, const uint8_t*, const uint32_t*, const uint32_t*,
-                     const uint8_t*, ps_qap**) {
-  return PS_ERR_UNSUPPORTED;
+int ps_qap_load_r1cs(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, const uint32_t* l_row_ptr, const uint32_t* l_col,
+                     const uint8_t* l_val, const uint32_t* r_row_ptr, const uint32_t* r_col, const uint8_t* r_val,
+                     const uint32_t* o_row_ptr, const uint32_t* o_col, const uint8_t* o_val, ps_qap** qap) {
+  if (!qap || !l_row_ptr || !r_row_ptr || !o_row_ptr || n_gates < 2 || n_vars < 1 || n_io > n_vars) return PS_ERR_ARG;
+  if (n_gates & (n_gates - 1)) return PS_ERR_UNSUPPORTED;  // the interpolation tree needs n = 2^k
+  if (n_gates > (1u << 26) || n_vars > (1u << 28)) return PS_ERR_UNSUPPORTED;
+  PS_TRY(begin_call(ctx));
+  ps_stream_t st = ctx->stream;
+  ps_qap* q = new (std::nothrow) ps_qap();
+  SparseQap* sq = new (std::nothrow) SparseQap();
+  if (!q || !sq) { delete q; delete sq; return PS_ERR_ALLOC; }
+  q->n = n_gates; q->m = n_vars; q->n_io = n_io; q->dense = false; q->sparse = sq;
+  int k = 0;
+  while (((size_t)1 << k) < n_gates) k++;
+  const uint32_t* rps[3] = {l_row_ptr, r_row_ptr, o_row_ptr};
+  const uint32_t* cols[3] = {l_col, r_col, o_col};
+  const uint8_t* vals[3] = {l_val, r_val, o_val};
+  int rc = PS_OK;
+  uint32_t* d_err = ctx->arena.take<uint32_t>(1);
+  if (!d_err) rc = PS_ERR_ALLOC;
+  if (rc == PS_OK) rc = dev_memset(d_err, 0, 4, st);
+  for (int i = 0; i < 3 && rc == PS_OK; i++) {
+    size_t nnz = rps[i][n_gates];
+    if (rps[i][0] != 0 || (nnz && (!cols[i] || !vals[i]))) { rc = PS_ERR_ARG; break; }
+    for (size_t j = 0; j < n_gates && rc == PS_OK; j++) if (rps[i][j] > rps[i][j + 1]) rc = PS_ERR_ARG;
+    for (size_t t = 0; t < nnz && rc == PS_OK; t++) if (cols[i][t] >= n_vars) rc = PS_ERR_ARG;
+    if (rc != PS_OK) break;
+    CsrDev& m = sq->mat[i];
+    m.nnz = nnz;
+    rc = dev_alloc((void**)&m.row_ptr, (n_gates + 1) * 4);
+    if (rc == PS_OK) rc = dev_alloc((void**)&m.col, nnz * 4);
+    if (rc == PS_OK) rc = dev_alloc((void**)&m.val, nnz * sizeof(Fr));
+    if (rc == PS_OK) rc = dev_h2d(m.row_ptr, rps[i], (n_gates + 1) * 4, st);
+    if (rc == PS_OK && nnz) rc = dev_h2d(m.col, cols[i], nnz * 4, st);
+    uint8_t* d_bytes = ctx->arena.take<uint8_t>(nnz * 32);
+    if (rc == PS_OK && !d_bytes) rc = PS_ERR_ALLOC;
+    if (rc == PS_OK && nnz) rc = dev_h2d(d_bytes, vals[i], nnz * 32, st);
+    if (rc == PS_OK) rc = ps_launch<FrFromBytesK>(st, nnz, (const uint8_t*)d_bytes, (uint32_t*)m.val, 1, d_err);
+  }
+  Fr* d_z = ctx->arena.take<Fr>(n_gates + 1);
+  if (rc == PS_OK && !d_z) rc = PS_ERR_ALLOC;
+  if (rc == PS_OK) rc = inv_zprime_build(ctx, sq, (uint32_t)n_gates);
+  if (rc == PS_OK) rc = ztree_build(ctx, sq, (uint32_t)n_gates, k, d_z);
+  if (rc == PS_OK) rc = qap_prepare_tables(ctx, q, d_z);
+  if (rc == PS_OK) rc = check_err_flag(ctx, d_err, PS_ERR_ENCODING);
+  if (rc != PS_OK) { ps_qap_free(q); return rc; }
+  *qap = q;
+  return PS_OK;
 }
 
-void ps_qap_free(ps_qap* qap) { qap_release(qap); }
+void ps_qap_free(ps_qap* qap) {
+  if (qap && qap->sparse) { ((SparseQap*)qap->sparse)->release(); delete (SparseQap*)qap->sparse; qap->sparse = nullptr; }
+  qap_release(qap);
+}
 
 int ps_quotient(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_be, uint8_t* out_h, uint8_t* out_abc) {
   if (!qap || !witness_be || !out_h) return PS_ERR_ARG;
@@ -624,7 +715,10 @@ int ps_g16_prove(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const ui
   ps_stream_t st = ctx->stream;
   const size_t n = qap->n, nio = qap->n_io, diff = qap->m - qap->n_io;
   QuotientBufs qb;
+  ctx->evp_valid = false;
+  PS_TRY(ctx_prove_event(ctx, 0));
   PS_TRY(run_quotient(ctx, qap, witness_be, &qb));
+  PS_TRY(ctx_prove_event(ctx, 1));
   // r, s
   uint8_t rs_bytes[64];
   memcpy(rs_bytes, r_be, 32); memcpy(rs_bytes + 32, s_be, 32);
@@ -657,11 +751,16 @@ int ps_g16_prove(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const ui
   PS_LAUNCH(FrAxpbyK, st, n, s, (const Fr*)qb.a, r, (const Fr*)qb.b, scC + nio + (n - 1));
   PS_LAUNCH(FrSet3K, st, 3, s, r, rs, 3, scC + nio + (n - 1) + n);
   PS_TRY(msm_on_bases<Fp>(ctx, key->A, 0, (const uint32_t*)scA, n + 2, 1, resG1));
+  PS_TRY(ctx_prove_event(ctx, 2));
   PS_TRY(msm_on_bases<Fp>(ctx, key->C, 0, (const uint32_t*)scC, nio + (n - 1) + n + 3, 1, resG1 + 1));
+  PS_TRY(ctx_prove_event(ctx, 3));
   PS_TRY(msm_on_bases<Fp2>(ctx, key->B, 0, (const uint32_t*)scB, n + 2, 1, resG2));
+  PS_TRY(ctx_prove_event(ctx, 4));
   uint8_t ac[96];
   PS_TRY(encode_points<Fp>(ctx, resG1, 2, ac));
   PS_TRY(encode_points<Fp2>(ctx, resG2, 1, outB));
+  PS_TRY(ctx_prove_event(ctx, 5));
+  ctx->evp_valid = true;
   if (out_h) PS_TRY(export_fr(ctx, qb.h, n - 1, out_h));
   PS_TRY(check_err_flag(ctx, qb.enc_err, PS_ERR_ENCODING));
   PS_TRY(check_err_flag(ctx, qb.flag, PS_ERR_REMAINDER));

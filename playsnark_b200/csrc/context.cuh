@@ -14,6 +14,9 @@ struct ps_ctx {
   // phase events of the last MSM (cudaEvent_t): start, sorted, accumulated, combined, reduced
   void* ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
+  // phase events of the last Groth16 prove: start, quotient done, MSM A, MSM C, MSM B, encoded
+  void* evp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool evp_valid = false;
 };
 
 namespace ps {
@@ -27,6 +30,14 @@ inline int ctx_ntt_tables(ps_ctx* ctx, int log_n, const NttTables** out) {
 inline int ctx_event(ps_ctx* ctx, int i) {
 #if PS_GPU
   if (ctx->ev[i]) PS_CUDA_TRY(cudaEventRecord((cudaEvent_t)ctx->ev[i], ctx->stream));
+#else
+  (void)ctx; (void)i;
+#endif
+  return PS_OK;
+}
+inline int ctx_prove_event(ps_ctx* ctx, int i) {
+#if PS_GPU
+  if (ctx->evp[i]) PS_CUDA_TRY(cudaEventRecord((cudaEvent_t)ctx->evp[i], ctx->stream));
 #else
   (void)ctx; (void)i;
 #endif

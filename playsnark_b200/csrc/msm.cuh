@@ -432,9 +432,11 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   if (max_ent >= 0xFFFFFFFFull) return PS_ERR_UNSUPPORTED;
 
   // entries per accumulate thread: keep >= ~8 waves of threads when the problem is large enough
-  // about a million accumulate threads for large inputs (fewer boundary partials), never below 8 waves
+  // entries per accumulate thread: at least twice the average bucket so that most buckets lie inside
+  // one thread's range (few boundary partials), while keeping >= ~200K threads in flight
   uint32_t L = 32;
-  while (L < 256 && max_ent / L > ((size_t)1 << 20)) L <<= 1;
+  const size_t avg_bucket = max_ent / nb + 1;
+  while (L < 512 && L < 2 * avg_bucket && max_ent / (2 * L) >= 200000) L <<= 1;
   while (L > 2 && max_ent / L < (size_t)ctx->sm_count * 1024) L >>= 1;
   const size_t T1 = (max_ent + L - 1) / L;
   const uint32_t CF = 64;  // slots merged per combine thread (most are empty after the pair merge)

@@ -123,33 +123,40 @@ inline Fr fr_root_of_unity(int log_n) {
   return w;
 }
 
-// forward DIF on n = 2^log_n elements (natural -> bit-reversed); tw[i] = omega_n^i, i < n/2
-inline int ntt_forward(ps_stream_t st, Fr* a, int log_n, const Fr* tw) {
-  uint32_t n = 1u << log_n;
+// Batched forward DIF: `len` elements = len / 2^log_block independent transforms of size 2^log_block
+// laid out back to back (natural -> bit-reversed inside each block).  tw[i] = omega_{n_tw}^i for
+// i < n_tw/2 with n_tw >= 2^log_block (a block transform is the tail of a larger transform's stages).
+inline int ntt_forward_blocks(ps_stream_t st, Fr* a, size_t len, int log_block, const Fr* tw, uint32_t n_tw) {
   int done = 0;
-  while (done < log_n) {
-    int r = log_n - done >= 3 ? 3 : log_n - done;
-    uint32_t B = n >> done;
-    if (r == 3) PS_LAUNCH(NttDifK<3>, st, n >> 3, a, n, B, tw);
-    else if (r == 2) PS_LAUNCH(NttDifK<2>, st, n >> 2, a, n, B, tw);
-    else PS_LAUNCH(NttDifK<1>, st, n >> 1, a, n, B, tw);
+  while (done < log_block) {
+    int r = log_block - done >= 3 ? 3 : log_block - done;
+    uint32_t B = 1u << (log_block - done);
+    if (r == 3) PS_LAUNCH(NttDifK<3>, st, len >> 3, a, n_tw, B, tw);
+    else if (r == 2) PS_LAUNCH(NttDifK<2>, st, len >> 2, a, n_tw, B, tw);
+    else PS_LAUNCH(NttDifK<1>, st, len >> 1, a, n_tw, B, tw);
     done += r;
   }
   return PS_OK;
 }
-// inverse DIT (bit-reversed -> natural), WITHOUT the 1/n factor; tw_inv[i] = omega_n^-i
-inline int ntt_inverse_unscaled(ps_stream_t st, Fr* a, int log_n, const Fr* tw_inv) {
-  uint32_t n = 1u << log_n;
+// Batched inverse DIT (bit-reversed -> natural inside each block), WITHOUT the 1/2^log_block factor.
+inline int ntt_inverse_blocks_unscaled(ps_stream_t st, Fr* a, size_t len, int log_block, const Fr* tw_inv, uint32_t n_tw) {
   int done = 0;
-  while (done < log_n) {
-    int r = log_n - done >= 3 ? 3 : log_n - done;
+  while (done < log_block) {
+    int r = log_block - done >= 3 ? 3 : log_block - done;
     uint32_t B0 = 1u << done;
-    if (r == 3) PS_LAUNCH(NttDitK<3>, st, n >> 3, a, n, B0, tw_inv);
-    else if (r == 2) PS_LAUNCH(NttDitK<2>, st, n >> 2, a, n, B0, tw_inv);
-    else PS_LAUNCH(NttDitK<1>, st, n >> 1, a, n, B0, tw_inv);
+    if (r == 3) PS_LAUNCH(NttDitK<3>, st, len >> 3, a, n_tw, B0, tw_inv);
+    else if (r == 2) PS_LAUNCH(NttDitK<2>, st, len >> 2, a, n_tw, B0, tw_inv);
+    else PS_LAUNCH(NttDitK<1>, st, len >> 1, a, n_tw, B0, tw_inv);
     done += r;
   }
   return PS_OK;
+}
+// single transform of size n = 2^log_n with its own table
+inline int ntt_forward(ps_stream_t st, Fr* a, int log_n, const Fr* tw) {
+  return ntt_forward_blocks(st, a, (size_t)1 << log_n, log_n, tw, 1u << log_n);
+}
+inline int ntt_inverse_unscaled(ps_stream_t st, Fr* a, int log_n, const Fr* tw_inv) {
+  return ntt_inverse_blocks_unscaled(st, a, (size_t)1 << log_n, log_n, tw_inv, 1u << log_n);
 }
 
 // Twiddle tables for one transform size, resident on the device.

@@ -25,6 +25,7 @@ struct ps_qap {
   ps::Fr* ginv_pow = nullptr;   // g^-k / n'
   ps::Fr* zinv_coset = nullptr; // 1 / z(g * omega^k), bit-reversed order
   ps::Fr* z_plain = nullptr;    // z(omega^k), bit-reversed order
+  void* sparse = nullptr;       // ps::SparseQap* when built from a sparse R1CS (interp.cuh)
 };
 
 namespace ps {
@@ -151,7 +152,8 @@ inline int qap_prepare_tables(ps_ctx* ctx, ps_qap* q, const Fr* d_z) {
 // a, b, c: device, n' entries each (coefficients, zero padded, Montgomery).  On return `h` (n'
 // entries) holds the quotient coefficients and *d_flag is non-zero iff the remainder is non-zero.
 // a, b, c are preserved.  Scratch comes from the arena.
-inline int quotient_from_abc(ps_ctx* ctx, const ps_qap* q, const Fr* a, const Fr* b, const Fr* c, Fr* h, uint32_t* d_flag) {
+inline int quotient_from_abc(ps_ctx* ctx, const ps_qap* q, const Fr* a, const Fr* b, const Fr* c, Fr* h, uint32_t* d_flag,
+                             bool verify = true) {
   ps_stream_t st = ctx->stream;
   const uint32_t np = 1u << q->log_np;
   Arena& ar = ctx->arena;
@@ -168,6 +170,7 @@ inline int quotient_from_abc(ps_ctx* ctx, const ps_qap* q, const Fr* a, const Fr
   PS_LAUNCH(QuotientPointwiseK, st, np, (const Fr*)A, (const Fr*)B, (const Fr*)C, (const Fr*)q->zinv_coset, h);
   PS_TRY(ntt_inverse_unscaled(st, h, q->log_np, q->tabs.tw_inv));
   PS_LAUNCH(FrMulTableK, st, np, h, (const Fr*)q->ginv_pow);
+  if (!verify) return PS_OK;  // the caller has already proved divisibility (gate check of the sparse path)
   // exactness check on <omega>
   PS_LAUNCH(ScaleCopyK, st, np, a, np, (const Fr*)nullptr, A);
   PS_LAUNCH(ScaleCopyK, st, np, b, np, (const Fr*)nullptr, B);

@@ -260,3 +260,47 @@ def phgr13_circuit(be, n, seed, verify=True):
     assert pp.h == want["h"]
     if verify:
         assert O.phgr13_verify(st["VK"], oq, want, w[:oq.nb_vars - oq.nb_io])
+
+
+def sparse_quotient_vs_dense(be, n, seed):
+    """the sparse-R1CS path (SpMV + interpolation on {1..n}) against the oracle's Interpolate / Div2"""
+    r, w = H.mixed_circuit(n, seed, max(1, n // 2))
+    oq = O.to_qap(r)
+    sq = api.SparseQAP.from_dense_rows(len(r.vars), r.nb_io(), r.left, r.right, r.out)
+    h, (a, b, c) = api.Quotient(sq, w, backend=be, return_abc=True)
+    assert (a, b, c) == tuple(oq.compute_aggregate_poly(w))
+    assert h == oq.quotient(w)
+    import pytest
+    bad = list(w); bad[-1] = (bad[-1] + 1) % O.R
+    with pytest.raises(ArithmeticError, match="apocalypse"):
+        api.Quotient(sq, bad, backend=be)
+    # dense and sparse forms of the same circuit give the same proof
+    smp = O.Sampler(seed)
+    tr = O.groth16_setup(oq, smp)
+    rr, ss = smp.fr(), smp.fr()
+    mtr = H.mirror_g16_setup(tr)
+    p1 = api.Groth16Prove(mtr, H.mirror_qap(oq), w, rr, ss, backend=be)
+    p2 = api.Groth16Prove(mtr, sq, w, rr, ss, backend=be)
+    assert (p1.A, p1.B, p1.C) == (p2.A, p2.B, p2.C)
+    want = O.groth16_prove(tr, oq, w, rr, ss)
+    assert p2.A == O.g1_compress(want["A"]) and p2.B == O.g2_compress(want["B"]) and p2.C == O.g1_compress(want["C"])
+
+
+def groth16_sparse_exponent_check(be, log_n, seed):
+    """full Groth16 prove on a sparse synthetic circuit of 2^log_n gates (configs C3/C5): the proof
+    must equal the exponent-level recomputation from the toxic waste, and h must satisfy
+    h(x) z(x) = a(x) b(x) - c(x) at the toxic point."""
+    n = 1 << log_n
+    sq, wit = H.sparse_circuit(n, seed, n // 2)
+    tr, tw = H.sparse_groth16_setup(be, sq, seed)
+    smp = O.Sampler(seed + 1000)
+    r, s = smp.fr(), smp.fr()
+    pr = api.Groth16Prove(tr, sq, wit, r, s, backend=be, want_h=True)
+    A, B, Cc, (ax, bx, cx) = H.sparse_groth16_expected(sq, wit, tw, r, s)
+    assert len(pr.h) == n - 1
+    assert O.poly_eval(pr.h, tw["X"]) * tw["zx"] % O.R == (ax * bx - cx) % O.R
+    assert pr.A == A and pr.B == B and pr.C == Cc
+    import pytest
+    bad = list(wit); bad[-1] = (bad[-1] + 1) % O.R
+    with pytest.raises(ArithmeticError, match="apocalypse"):
+        api.Groth16Prove(tr, sq, bad, r, s, backend=be)

@@ -63,3 +63,10 @@ def test_readme_phgr13(be): P.readme_phgr13(be)
 def test_groth16_mixed(be): P.groth16_circuit(be, 10, seed=3)
 def test_groth16_chain_negative_witness(be): P.groth16_circuit(be, 8, seed=4, circuit="chain", verify=False)
 def test_phgr13_mixed(be): P.phgr13_circuit(be, 9, seed=6)
+
+
+@pytest.mark.parametrize("n", [4, 16])
+def test_sparse_quotient(be, n): P.sparse_quotient_vs_dense(be, n, seed=n)
+
+
+def test_sparse_groth16_exponent_check(be): P.groth16_sparse_exponent_check(be, 5, seed=8)

@@ -101,6 +101,16 @@ def test_groth16_chain_negative_witness(be): P.groth16_circuit(be, 32, seed=4, c
 def test_phgr13_mixed(be): P.phgr13_circuit(be, 20, seed=6)
 
 
+@pytest.mark.parametrize("n", [4, 16, 64])
+def test_sparse_quotient(be, n): P.sparse_quotient_vs_dense(be, n, seed=n)
+
+
+@pytest.mark.parametrize("log_n", [8, 12, 16])
+def test_sparse_groth16_exponent_check(be, log_n):
+    # config C3: 2^16 constraints, full prove (interpolation + NTT quotient + 3 MSMs), exponent-level parity
+    P.groth16_sparse_exponent_check(be, log_n, seed=log_n)
+
+
 def test_no_device_is_loud():
     lib = L.load()
     import ctypes as C
