@@ -17,7 +17,9 @@
 //                     range and emits at most two boundary partials
 //   5. MsmRunMergeK / MsmCombineK   merge of the boundary partials (XYZZ + XYZZ): short runs in one
 //                     parallel pass, the rest log-depth
-//   6. MsmReduceFirstK / MsmReduceK   sum_d d * B_d per bucket set as a tree of (acc, run) pairs
+//   6. MsmReduceFirstK / MsmReduceK   sum_d d * B_d per bucket set: running sums over small groups, 4-way
+//                     weighted merges of (acc, run) pairs, then MsmBitGatherK / MsmPairSumK /
+//                     MsmBitFinalK: a low-depth tail by binary decomposition of the weights
 //   7. MsmFinalK      Horner over the bucket sets (c*T doublings between sets)
 // With T precomputed tables (2^(c t) * P_i, t < T) the windows w = s*T + t share bucket set s.
 #pragma once
@@ -282,6 +284,59 @@ struct MsmReduceK {
   }
 };
 
+// Low-depth tail of the bucket reduction.  With G = 2^g elements (acc_j, run_j) left per set,
+//   sum_j acc_j + len * sum_j j * run_j  =  A + len * sum_{k<g} 2^k T_k ,   T_k = sum_{j : bit k of j} run_j ,
+// so the tail is g+1 independent plain sums (pairwise trees, one addition deep per launch) and a
+// short Horner, instead of a chain of weighted merges with growing doubling counts.
+// Y rows per set: row 0 = acc pairs already added, row k+1 = the run_j with bit k of j set; G/2 entries each.
+template <class F>
+struct MsmBitGatherK {
+  static constexpr int BLOCK = 64;
+  PS_DEV static void run(uint32_t tid, uint32_t G, int g, const XYZZ<F>* acc, const XYZZ<F>* run, XYZZ<F>* Y) {
+    const uint32_t half = G / 2;
+    uint32_t s = tid / ((uint32_t)(g + 1) * half), rem = tid % ((uint32_t)(g + 1) * half);
+    uint32_t r = rem / half, i = rem % half;
+    XYZZ<F> y;
+    if (r == 0) {
+      y = acc[(size_t)s * G + 2 * i];
+      xyzz_add_c(y, acc[(size_t)s * G + 2 * i + 1]);
+    } else {
+      uint32_t k = r - 1;
+      uint32_t j = ((i >> k) << (k + 1)) | (1u << k) | (i & ((1u << k) - 1));
+      y = run[(size_t)s * G + j];
+    }
+    Y[tid] = y;
+  }
+};
+// out[row][i] = in[row][2i] + in[row][2i+1];  rows of n_in entries -> rows of n_in/2
+template <class F>
+struct MsmPairSumK {
+  static constexpr int BLOCK = 64;
+  PS_DEV static void run(uint32_t tid, uint32_t n_in, const XYZZ<F>* in, XYZZ<F>* out) {
+    uint32_t half = n_in / 2;
+    uint32_t row = tid / half, i = tid % half;
+    XYZZ<F> y = in[(size_t)row * n_in + 2 * i];
+    xyzz_add_c(y, in[(size_t)row * n_in + 2 * i + 1]);
+    out[tid] = y;
+  }
+};
+// per set: R = sum_k 2^k T_k (Horner), out = A + 2^log_len R;  Y holds g+1 single-entry rows per set
+template <class F>
+struct MsmBitFinalK {
+  static constexpr int BLOCK = 32;
+  PS_DEV static void run(uint32_t s, int g, int log_len, const XYZZ<F>* Y, XYZZ<F>* out) {
+    const XYZZ<F>* row = Y + (size_t)s * (g + 1);
+    XYZZ<F> r = XYZZ<F>::inf();
+    for (int k = g - 1; k >= 0; k--) {
+      r = xyzz_dbl_c(r);
+      xyzz_add_c(r, row[k + 1]);
+    }
+    for (int d = 0; d < log_len; d++) r = xyzz_dbl_c(r);
+    xyzz_add_c(r, row[0]);
+    out[s] = r;
+  }
+};
+
 // Horner over the bucket sets: R = sum_s 2^(shift*s) * set[s]; optionally adds into *out.
 template <class F>
 struct MsmFinalK {
@@ -432,12 +487,14 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   if (max_ent >= 0xFFFFFFFFull) return PS_ERR_UNSUPPORTED;
 
   // entries per accumulate thread: keep >= ~8 waves of threads when the problem is large enough
-  // entries per accumulate thread: at least twice the average bucket so that most buckets lie inside
-  // one thread's range (few boundary partials), while keeping >= ~200K threads in flight
-  uint32_t L = 32;
+  // entries per accumulate thread: about one average bucket or more, so that a bucket spans at most
+  // two or three threads (few boundary partials, short merge runs); twice that when the input is
+  // large enough to keep > 400K threads; never so long that fewer than ~24K threads remain.
   const size_t avg_bucket = max_ent / nb + 1;
-  while (L < 512 && L < 2 * avg_bucket && max_ent / (2 * L) >= 200000) L <<= 1;
-  while (L > 2 && max_ent / L < (size_t)ctx->sm_count * 1024) L >>= 1;
+  uint32_t L = 8;
+  while (L < 512 && L < avg_bucket) L <<= 1;
+  if (L < 512 && max_ent / (2 * (size_t)L) >= 400000) L <<= 1;
+  while (L > 8 && max_ent / L < 24576) L >>= 1;
   const size_t T1 = (max_ent + L - 1) / L;
   const uint32_t CF = 64;  // slots merged per combine thread (most are empty after the pair merge)
 
@@ -481,7 +538,7 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   PS_TRY(ctx_event(ctx, 3));
   // bucket reduction
   {
-    // first level: aim at >= 64K threads, group size a power of two
+    // first level: group size a power of two, about 128K threads
     uint32_t gsz = 1;
     while ((uint64_t)g.S * (g.D / gsz) > 131072 && gsz < g.D) gsz <<= 1;
     if (gsz < 2 && g.D >= 2) gsz = 2;
@@ -496,18 +553,35 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
     int log_len = 0;
     while ((1u << log_len) < gsz) log_len++;
     int cur = 0;
-    while (n_in > 1) {
-      uint32_t f = n_in < 4 ? n_in : 4;  // short serial chains: the levels are latency-, not work-bound
-      uint32_t n_out = n_in / f;  // both powers of two
+    // a few 4-way weighted merges while plenty of elements remain (work-bound levels)
+    while (n_in > 8192) {
+      uint32_t f = 4, n_out = n_in / f;
       PS_LAUNCH(MsmReduceK<F>, st, (size_t)g.S * n_out, n_in, n_out, f, log_len, (const XYZZ<F>*)accv[cur],
                 (const XYZZ<F>*)runv[cur], accv[cur ^ 1], runv[cur ^ 1]);
-      int lf = 0;
-      while ((1u << lf) < f) lf++;
-      log_len += lf;
+      log_len += 2;
       n_in = n_out;
       cur ^= 1;
     }
-    PS_LAUNCH(MsmFinalK<F>, st, 1, g.S, g.c * g.T, (const XYZZ<F>*)accv[cur], d_out);
+    XYZZ<F>* sets = accv[cur];
+    if (n_in > 1) {
+      // low-depth tail: g+1 plain pairwise sums per set, then a short Horner
+      int gb = 0;
+      while ((1u << gb) < n_in) gb++;
+      const uint32_t half = n_in / 2;
+      size_t rows = (size_t)g.S * (gb + 1);
+      XYZZ<F>* Y[2] = {ar.take<XYZZ<F>>(rows * half), ar.take<XYZZ<F>>(rows * (half / 2 + 1))};
+      XYZZ<F>* set_out = ar.take<XYZZ<F>>(g.S);
+      if (!Y[0] || !Y[1] || !set_out) return PS_ERR_ALLOC;
+      PS_LAUNCH(MsmBitGatherK<F>, st, rows * half, n_in, gb, (const XYZZ<F>*)accv[cur], (const XYZZ<F>*)runv[cur], Y[0]);
+      int yc = 0;
+      for (uint32_t w = half; w > 1; w >>= 1) {
+        PS_LAUNCH(MsmPairSumK<F>, st, rows * (w / 2), w, (const XYZZ<F>*)Y[yc], Y[yc ^ 1]);
+        yc ^= 1;
+      }
+      PS_LAUNCH(MsmBitFinalK<F>, st, (size_t)g.S, gb, log_len, (const XYZZ<F>*)Y[yc], set_out);
+      sets = set_out;
+    }
+    PS_LAUNCH(MsmFinalK<F>, st, 1, g.S, g.c * g.T, (const XYZZ<F>*)sets, d_out);
   }
   PS_TRY(ctx_event(ctx, 4));
   ctx->ev_valid = true;

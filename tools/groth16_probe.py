@@ -26,6 +26,16 @@ for i in range(reps):
     t0 = time.time(); pr = ps.Groth16Prove(tr, sq, wb, r, s, backend=be); dt = time.time() - t0
     print("prove %d: %.2f ms wall (witness pre-marshalled), %d launches, device phases %s" % (
         i, dt * 1e3, be.launch_count() - l0, {k: round(v, 2) for k, v in be.prove_timing().items()}), flush=True)
+print("last MSM inside prove (B, G2):", {k: round(v, 2) for k, v in be.msm_timing().items()})
+import random as _r
+from playsnark_b200 import _lib as _L
+_rng = _r.Random(5)
+_sc = b"".join(_rng.randrange(ps.R).to_bytes(32, "big") for _ in range(n + 2))
+for grp in (_L.PS_G1, _L.PS_G2):
+    _b = be.bases_from_scalars(grp, _sc, 0, -1)
+    be.msm(_b, _sc); be.msm(_b, _sc)
+    info = (__import__("ctypes").c_int * 4)(); be.lib.ps_bases_info(_b.handle, info)
+    print("standalone group %d n+2 points c=%d W=%d T=%d:" % (grp, info[0], info[1], info[2]), {k: round(v, 2) for k, v in be.msm_timing().items()})
 t0 = time.time(); h, _ = ps.Quotient(sq, wit, backend=be, return_abc=True); print("quotient alone %.2f ms" % ((time.time() - t0) * 1e3))
 A, B, C, _ = H.sparse_groth16_expected(sq, wit, tw, r, s)
 assert (pr.A, pr.B, pr.C) == (A, B, C), "proof differs from the exponent-level expectation"
