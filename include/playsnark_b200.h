@@ -134,6 +134,16 @@ int ps_g16_prove(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const ui
                  const uint8_t* r_be, const uint8_t* s_be, uint8_t* outA, uint8_t* outB, uint8_t* outC,
                  uint8_t* out_h);
 
+/* Groth16 across several GPUs (one process per GPU, every process holds the key): rank 0 runs the
+ * quotient and emits the scalar vectors of the proof's three MSMs (`which` 0 = A over G1, 1 = C over
+ * G1, 2 = B over G2; standard-form limbs, 8 x u32 each, device memory sized by ps_g16_scalar_count);
+ * after a broadcast every rank sums its index range with ps_msm_device over ps_g16_key_bases and the
+ * partials are gathered and added with ps_msm_combine.                                           */
+size_t ps_g16_scalar_count(const ps_g16_key* key, int which);
+const ps_bases* ps_g16_key_bases(const ps_g16_key* key, int which);
+int ps_g16_scalars(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const uint8_t* witness_be,
+                   const uint8_t* r_be, const uint8_t* s_be, void* d_scA, void* d_scC, void* d_scB);
+
 /* ---- PHGR13 / Pinocchio (pinochio.go) ------------------------------------------------------------ */
 /* PHGR13EvalKey (pinochio.go:37-62): gsi[n-1]; vs, ys, vas, was, yas, vbs, wbs, ybs [n_mid] in G1
  * (wbs is typed []G2 in the reference but holds G1 points, pinochio.go:114,136); ws [n_mid] G2. */

@@ -45,6 +45,9 @@ SYMBOLS = [
     ("ps_g16_key_load", _I, [_P, _SZ, _SZ, _I] + [_B] * 9 + [C.POINTER(_P)]),
     ("ps_g16_key_free", None, [_P]),
     ("ps_g16_prove", _I, [_P, _P, _P, _P, _B, _B, _P, _P, _P, _P]),
+    ("ps_g16_scalar_count", _SZ, [_P, _I]),
+    ("ps_g16_key_bases", _P, [_P, _I]),
+    ("ps_g16_scalars", _I, [_P, _P, _P, _P, _B, _B, _P, _P, _P]),
     ("ps_phgr13_key_load", _I, [_P, _SZ, _SZ, _I] + [_B] * 10 + [C.POINTER(_P)]),
     ("ps_phgr13_key_free", None, [_P]),
     ("ps_phgr13_prove", _I, [_P, _P, _P, _P, _P, _P]),

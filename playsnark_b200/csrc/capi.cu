@@ -234,7 +234,7 @@ int check_err_flag(ps_ctx* ctx, const uint32_t* d_err, int code) {
 
 // witness -> device Montgomery; a, b, c, h on the device (n' entries each)
 struct QuotientBufs { Fr *w, *a, *b, *c, *h; uint32_t* flag; uint32_t* enc_err; };
-int run_quotient_sparse(ps_ctx* ctx, const ps_qap* q, const uint8_t* witness_be, QuotientBufs* o) {
+int run_quotient_sparse(ps_ctx* ctx, const ps_qap* q, const uint8_t* witness_be, QuotientBufs* o, bool want_c) {
   const SparseQap* sq = (const SparseQap*)q->sparse;
   const uint32_t n = (uint32_t)q->n;
   ps_stream_t st = ctx->stream;
@@ -245,21 +245,21 @@ int run_quotient_sparse(ps_ctx* ctx, const ps_qap* q, const uint8_t* witness_be,
   Fr* coef = ctx->arena.take<Fr>((size_t)3 * n);
   o->h = ctx->arena.take<Fr>(n);
   o->flag = ctx->arena.take<uint32_t>(1);
-  uint32_t* flag2 = ctx->arena.take<uint32_t>(1);
-  if (!ev || !coef || !o->h || !o->flag || !flag2) return PS_ERR_ALLOC;
+  if (!ev || !coef || !o->h || !o->flag) return PS_ERR_ALLOC;
   PS_TRY(dev_memset(o->flag, 0, 4, st));
   PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
             (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
             (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, (const Fr*)o->w, ev);
   PS_LAUNCH(GateCheckK, st, n, n, (const Fr*)ev, o->flag);
-  PS_TRY(interpolate3(ctx, sq, n, q->log_np, ev, coef));
+  // only a and b are interpolated: c = a*b mod z never has to exist for the proof
+  PS_TRY(interpolate_ap(ctx, sq, n, q->log_np, 2, ev, coef));
   o->a = coef; o->b = coef + n; o->c = coef + 2 * (size_t)n;
-  PS_TRY(quotient_from_abc(ctx, q, o->a, o->b, o->c, o->h, flag2, false));
+  PS_TRY(quotient_series(ctx, sq, n, q->log_np, o->a, o->b, o->h, want_c ? o->c : (Fr*)nullptr));
   return PS_OK;
 }
 
-int run_quotient(ps_ctx* ctx, const ps_qap* q, const uint8_t* witness_be, QuotientBufs* o) {
-  if (!q->dense) return run_quotient_sparse(ctx, q, witness_be, o);
+int run_quotient(ps_ctx* ctx, const ps_qap* q, const uint8_t* witness_be, QuotientBufs* o, bool want_c = false) {
+  if (!q->dense) return run_quotient_sparse(ctx, q, witness_be, o, want_c);
   const uint32_t np = 1u << q->log_np;
   uint32_t* d_w = nullptr;
   PS_TRY(stage_scalars(ctx, witness_be, q->m, 1, &d_w, &o->enc_err));
@@ -642,7 +642,8 @@ int ps_qap_load_r1cs(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, co
   if (rc == PS_OK && !d_z) rc = PS_ERR_ALLOC;
   if (rc == PS_OK) rc = inv_zprime_build(ctx, sq, (uint32_t)n_gates);
   if (rc == PS_OK) rc = ztree_build(ctx, sq, (uint32_t)n_gates, k, d_z);
-  if (rc == PS_OK) rc = qap_prepare_tables(ctx, q, d_z);
+  if (rc == PS_OK) rc = series_tables_build(ctx, sq, (uint32_t)n_gates, k, d_z);
+  q->log_np = k;
   if (rc == PS_OK) rc = check_err_flag(ctx, d_err, PS_ERR_ENCODING);
   if (rc != PS_OK) { ps_qap_free(q); return rc; }
   *qap = q;
@@ -658,7 +659,7 @@ int ps_quotient(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_be, uint8
   if (!qap || !witness_be || !out_h) return PS_ERR_ARG;
   PS_TRY(begin_call(ctx));
   QuotientBufs qb;
-  PS_TRY(run_quotient(ctx, qap, witness_be, &qb));
+  PS_TRY(run_quotient(ctx, qap, witness_be, &qb, out_abc != nullptr));
   PS_TRY(export_fr(ctx, qb.h, qap->n - 1, out_h));
   if (out_abc) {
     PS_TRY(export_fr(ctx, qb.a, qap->n, out_abc));
@@ -707,66 +708,109 @@ void ps_g16_key_free(ps_g16_key* key) {
   delete key;
 }
 
+namespace {
+// Fr vectors in Montgomery form -> standard form, in place
+struct FrFromMontK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, Fr* a) { a[i] = a[i].from_mont(); }
+};
+
+struct G16Scalars { Fr *scA, *scB, *scC; size_t nA, nB, nC; QuotientBufs qb; };
+
+// quotient + the three MSM scalar vectors of the Groth16 proof (Montgomery form, arena memory)
+int g16_build_scalars(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const uint8_t* witness_be, const uint8_t* r_be,
+                      const uint8_t* s_be, G16Scalars* o) {
+  if (key->n != qap->n || key->n_nio != qap->n_io) return PS_ERR_LENGTH;
+  ps_stream_t st = ctx->stream;
+  const size_t n = qap->n, nio = qap->n_io, diff = qap->m - qap->n_io;
+  PS_TRY(run_quotient(ctx, qap, witness_be, &o->qb));
+  Fr hrs[2];
+  for (int t = 0; t < 2; t++) {
+    const uint8_t* src = t == 0 ? r_be : s_be;
+    Fr x;
+    for (int j = 0; j < 8; j++) {
+      const uint8_t* p = src + 4 * (7 - j);
+      x.v[j] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+    }
+    if (!limbs_lt_mod<FrParams>(x.v)) return PS_ERR_ENCODING;
+    hrs[t] = x.to_mont();
+  }
+  const Fr r = hrs[0], s = hrs[1], rs = hrs[0] * hrs[1];
+  o->nA = n + 2; o->nB = n + 2; o->nC = nio + (n - 1) + n + 3;
+  o->scA = ctx->arena.take<Fr>(o->nA);
+  o->scB = ctx->arena.take<Fr>(o->nB);
+  o->scC = ctx->arena.take<Fr>(o->nC);
+  if (!o->scA || !o->scB || !o->scC) return PS_ERR_ALLOC;
+  const QuotientBufs& qb = o->qb;
+  PS_LAUNCH(FrCopyK, st, n, (const Fr*)qb.a, o->scA);
+  PS_LAUNCH(FrSet3K, st, 2, r, Fr::one(), Fr::zero(), 2, o->scA + n);
+  PS_LAUNCH(FrCopyK, st, n, (const Fr*)qb.b, o->scB);
+  PS_LAUNCH(FrSet3K, st, 2, s, Fr::one(), Fr::zero(), 2, o->scB + n);
+  PS_LAUNCH(FrCopyK, st, nio, (const Fr*)(qb.w + diff), o->scC);
+  PS_LAUNCH(FrCopyK, st, n - 1, (const Fr*)qb.h, o->scC + nio);
+  PS_LAUNCH(FrAxpbyK, st, n, s, (const Fr*)qb.a, r, (const Fr*)qb.b, o->scC + nio + (n - 1));
+  PS_LAUNCH(FrSet3K, st, 3, s, r, rs, 3, o->scC + nio + (n - 1) + n);
+  return PS_OK;
+}
+}  // namespace
+
 int ps_g16_prove(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const uint8_t* witness_be, const uint8_t* r_be,
                  const uint8_t* s_be, uint8_t* outA, uint8_t* outB, uint8_t* outC, uint8_t* out_h) {
   if (!key || !qap || !witness_be || !r_be || !s_be || !outA || !outB || !outC) return PS_ERR_ARG;
-  if (key->n != qap->n || key->n_nio != qap->n_io) return PS_ERR_LENGTH;
   PS_TRY(begin_call(ctx));
-  ps_stream_t st = ctx->stream;
-  const size_t n = qap->n, nio = qap->n_io, diff = qap->m - qap->n_io;
-  QuotientBufs qb;
+  G16Scalars sc;
   ctx->evp_valid = false;
   PS_TRY(ctx_prove_event(ctx, 0));
-  PS_TRY(run_quotient(ctx, qap, witness_be, &qb));
+  PS_TRY(g16_build_scalars(ctx, key, qap, witness_be, r_be, s_be, &sc));
   PS_TRY(ctx_prove_event(ctx, 1));
-  // r, s
-  uint8_t rs_bytes[64];
-  memcpy(rs_bytes, r_be, 32); memcpy(rs_bytes + 32, s_be, 32);
-  Fr hrs[2];
-  {
-    // host copies of r, s in Montgomery form for the kernel arguments
-    for (int t = 0; t < 2; t++) {
-      Fr x;
-      for (int j = 0; j < 8; j++) {
-        const uint8_t* p = rs_bytes + 32 * t + 4 * (7 - j);
-        x.v[j] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
-      }
-      if (!limbs_lt_mod<FrParams>(x.v)) return PS_ERR_ENCODING;
-      hrs[t] = x.to_mont();
-    }
-  }
-  const Fr r = hrs[0], s = hrs[1], rs = hrs[0] * hrs[1];
-  Fr* scA = ctx->arena.take<Fr>(n + 2);
-  Fr* scB = ctx->arena.take<Fr>(n + 2);
-  Fr* scC = ctx->arena.take<Fr>(nio + (n - 1) + n + 3);
   G1XYZZ* resG1 = ctx->arena.take<G1XYZZ>(2);
   G2XYZZ* resG2 = ctx->arena.take<G2XYZZ>(1);
-  if (!scA || !scB || !scC || !resG1 || !resG2) return PS_ERR_ALLOC;
-  PS_LAUNCH(FrCopyK, st, n, (const Fr*)qb.a, scA);
-  PS_LAUNCH(FrSet3K, st, 2, r, Fr::one(), Fr::zero(), 2, scA + n);
-  PS_LAUNCH(FrCopyK, st, n, (const Fr*)qb.b, scB);
-  PS_LAUNCH(FrSet3K, st, 2, s, Fr::one(), Fr::zero(), 2, scB + n);
-  PS_LAUNCH(FrCopyK, st, nio, (const Fr*)(qb.w + diff), scC);
-  PS_LAUNCH(FrCopyK, st, n - 1, (const Fr*)qb.h, scC + nio);
-  PS_LAUNCH(FrAxpbyK, st, n, s, (const Fr*)qb.a, r, (const Fr*)qb.b, scC + nio + (n - 1));
-  PS_LAUNCH(FrSet3K, st, 3, s, r, rs, 3, scC + nio + (n - 1) + n);
-  PS_TRY(msm_on_bases<Fp>(ctx, key->A, 0, (const uint32_t*)scA, n + 2, 1, resG1));
+  if (!resG1 || !resG2) return PS_ERR_ALLOC;
+  PS_TRY(msm_on_bases<Fp>(ctx, key->A, 0, (const uint32_t*)sc.scA, sc.nA, 1, resG1));
   PS_TRY(ctx_prove_event(ctx, 2));
-  PS_TRY(msm_on_bases<Fp>(ctx, key->C, 0, (const uint32_t*)scC, nio + (n - 1) + n + 3, 1, resG1 + 1));
+  PS_TRY(msm_on_bases<Fp>(ctx, key->C, 0, (const uint32_t*)sc.scC, sc.nC, 1, resG1 + 1));
   PS_TRY(ctx_prove_event(ctx, 3));
-  PS_TRY(msm_on_bases<Fp2>(ctx, key->B, 0, (const uint32_t*)scB, n + 2, 1, resG2));
+  PS_TRY(msm_on_bases<Fp2>(ctx, key->B, 0, (const uint32_t*)sc.scB, sc.nB, 1, resG2));
   PS_TRY(ctx_prove_event(ctx, 4));
   uint8_t ac[96];
   PS_TRY(encode_points<Fp>(ctx, resG1, 2, ac));
   PS_TRY(encode_points<Fp2>(ctx, resG2, 1, outB));
   PS_TRY(ctx_prove_event(ctx, 5));
   ctx->evp_valid = true;
-  if (out_h) PS_TRY(export_fr(ctx, qb.h, n - 1, out_h));
-  PS_TRY(check_err_flag(ctx, qb.enc_err, PS_ERR_ENCODING));
-  PS_TRY(check_err_flag(ctx, qb.flag, PS_ERR_REMAINDER));
+  if (out_h) PS_TRY(export_fr(ctx, sc.qb.h, qap->n - 1, out_h));
+  PS_TRY(check_err_flag(ctx, sc.qb.enc_err, PS_ERR_ENCODING));
+  PS_TRY(check_err_flag(ctx, sc.qb.flag, PS_ERR_REMAINDER));
   memcpy(outA, ac, 48);
   memcpy(outC, ac + 48, 48);
   return PS_OK;
+}
+
+size_t ps_g16_scalar_count(const ps_g16_key* key, int which) {
+  if (!key) return 0;
+  const ps_bases* b = which == 0 ? key->A : (which == 1 ? key->C : (which == 2 ? key->B : nullptr));
+  return b ? b->n : 0;
+}
+
+const ps_bases* ps_g16_key_bases(const ps_g16_key* key, int which) {
+  if (!key) return nullptr;
+  return which == 0 ? key->A : (which == 1 ? key->C : (which == 2 ? key->B : nullptr));
+}
+
+int ps_g16_scalars(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const uint8_t* witness_be, const uint8_t* r_be,
+                   const uint8_t* s_be, void* d_scA, void* d_scC, void* d_scB) {
+  if (!key || !qap || !witness_be || !r_be || !s_be || !d_scA || !d_scC || !d_scB) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  G16Scalars sc;
+  PS_TRY(g16_build_scalars(ctx, key, qap, witness_be, r_be, s_be, &sc));
+  ps_stream_t st = ctx->stream;
+  PS_LAUNCH(FrFromMontK, st, sc.nA, sc.scA);
+  PS_LAUNCH(FrFromMontK, st, sc.nC, sc.scC);
+  PS_LAUNCH(FrFromMontK, st, sc.nB, sc.scB);
+  PS_TRY(dev_d2d(d_scA, sc.scA, sc.nA * sizeof(Fr), st));
+  PS_TRY(dev_d2d(d_scC, sc.scC, sc.nC * sizeof(Fr), st));
+  PS_TRY(dev_d2d(d_scB, sc.scB, sc.nB * sizeof(Fr), st));
+  PS_TRY(check_err_flag(ctx, sc.qb.enc_err, PS_ERR_ENCODING));
+  return check_err_flag(ctx, sc.qb.flag, PS_ERR_REMAINDER);
 }
 
 // ---- PHGR13 -------------------------------------------------------------------------------------------

@@ -9,8 +9,13 @@
 //      tree, N_parent = N_L Z_R + N_R Z_L, with batched NTT products.  The Z-tree depends only on n:
 //      it is built once per QAP and kept resident in its NTT domain (log2(n) * 2n Fr: 1.3 GB at
 //      n = 2^20 -- HBM is plentiful); its root is z(x) (qap.go:41-55).
-// The coefficient vectors are identical to Interpolate's (algebra.go:254-280): the interpolant is
-// unique.  n must be a power of two in this path.
+//      Each level reuses the evaluations it has just produced as the even half of the next level's
+//      (twice as large) transform and only computes the odd half (coefficients * omega_{4s}^t).
+//   4. h = floor(a b / z) (= (a b - c)/z since c = a b mod z): the top n-1 coefficients of a b,
+//      reversed, times the power-series inverse of rev(z) (precomputed per QAP by Newton iteration)
+//      -- so c never has to be interpolated.
+// The coefficient vectors are identical to Interpolate's (algebra.go:254-280) and Div2's
+// (algebra.go:140-159): interpolant and quotient are unique.  n must be a power of two in this path.
 #pragma once
 #include "poly.cuh"
 
@@ -27,9 +32,11 @@ struct SparseQap {
   CsrDev mat[3];                 // left, right, out
   Fr* inv_zprime = nullptr;      // 1 / z'(j), j = 1..n
   std::vector<Fr*> ztree;        // level l: NTT_{2s} of every node's Z (s = 2^l), n/s nodes x 2s
+  Fr* s_hat = nullptr;           // NTT_{2n} of the series inverse of rev(z) mod x^(n-1)   (bit-reversed)
+  Fr* z_hat = nullptr;           // NTT_{2n} of z                                          (bit-reversed)
   void release() {
     for (auto& m : mat) { dev_free(m.row_ptr); dev_free(m.col); dev_free(m.val); }
-    dev_free(inv_zprime);
+    dev_free(inv_zprime); dev_free(s_hat); dev_free(z_hat);
     for (auto* p : ztree) dev_free(p);
     ztree.clear();
   }
@@ -168,25 +175,192 @@ inline int inv_zprime_build(ps_ctx* ctx, SparseQap* sq, uint32_t n) {
   return dev_sync(ctx->stream);
 }
 
-// ev: [a | b | c] evaluations (3n) -> coef: [a | b | c] coefficients (3n).  Scratch from the arena.
-inline int interpolate3(ps_ctx* ctx, const SparseQap* sq, uint32_t n, int k, const Fr* ev, Fr* coef) {
+// E0[poly][j][0..2) = [w_j, w_j]: the size-2 transform of the constant polynomial w_j   (thread over P*n)
+struct InterpLeafK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t idx, uint32_t n, const Fr* ev, const Fr* izp, Fr* E) {
+    Fr w = ev[idx] * izp[idx % n];
+    E[2 * (size_t)idx] = w;
+    E[2 * (size_t)idx + 1] = w;
+  }
+};
+// O = E_L Zhat_R + E_R Zhat_L per parent (2s evaluations).  Written twice: into the even half of the
+// parent's next-level block (Enext, 4s per parent) and into the contiguous scratch C.   (thread over P*n)
+struct InterpCombine2K {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t idx, uint32_t n, uint32_t two_s, const Fr* E, const Fr* Zhat, Fr* Enext, Fr* Cbuf) {
+    uint32_t poly = idx / n, r = idx % n;
+    uint32_t p = r / two_s, e = r % two_s;
+    const Fr* El = E + (size_t)poly * 2 * n + (size_t)(2 * p) * two_s;
+    const Fr* Zl = Zhat + (size_t)(2 * p) * two_s;
+    Fr o = El[e] * Zl[two_s + e] + El[two_s + e] * Zl[e];
+    if (Enext) Enext[(size_t)poly * 2 * n + (size_t)p * 2 * two_s + e] = o;
+    Cbuf[idx] = o;
+  }
+};
+// C[t] *= scale * omega_{4s}^t  (t = position inside the 2s-block);  tw = omega_{n_tw}^i   (thread over P*n)
+struct InterpTwistK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t idx, uint32_t two_s, uint32_t tw_step, Fr scale, const Fr* tw, Fr* Cbuf) {
+    uint32_t t = idx % two_s;
+    Cbuf[idx] = Cbuf[idx] * scale * tw[(size_t)t * tw_step];
+  }
+};
+// odd halves: Enext[poly][p][2s + e] = C[poly][p][e]                                     (thread over P*n)
+struct InterpOddK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t idx, uint32_t n, uint32_t two_s, const Fr* Cbuf, Fr* Enext) {
+    uint32_t poly = idx / n, r = idx % n;
+    uint32_t p = r / two_s, e = r % two_s;
+    Enext[(size_t)poly * 2 * n + (size_t)p * 2 * two_s + two_s + e] = Cbuf[idx];
+  }
+};
+// a[i] *= scale
+struct FrScaleK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, Fr scale, Fr* a) { a[i] = a[i] * scale; }
+};
+
+// ev: P polynomials' evaluations on {1..n} (P*n) -> coef: their coefficients (P*n).
+inline int interpolate_ap(ps_ctx* ctx, const SparseQap* sq, uint32_t n, int k, int P, const Fr* ev, Fr* coef) {
   ps_stream_t st = ctx->stream;
   const NttTables* tabs = nullptr;
   PS_TRY(ctx_ntt_tables(ctx, k + 1, &tabs));
   const uint32_t n_tw = 2 * n;
-  const size_t P = 3;
-  Fr* W = ctx->arena.take<Fr>(P * 2 * n);
-  Fr* N = ctx->arena.take<Fr>(P * n);
-  if (!W || !N) return PS_ERR_ALLOC;
-  PS_LAUNCH(InterpWeightK, st, P * n, n, ev, (const Fr*)sq->inv_zprime, N);
+  Fr* E[2] = {ctx->arena.take<Fr>((size_t)P * 2 * n), ctx->arena.take<Fr>((size_t)P * 2 * n)};
+  Fr* Cbuf = ctx->arena.take<Fr>((size_t)P * n);
+  if (!E[0] || !E[1] || !Cbuf) return PS_ERR_ALLOC;
+  PS_LAUNCH(InterpLeafK, st, (size_t)P * n, n, ev, (const Fr*)sq->inv_zprime, E[0]);
+  int cur = 0;
   for (int l = 0; l < k; l++) {
-    const uint32_t s = 1u << l, two_s = 2 * s;
+    const uint32_t two_s = 2u << l;
+    const bool last = (l + 1 == k);
     Fr inv2s = fr_inv(fr_host_from_u64(two_s));
-    Fr* dst = (l + 1 == k) ? coef : N;
-    PS_LAUNCH(InterpPadK, st, P * 2 * n, n, s, (const Fr*)N, W);
-    PS_TRY(ntt_forward_blocks(st, W, P * 2 * n, l + 1, tabs->tw, n_tw));
-    PS_LAUNCH(InterpCombineK, st, P * n, n, two_s, (const Fr*)W, (const Fr*)sq->ztree[l], inv2s, dst);
-    PS_TRY(ntt_inverse_blocks_unscaled(st, dst, P * n, l + 1, tabs->tw_inv, n_tw));
+    Fr* dst = last ? coef : Cbuf;
+    PS_LAUNCH(InterpCombine2K, st, (size_t)P * n, n, two_s, (const Fr*)E[cur], (const Fr*)sq->ztree[l], last ? (Fr*)nullptr : E[cur ^ 1], dst);
+    PS_TRY(ntt_inverse_blocks_unscaled(st, dst, (size_t)P * n, l + 1, tabs->tw_inv, n_tw));
+    if (last) {
+      PS_LAUNCH(FrScaleK, st, (size_t)P * n, inv2s, dst);
+    } else {
+      PS_LAUNCH(InterpTwistK, st, (size_t)P * n, two_s, n_tw / (2 * two_s), inv2s, (const Fr*)tabs->tw, Cbuf);
+      PS_TRY(ntt_forward_blocks(st, Cbuf, (size_t)P * n, l + 1, tabs->tw, n_tw));
+      PS_LAUNCH(InterpOddK, st, (size_t)P * n, n, two_s, (const Fr*)Cbuf, E[cur ^ 1]);
+      cur ^= 1;
+    }
+  }
+  return PS_OK;
+}
+
+// ---- division by z through the power-series inverse of rev(z) -----------------------------------------
+// F[i] = z[n - i] for i < lim (and i <= n), 0 above                                   (thread over len)
+struct RevZPadK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, uint32_t n, uint32_t lim, const Fr* z, Fr* F) {
+    F[i] = (i < lim && i <= n) ? z[n - i] : Fr::zero();
+  }
+};
+// E[i] = F[i] * G[i] * G[i] * scale
+struct MulSqK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, const Fr* F, const Fr* G, Fr scale, Fr* E) { E[i] = F[i] * G[i] * G[i] * scale; }
+};
+// S_new[i] = 2 S_old[i] (i < m) - e[i], i < 2m
+struct NewtonUpdateK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, uint32_t m, const Fr* S_old, const Fr* e, Fr* S_new) {
+    Fr v = i < m ? S_old[i].dbl() : Fr::zero();
+    S_new[i] = v - e[i];
+  }
+};
+// X[i] = A[i] * B[i] * scale
+struct FrMul3K {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, const Fr* A, const Fr* B, Fr scale, Fr* X) { X[i] = A[i] * B[i] * scale; }
+};
+// T[i] = P[2n-2-i] for i <= n-2, 0 above                                               (thread over 2n)
+struct RevTopK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, uint32_t n, const Fr* Pc, Fr* T) { T[i] = (i + 2 <= n) ? Pc[2 * (size_t)n - 2 - i] : Fr::zero(); }
+};
+// h[k] = revh[n-2-k] for k <= n-2, h[n-1] = 0                                          (thread over n)
+struct RevOutK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t k, uint32_t n, const Fr* revh, Fr* h) { h[k] = (k + 2 <= n) ? revh[n - 2 - k] : Fr::zero(); }
+};
+// c[i] = P[i] - Q[i], i < n
+struct FrSubK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, const Fr* Pc, const Fr* Q, Fr* c) { c[i] = Pc[i] - Q[i]; }
+};
+
+// Precomputes s_hat and z_hat from z (n+1 coefficients on the device).
+inline int series_tables_build(ps_ctx* ctx, SparseQap* sq, uint32_t n, int k, const Fr* d_z) {
+  ps_stream_t st = ctx->stream;
+  Arena& ar = ctx->arena;
+  const size_t N2 = (size_t)2 * n;
+  Fr* S[2] = {ar.take<Fr>(N2), ar.take<Fr>(N2)};
+  Fr* F = ar.take<Fr>(2 * N2); Fr* G = ar.take<Fr>(2 * N2); Fr* E = ar.take<Fr>(2 * N2);
+  if (!S[0] || !S[1] || !F || !G || !E) return PS_ERR_ALLOC;
+  PS_TRY(dev_memset(S[0], 0, N2 * sizeof(Fr), st));
+  Fr one = Fr::one();
+  PS_TRY(dev_h2d(S[0], &one, sizeof(Fr), st));  // S = 1 mod x  (rev(z)[0] = 1: z is monic)
+  PS_TRY(dev_sync(st));
+  int cur = 0;
+  for (uint32_t m = 1; m < n; m <<= 1) {
+    int lg = 0;
+    while ((1u << lg) < 4 * m) lg++;
+    const NttTables* t = nullptr;
+    PS_TRY(ctx_ntt_tables(ctx, lg, &t));
+    const uint32_t len = 4 * m;
+    PS_LAUNCH(RevZPadK, st, len, n, 2 * m, d_z, F);
+    PS_LAUNCH(ScaleCopyK, st, len, (const Fr*)S[cur], m, (const Fr*)nullptr, G);
+    PS_TRY(ntt_forward(st, F, lg, t->tw));
+    PS_TRY(ntt_forward(st, G, lg, t->tw));
+    PS_LAUNCH(MulSqK, st, len, (const Fr*)F, (const Fr*)G, fr_inv(fr_host_from_u64(len)), E);
+    PS_TRY(ntt_inverse_unscaled(st, E, lg, t->tw_inv));
+    PS_LAUNCH(NewtonUpdateK, st, 2 * m, m, (const Fr*)S[cur], (const Fr*)E, S[cur ^ 1]);
+    cur ^= 1;
+  }
+  // precision is now >= n >= n-1 coefficients; keep the first n-1, transform at size 2n
+  const NttTables* t2 = nullptr;
+  PS_TRY(ctx_ntt_tables(ctx, k + 1, &t2));
+  PS_TRY(dev_alloc((void**)&sq->s_hat, N2 * sizeof(Fr)));
+  PS_TRY(dev_alloc((void**)&sq->z_hat, N2 * sizeof(Fr)));
+  PS_LAUNCH(ScaleCopyK, st, N2, (const Fr*)S[cur], n - 1, (const Fr*)nullptr, sq->s_hat);
+  PS_TRY(ntt_forward(st, sq->s_hat, k + 1, t2->tw));
+  PS_LAUNCH(ScaleCopyK, st, N2, d_z, n + 1, (const Fr*)nullptr, sq->z_hat);
+  PS_TRY(ntt_forward(st, sq->z_hat, k + 1, t2->tw));
+  return PS_OK;
+}
+
+// h = floor(a*b / z): a, b have n coefficients (device); h receives n entries (h[n-1] = 0).
+// c_out (optional, n entries) = a*b - h*z, the polynomial computeAggregatePoly would have returned.
+inline int quotient_series(ps_ctx* ctx, const SparseQap* sq, uint32_t n, int k, const Fr* a, const Fr* b, Fr* h, Fr* c_out) {
+  ps_stream_t st = ctx->stream;
+  Arena& ar = ctx->arena;
+  const size_t N2 = (size_t)2 * n;
+  const NttTables* t = nullptr;
+  PS_TRY(ctx_ntt_tables(ctx, k + 1, &t));
+  Fr* A = ar.take<Fr>(N2); Fr* B = ar.take<Fr>(N2); Fr* Pc = ar.take<Fr>(N2); Fr* T = ar.take<Fr>(N2);
+  if (!A || !B || !Pc || !T) return PS_ERR_ALLOC;
+  Fr invN = fr_inv(fr_host_from_u64(N2));
+  PS_LAUNCH(ScaleCopyK, st, N2, a, n, (const Fr*)nullptr, A);
+  PS_LAUNCH(ScaleCopyK, st, N2, b, n, (const Fr*)nullptr, B);
+  PS_TRY(ntt_forward(st, A, k + 1, t->tw));
+  PS_TRY(ntt_forward(st, B, k + 1, t->tw));
+  PS_LAUNCH(FrMul3K, st, N2, (const Fr*)A, (const Fr*)B, invN, Pc);
+  PS_TRY(ntt_inverse_unscaled(st, Pc, k + 1, t->tw_inv));          // Pc = a*b, 2n-1 coefficients
+  PS_LAUNCH(RevTopK, st, N2, n, (const Fr*)Pc, T);
+  PS_TRY(ntt_forward(st, T, k + 1, t->tw));
+  PS_LAUNCH(FrMul3K, st, N2, (const Fr*)T, (const Fr*)sq->s_hat, invN, T);
+  PS_TRY(ntt_inverse_unscaled(st, T, k + 1, t->tw_inv));           // T[0..n-1) = rev(h)
+  PS_LAUNCH(RevOutK, st, n, n, (const Fr*)T, h);
+  if (c_out) {
+    PS_LAUNCH(ScaleCopyK, st, N2, (const Fr*)h, n, (const Fr*)nullptr, A);
+    PS_TRY(ntt_forward(st, A, k + 1, t->tw));
+    PS_LAUNCH(FrMul3K, st, N2, (const Fr*)A, (const Fr*)sq->z_hat, invN, A);
+    PS_TRY(ntt_inverse_unscaled(st, A, k + 1, t->tw_inv));         // A = h*z
+    PS_LAUNCH(FrSubK, st, n, (const Fr*)Pc, (const Fr*)A, c_out);
   }
   return PS_OK;
 }

@@ -32,6 +32,23 @@ for group, F, gen, comp in ((L.PS_G1, O.F1, O.G1_GEN, O.g1_compress), (L.PS_G2, 
     else:
         assert res is None
 assert D.shard_range(10, 0, 3) == (0, 4) and D.shard_range(10, 2, 3) == (7, 10)
+# Groth16 with the three MSMs sharded over the ranks, against the oracle prover (same seeds on all ranks)
+from tests import helpers as H
+r1cs, wit = H.mixed_circuit(12, 5, 6)
+oq = O.to_qap(r1cs)
+smp = O.Sampler(5)
+tr = O.groth16_setup(oq, smp)
+rr, ss = smp.fr(), smp.fr()
+res = D.groth16_prove_sharded(be, H.mirror_g16_setup(tr), H.mirror_qap(oq), wit, rr, ss, dist)
+if rank == 0:
+    want = O.groth16_prove(tr, oq, wit, rr, ss)
+    assert res == (O.g1_compress(want["A"]), O.g2_compress(want["B"]), O.g1_compress(want["C"]))
+bad = list(wit); bad[-1] = (bad[-1] + 1) %% O.R
+try:
+    D.groth16_prove_sharded(be, H.mirror_g16_setup(tr), H.mirror_qap(oq), bad, rr, ss, dist)
+    raise SystemExit("expected apocalypse on every rank")
+except ArithmeticError:
+    pass
 dist.barrier()
 if rank == 0:
     print("SHARDED_OK")
