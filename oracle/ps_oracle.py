@@ -811,9 +811,10 @@ def generate_eval_commit(F, base, polys, x, shift):
     return [pt_mul(F, poly_eval(poly_normalize(p), x) * shift % R, base) for p in polys]
 
 
-def phgr13_setup(qap: QAP, sampler: Sampler):
+def phgr13_setup(qap: QAP, sampler: Sampler, with_vk: bool = True):
     """NewPHGR13TrustedSetup, pinochio.go:93-176, sampling order preserved
-    (s, av, aw, ay, rv, rw, beta, gamma)."""
+    (s, av, aw, ay, rv, rw, beta, gamma).  with_vk=False skips the three all-variable commitment
+    vectors of the verification key (only needed by PHGR13Verify) for large prover-only tests."""
     ek, vk, t = {}, {}, {}
     s = sampler.fr()
     ek["gsi"] = generate_powers_commit(F1, G1_GEN, s, 1, (len(qap.z) - 1) - 2)
@@ -838,9 +839,10 @@ def phgr13_setup(qap: QAP, sampler: Sampler):
     vk["av"] = g2_mul(av); vk["aw"] = g1_mul(aw); vk["ay"] = g2_mul(ay)
     vk["gamma"] = g2_mul(gamma); vk["bgamma"] = g1_mul(bgamma); vk["bgamma2"] = g2_mul(bgamma)
     vk["yts"] = g2_mul(poly_eval(qap.z, s), g2y)
-    vk["vs"] = generate_eval_commit(F1, gv, qap.left, s, 1)
-    vk["ws"] = generate_eval_commit(F2, gw, qap.right, s, 1)
-    vk["ys"] = generate_eval_commit(F1, gy, qap.out, s, 1)
+    if with_vk:
+        vk["vs"] = generate_eval_commit(F1, gv, qap.left, s, 1)
+        vk["ws"] = generate_eval_commit(F2, gw, qap.right, s, 1)
+        vk["ys"] = generate_eval_commit(F1, gy, qap.out, s, 1)
     t.update(beta=beta, s=s, gv=gv, gw=gw, gy=gy, ry=ry, rv=rv, rw=rw)
     return {"EK": ek, "VK": vk, "t": t}
 

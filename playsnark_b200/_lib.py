@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplaysnark_b200.so")
+# PLAYSNARK_B200_LIB may point at another nvcc build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("PLAYSNARK_B200_LIB") or os.path.join(_HERE, "libplaysnark_b200.so")
 
 PS_OK, PS_ERR_ARG, PS_ERR_LENGTH, PS_ERR_REMAINDER, PS_ERR_ENCODING, PS_ERR_CUDA, PS_ERR_ALLOC, PS_ERR_UNSUPPORTED = range(8)
 PS_FMT_COMPRESSED, PS_FMT_AFFINE = 0, 1

@@ -64,9 +64,13 @@ PS_DEV void ps_atomic_or(uint32_t* p, uint32_t v) {
 
 inline uint64_t& launch_counter() { static uint64_t c = 0; return c; }
 
+// optional K::MIN_BLOCKS (resident blocks per SM the register allocator must allow)
+template <class K, class = void> struct MinBlocks { static constexpr int V = 1; };
+template <class K> struct MinBlocks<K, decltype((void)K::MIN_BLOCKS)> { static constexpr int V = K::MIN_BLOCKS; };
+
 #if PS_GPU
 template <class K, class... Args>
-__global__ void __launch_bounds__(K::BLOCK) ps_kernel(uint32_t n, Args... args) {
+__global__ void __launch_bounds__(K::BLOCK, MinBlocks<K>::V) ps_kernel(uint32_t n, Args... args) {
   uint32_t tid = blockIdx.x * (uint32_t)K::BLOCK + threadIdx.x;
   if (tid < n) K::run(tid, args...);
 }

@@ -64,11 +64,6 @@ struct GateCheckK {
     if ((ev[j] * ev[n + j]) != ev[2 * (size_t)n + j]) ps_atomic_or(flag, 1u);
   }
 };
-// w[p][j] = ev[p][j] * inv_zprime[j]
-struct InterpWeightK {
-  static constexpr int BLOCK = 256;
-  PS_DEV static void run(uint32_t idx, uint32_t n, const Fr* ev, const Fr* izp, Fr* w) { w[idx] = ev[idx] * izp[idx % n]; }
-};
 // leaves of the Z-tree: node i is (x - (i+1)) -> [-(i+1), 1]
 struct TreeLeafK {
   static constexpr int BLOCK = 256;
@@ -111,27 +106,6 @@ struct TreeRootK {
     z[e] = v;
   }
 };
-// W[poly][node][0..2s) = [N[poly][node][0..s), 0...]                              (thread over P*2n)
-struct InterpPadK {
-  static constexpr int BLOCK = 256;
-  PS_DEV static void run(uint32_t idx, uint32_t n, uint32_t s, const Fr* N, Fr* W) {
-    uint32_t poly = idx / (2 * n), r = idx % (2 * n);
-    uint32_t node = r / (2 * s), e = r % (2 * s);
-    W[idx] = e < s ? N[(size_t)poly * n + (size_t)node * s + e] : Fr::zero();
-  }
-};
-// O[poly][p][e] = (W[poly][2p][e] Zhat[2p+1][e] + W[poly][2p+1][e] Zhat[2p][e]) * inv2s   (thread over P*n)
-struct InterpCombineK {
-  static constexpr int BLOCK = 256;
-  PS_DEV static void run(uint32_t idx, uint32_t n, uint32_t two_s, const Fr* W, const Fr* Zhat, Fr inv2s, Fr* O) {
-    uint32_t poly = idx / n, r = idx % n;
-    uint32_t p = r / two_s, e = r % two_s;
-    const Fr* Wl = W + (size_t)poly * 2 * n + (size_t)(2 * p) * two_s;
-    const Fr* Zl = Zhat + (size_t)(2 * p) * two_s;
-    O[idx] = (Wl[e] * Zl[two_s + e] + Wl[two_s + e] * Zl[e]) * inv2s;
-  }
-};
-
 // Builds the Z-tree for n = 2^k (device), writes z (n+1 coefficients, Montgomery) to d_z.
 inline int ztree_build(ps_ctx* ctx, SparseQap* sq, uint32_t n, int k, Fr* d_z) {
   ps_stream_t st = ctx->stream;

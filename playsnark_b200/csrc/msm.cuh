@@ -136,9 +136,17 @@ PS_DEV Affine<F> msm_load_point(const Affine<F>* tab, uint32_t e) {
 }
 
 // slot flags: bit0 = the bucket has partials to the left, bit1 = to the right
+#ifndef PS_G1_MINB
+#define PS_G1_MINB 3
+#endif
+#ifndef PS_G2_MINB
+#define PS_G2_MINB 2
+#endif
 template <class F>
 struct MsmAccumK {
   static constexpr int BLOCK = 128;
+  // registers: G1 fits 3 resident blocks per SM without spilling; G2 (Fp2) is register-bound
+  static constexpr int MIN_BLOCKS = sizeof(F) == sizeof(Fp) ? PS_G1_MINB : PS_G2_MINB;
   PS_DEV static void run(uint32_t tid, uint32_t nb, uint32_t L, const Affine<F>* tab, const uint32_t* ent,
                          const uint32_t* off, XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid,
                          uint8_t* slot_fl) {

@@ -304,3 +304,51 @@ def groth16_sparse_exponent_check(be, log_n, seed):
     bad = list(wit); bad[-1] = (bad[-1] + 1) % O.R
     with pytest.raises(ArithmeticError, match="apocalypse"):
         api.Groth16Prove(tr, sq, bad, r, s, backend=be)
+
+
+def config_c2(be, n=1 << 10):
+    """BASELINE configs[1]: repeated-squaring R1CS with 2^10 multiplication gates (dense QAP of
+    3*1026*1024 coefficients), Groth16 and PHGR13 prove; int witness x0 = -1 (the only chain that fits
+    the reference's Value int) -- a full-width negative scalar r-1 repeated."""
+    r, w = H.squaring_chain(n, O.R - 1)
+    assert set(w) <= {1, O.R - 1}
+    oq = O.to_qap(r)
+    q = H.mirror_qap(oq)
+    # Groth16: setup by scalar exponents on the device's fixed-base kernel, checked in the exponent
+    smp = O.Sampler(2)
+    tw = {k: smp.fr() for k in ("Alpha", "Beta", "Delta", "X", "Gamma")}
+    x = tw["X"]
+    pw = [pow(x, i, O.R) for i in range(n)]
+    dinv = pow(tw["Delta"], -1, O.R)
+    diff = oq.nb_vars - oq.nb_io
+    nio = [O.linear_poly_for_var(oq, i, x, tw["Alpha"], tw["Beta"]) * dinv % O.R for i in range(diff, oq.nb_vars)]
+    txd = O.poly_eval(oq.z, x) * dinv % O.R
+    g1 = lambda exps: be.bases_from_scalars(L.PS_G1, exps).export()
+    g2 = lambda exps: be.bases_from_scalars(L.PS_G2, exps).export()
+    tr = api.Groth16Setup(Alpha=g1([tw["Alpha"]])[0], Beta=g1([tw["Beta"]])[0], Delta=g1([tw["Delta"]])[0], Xi=g1(pw),
+                          NioLP=g1(nio), XiT=g1([p * txd % O.R for p in pw[:n - 1]]), Beta2=g2([tw["Beta"]])[0],
+                          Delta2=g2([tw["Delta"]])[0], Xi2=g2(pw))
+    rr, ss = smp.fr(), smp.fr()
+    pr = api.Groth16Prove(tr, q, w, rr, ss, backend=be, want_h=True)
+    h = oq.quotient(w)                                   # Poly.Div2 restatement, n = 2^10
+    assert pr.h == h and len(h) == n - 1
+    a, b, c = oq.compute_aggregate_poly(w)
+    ax, bx = O.poly_eval(a, x), O.poly_eval(b, x)
+    ea = (tw["Alpha"] + ax + rr * tw["Delta"]) % O.R
+    eb = (tw["Beta"] + bx + ss * tw["Delta"]) % O.R
+    ec = (sum(wv * e for wv, e in zip(w[diff:], nio)) + O.poly_eval(h, x) * txd + ss * ea + rr * eb
+          - rr * ss % O.R * tw["Delta"]) % O.R
+    assert pr.A == O.g1_compress(O.g1_mul(ea)) and pr.B == O.g2_compress(O.g2_mul(eb)) and pr.C == O.g1_compress(O.g1_mul(ec))
+    # PHGR13 on the same QAP: evaluation key from the oracle (prover side only), proof vs the oracle prover
+    st = O.phgr13_setup(oq, O.Sampler(3), with_vk=False)
+    pp = api.PHGR13Prove(H.mirror_phgr13_ek(st["EK"]), q, w, backend=be, want_h=True)
+    assert pp.h == h
+    assert pp.hs == O.g1_compress(O.g1_mul(O.poly_eval(h, st["t"]["s"])))      # pinocchio_test.go:31-44
+    fe = w[diff:]
+    for f, key, F, comp in (("vss", "vs", O.F1, O.g1_compress), ("yss", "ys", O.F1, O.g1_compress),
+                            ("vass", "vas", O.F1, O.g1_compress), ("wass", "was", O.F1, O.g1_compress),
+                            ("yass", "yas", O.F1, O.g1_compress), ("wss", "ws", O.F2, O.g2_compress)):
+        assert getattr(pp, f) == comp(O.msm_naive(F, fe, st["EK"][key])), f
+    gz = O.g1_add(O.msm_naive(O.F1, fe, st["EK"]["vbs"]), O.g1_add(O.msm_naive(O.F1, fe, st["EK"]["wbs"]),
+                                                                    O.msm_naive(O.F1, fe, st["EK"]["ybs"])))
+    assert pp.gz == O.g1_compress(gz)

@@ -70,3 +70,6 @@ def test_sparse_quotient(be, n): P.sparse_quotient_vs_dense(be, n, seed=n)
 
 
 def test_sparse_groth16_exponent_check(be): P.groth16_sparse_exponent_check(be, 5, seed=8)
+
+
+def test_config_c2_shape_small(be): P.config_c2(be, n=16)

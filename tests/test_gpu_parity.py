@@ -111,6 +111,11 @@ def test_sparse_groth16_exponent_check(be, log_n):
     P.groth16_sparse_exponent_check(be, log_n, seed=log_n)
 
 
+def test_config_c2_dense_2p10(be):
+    # BASELINE configs[1]: 2^10 multiplication gates, dense QAP (101 MB), Groth16 + PHGR13
+    P.config_c2(be)
+
+
 def test_no_device_is_loud():
     lib = L.load()
     import ctypes as C
