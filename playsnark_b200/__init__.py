@@ -6,6 +6,6 @@ sm_100a CUDA kernels (playsnark_b200/csrc).
 """
 from .api import (  # noqa: F401
     R, Backend, Bases, Groth16Proof, Groth16Setup, PHGR13EvalKey, PHGR13Proof, QAP, SparseQAP, R1CS, Groth16Prove,
-    PHGR13Prove, Quotient, BlindEval, default_backend, set_default_backend,
+    PHGR13Prove, Quotient, BlindEval, ToQAP, default_backend, set_default_backend,
 )
 from ._lib import PlaysnarkError  # noqa: F401

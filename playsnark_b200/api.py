@@ -170,23 +170,77 @@ def BlindEval(p: Poly, blinded: Bases, backend: Optional[Backend] = None) -> byt
 
 
 # ---- R1CS / QAP types (r1cs.go:81-102, qap.go:10-27) ------------------------------------------------
-@dataclass
 class R1CS:
-    """Dense 0/1(/const) gate matrices; variable order [const, inputs..., outputs..., intermediates...]
-    (r1cs.go:132-144)."""
-    inputs: List[str] = field(default_factory=list)
-    outputs: List[str] = field(default_factory=list)
-    intermediates: List[str] = field(default_factory=list)
-    left: List[List[int]] = field(default_factory=list)
-    right: List[List[int]] = field(default_factory=list)
-    out: List[List[int]] = field(default_factory=list)
+    """r1cs.go:81-174: gate matrices left / right / out (rows = gates, columns = variables) over the
+    variable order [const, inputs..., outputs..., intermediates...] (mergeVars, r1cs.go:132-144).
+    Host-side bookkeeping only; rows are kept sparse ({column: value})."""
+
+    def __init__(self):
+        self.inputs: List[str] = []
+        self.outputs: List[str] = []
+        self.intermediates: List[str] = []
+        self._gates = []   # (left names->coef, right ..., out ...) by variable NAME, resolved in rows()
 
     @property
     def vars(self) -> List[str]:
         return ["const"] + self.inputs + self.outputs + self.intermediates
 
-    def nbIO(self) -> int:
+    def nbIO(self) -> int:                      # r1cs.go:108-110
         return 1 + len(self.inputs) + len(self.outputs)
+
+    def NewInput(self, name: str): self.inputs.append(name)          # r1cs.go:112-115
+    def NewOutput(self, name: str): self.outputs.append(name)        # r1cs.go:117-120
+    def NewVar(self, name: str): self.intermediates.append(name)     # r1cs.go:122-125
+
+    def IndexOf(self, name: str) -> int:                             # r1cs.go:21-28
+        try:
+            return self.vars.index(name)
+        except ValueError:
+            raise KeyError("plouf")
+
+    def Mul(self, left: str, right: str, out: str):                  # r1cs.go:148-152
+        self._gates.append(({left: 1}, {right: 1}, {out: 1}))
+
+    def Add(self, var1: str, var2: str, out: str):                   # r1cs.go:156-164
+        self._gates.append(({var1: 1, var2: 1}, {"const": 1}, {out: 1}))   # ConstraintOn marks 0/1 per name
+
+    def AddConst(self, var1: str, add: int, out: str):               # r1cs.go:168-174
+        row = {"const": 1, var1: 1}
+        row["const"] = row["const"] * add
+        self._gates.append((row, {"const": 1}, {out: 1}))
+
+    def rows(self):
+        """the three matrices as lists of {column index: Go int}"""
+        idx = {n: i for i, n in enumerate(self.vars)}
+        for names in self._gates:
+            for d in names:
+                for n in d:
+                    if n not in idx:
+                        raise KeyError("plouf")
+        conv = lambda k: [{idx[n]: v for n, v in g[k].items() if v} for g in self._gates]
+        return conv(0), conv(1), conv(2)
+
+
+def ToQAP(circuit: R1CS) -> "SparseQAP":
+    """ToQAP, qap.go:35-65.  The per-variable polynomials are not materialised (that costs O(m n^3)
+    field operations and 3*m*n*32 bytes in the reference): the result keeps the gate matrices in CSR
+    form and the device interpolates on {1..n} when proving.  nbGates must be a power of two; for
+    other sizes build the dense QAP (qap.go's layout) and pass it as `QAP`."""
+    left, right, out = circuit.rows()
+    n = len(left)
+    if n < 2 or n & (n - 1):
+        raise NotImplementedError("ToQAP on the device needs a power-of-two number of gates (got %d); "
+                                  "use the dense QAP form for other sizes" % n)
+
+    def csr(m):
+        rp, col, val = [0], [], []
+        for row in m:
+            for j in sorted(row):
+                col.append(j); val.append(int(row[j]) % R)
+            rp.append(len(col))
+        return rp, col, val
+
+    return SparseQAP(len(circuit.vars), circuit.nbIO(), n, csr(left), csr(right), csr(out))
 
 
 @dataclass

@@ -45,7 +45,7 @@ def build_host_emulation(out_dir: str) -> str:
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libps_hostemu.so")
     if stale(so, _sources()):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-x", "c++", "-DPS_HOST_EMU", "-shared", "-fPIC", "-o", so,
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-DPS_HOST_EMU", "-shared", "-fPIC", "-o", so,
                                os.path.join(CSRC, "capi.cu")], cwd=ROOT)
     return so
 

@@ -352,3 +352,39 @@ def config_c2(be, n=1 << 10):
     gz = O.g1_add(O.msm_naive(O.F1, fe, st["EK"]["vbs"]), O.g1_add(O.msm_naive(O.F1, fe, st["EK"]["wbs"]),
                                                                     O.msm_naive(O.F1, fe, st["EK"]["ybs"])))
     assert pp.gz == O.g1_compress(gz)
+
+
+def readme_flow_through_api(be):
+    """README / r1cs.go:178-198: createR1CS -> ToQAP -> Groth16Prove, all through the host mirror's
+    reference-shaped API, against the golden proof."""
+    c = api.R1CS()
+    c.NewInput("x"); c.NewOutput("out")
+    c.NewVar("u"); c.NewVar("v"); c.NewVar("w")
+    c.Mul("x", "x", "u"); c.Mul("u", "x", "v"); c.Add("v", "x", "w"); c.AddConst("w", 5, "out")
+    assert c.vars == ["const", "x", "out", "u", "v", "w"] and c.nbIO() == 3
+    sol = [0] * 6
+    for name, val in (("const", 1), ("x", 3), ("out", 35), ("u", 9), ("v", 27), ("w", 30)):
+        sol[c.IndexOf(name)] = val                       # createWitness, r1cs.go:67-76
+    q = api.ToQAP(c)
+    g = gold("readme_circuit")
+    assert q.nbVars == g["nb_vars"] and q.nbIO == g["nb_io"] and q.nbGates == g["nb_gates"]
+    h, (a, b, cc) = api.Quotient(q, sol, backend=be, return_abc=True)
+    I = lambda xs: [int(x, 16) for x in xs]
+    assert h == I(g["h"]) and a == I(g["a"]) and b == I(g["b"]) and cc == I(g["c"])
+    k = g["groth16"]
+    B = bytes.fromhex
+    tr = api.Groth16Setup(Alpha=B(k["Alpha"]), Beta=B(k["Beta"]), Delta=B(k["Delta"]), Xi=[B(x) for x in k["Xi"]],
+                          NioLP=[B(x) for x in k["NioLP"]], XiT=[B(x) for x in k["XiT"]], Beta2=B(k["Beta2"]),
+                          Delta2=B(k["Delta2"]), Xi2=[B(x) for x in k["Xi2"]])
+    pr = api.Groth16Prove(tr, q, sol, int(k["r"], 16), int(k["s"], 16), backend=be)
+    assert (pr.A.hex(), pr.B.hex(), pr.C.hex()) == (k["A"], k["B"], k["C"])
+    ek = api.PHGR13EvalKey(**{name: [bytes.fromhex(x) for x in v] for name, v in g["phgr13"]["ek"].items()})
+    pp = api.PHGR13Prove(ek, q, sol, backend=be)
+    for f in O.PHGR13_FIELDS:
+        assert getattr(pp, f).hex() == g["phgr13"]["proof"][f], f
+    import pytest
+    with pytest.raises(KeyError, match="plouf"):         # r1cs.go:27
+        c.IndexOf("nope")
+    c5 = api.R1CS(); c5.NewInput("x"); c5.NewOutput("o"); c5.Mul("x", "x", "o"); c5.Mul("x", "x", "o"); c5.Mul("x", "x", "o")
+    with pytest.raises(NotImplementedError):
+        api.ToQAP(c5)

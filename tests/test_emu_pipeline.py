@@ -73,3 +73,6 @@ def test_sparse_groth16_exponent_check(be): P.groth16_sparse_exponent_check(be, 
 
 
 def test_config_c2_shape_small(be): P.config_c2(be, n=16)
+
+
+def test_readme_flow_through_api(be): P.readme_flow_through_api(be)

@@ -116,6 +116,9 @@ def test_config_c2_dense_2p10(be):
     P.config_c2(be)
 
 
+def test_readme_flow_through_api(be): P.readme_flow_through_api(be)
+
+
 def test_no_device_is_loud():
     lib = L.load()
     import ctypes as C
