@@ -54,6 +54,8 @@ const char* ps_version(void);
 int ps_ctx_create(int device, ps_ctx** out);
 /* run on a caller-provided CUDA stream (cudaStream_t passed as void*), e.g. torch's current one */
 int ps_ctx_set_stream(ps_ctx* ctx, void* cuda_stream);
+/* tuning knobs: "msm_accumulate" = 0 (XYZZ accumulator chains, default) | 1 (batched affine tree rounds) */
+int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value);
 int ps_ctx_sync(ps_ctx* ctx);
 void ps_ctx_destroy(ps_ctx* ctx);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */

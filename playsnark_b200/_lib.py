@@ -26,6 +26,7 @@ SYMBOLS = [
     ("ps_version", C.c_char_p, []),
     ("ps_ctx_create", _I, [_I, C.POINTER(_P)]),
     ("ps_ctx_set_stream", _I, [_P, _P]),
+    ("ps_ctx_set_option", _I, [_P, C.c_char_p, _I]),
     ("ps_ctx_sync", _I, [_P]),
     ("ps_ctx_destroy", None, [_P]),
     ("ps_launch_count", C.c_uint64, []),

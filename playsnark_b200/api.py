@@ -93,6 +93,9 @@ class Backend:
             self.lib.ps_ctx_destroy(self.ctx)
             self.ctx = None
 
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.ps_ctx_set_option(self.ctx, name.encode(), value))
+
     def sync(self):
         self._check(self.lib.ps_ctx_sync(self.ctx))
 

@@ -62,6 +62,14 @@ PS_DEV void ps_atomic_or(uint32_t* p, uint32_t v) {
 #endif
 }
 
+PS_DEV void ps_atomic_max(uint32_t* p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+  atomicMax(p, v);
+#else
+  if (v > *p) *p = v;
+#endif
+}
+
 inline uint64_t& launch_counter() { static uint64_t c = 0; return c; }
 
 // optional K::MIN_BLOCKS (resident blocks per SM the register allocator must allow)

@@ -4,6 +4,7 @@
 #include "codec.cuh"
 #include "microbench.cuh"
 #include "msm.cuh"
+#include "msm_affine.cuh"
 #include "poly.cuh"
 #include "interp.cuh"
 
@@ -371,6 +372,16 @@ int ps_ctx_set_stream(ps_ctx* ctx, void* cuda_stream) {
   (void)cuda_stream;
 #endif
   return PS_OK;
+}
+
+int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value) {
+  if (!ctx || !name) return PS_ERR_ARG;
+  if (!strcmp(name, "msm_accumulate")) {
+    if (value != 0 && value != 1) return PS_ERR_ARG;
+    ctx->accum_mode = value;
+    return PS_OK;
+  }
+  return PS_ERR_ARG;
 }
 
 int ps_ctx_sync(ps_ctx* ctx) { return ctx ? dev_sync(ctx->stream) : PS_ERR_ARG; }

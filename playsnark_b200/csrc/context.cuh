@@ -17,6 +17,8 @@ struct ps_ctx {
   // phase events of the last Groth16 prove: start, quotient done, MSM A, MSM C, MSM B, encoded
   void* evp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool evp_valid = false;
+  // bucket accumulation: 0 = XYZZ chains (MsmAccumK), 1 = batched affine tree rounds (msm_affine.cuh)
+  int accum_mode = 0;
 };
 
 namespace ps {

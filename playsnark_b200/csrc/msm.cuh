@@ -486,6 +486,10 @@ inline int msm_pick_window_full(size_t n) {
 
 // Runs the pipeline; result (XYZZ) written to d_out (device).  `tab` holds g.T tables of g.nbase points.
 template <class F>
+int msm_accumulate_affine(ps_ctx* ctx, uint32_t nb, size_t max_ent, const Affine<F>* tab, const uint32_t* ent, const uint32_t* off0,
+                          XYZZ<F>* buckets);
+
+template <class F>
 int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scalars, int mont, XYZZ<F>* d_out) {
   ps_stream_t st = ctx->stream;
   Arena& ar = ctx->arena;
@@ -512,12 +516,7 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   uint32_t* ranks = ar.take<uint32_t>(max_ent);
   uint32_t* ent = ar.take<uint32_t>(max_ent);
   XYZZ<F>* buckets = ar.take<XYZZ<F>>(nb);
-  size_t slots_a = 2 * T1, slots_b = 2 * ((slots_a + CF - 1) / CF);
-  XYZZ<F>* sp[2] = {ar.take<XYZZ<F>>(slots_a), ar.take<XYZZ<F>>(slots_b)};
-  int32_t* sb[2] = {ar.take<int32_t>(slots_a), ar.take<int32_t>(slots_b)};
-  uint8_t* sf[2] = {ar.take<uint8_t>(slots_a), ar.take<uint8_t>(slots_b)};
-  if (!count || !off || !tile_sums || !ranks || !ent || !buckets || !sp[0] || !sp[1] || !sb[0] || !sb[1] || !sf[0] || !sf[1])
-    return PS_ERR_ALLOC;
+  if (!count || !off || !tile_sums || !ranks || !ent || !buckets) return PS_ERR_ALLOC;
 
   ctx->ev_valid = false;
   PS_TRY(ctx_event(ctx, 0));
@@ -527,20 +526,30 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   PS_TRY(exclusive_scan_u32(st, count, off, tile_sums, nb + 1));
   PS_LAUNCH(MsmScatterK, st, g.n, g, d_scalars, mont, (const uint32_t*)off, (const uint32_t*)ranks, ent);
   PS_TRY(ctx_event(ctx, 1));
-  PS_LAUNCH(MsmAccumK<F>, st, T1, nb, L, tab, (const uint32_t*)ent, (const uint32_t*)off, buckets, sp[0], sb[0], sf[0]);
-  PS_TRY(ctx_event(ctx, 2));
-  PS_LAUNCH(MsmRunMergeK<F>, st, T1, (uint32_t)T1, buckets, sp[0], sb[0], (const uint8_t*)sf[0]);
-  {
-    size_t n_in = slots_a;
-    int cur = 0;
-    for (;;) {
-      size_t threads = (n_in + CF - 1) / CF;
-      int final_pass = threads == 1;
-      PS_LAUNCH(MsmCombineK<F>, st, threads, (uint32_t)n_in, CF, (const XYZZ<F>*)sp[cur], (const int32_t*)sb[cur],
-                (const uint8_t*)sf[cur], buckets, sp[cur ^ 1], sb[cur ^ 1], sf[cur ^ 1], final_pass);
-      if (final_pass) break;
-      n_in = 2 * threads;
-      cur ^= 1;
+  if (ctx->accum_mode == 1) {
+    PS_TRY(msm_accumulate_affine<F>(ctx, nb, max_ent, tab, ent, off, buckets));
+    PS_TRY(ctx_event(ctx, 2));
+  } else {
+    size_t slots_a = 2 * T1, slots_b = 2 * ((slots_a + CF - 1) / CF);
+    XYZZ<F>* sp[2] = {ar.take<XYZZ<F>>(slots_a), ar.take<XYZZ<F>>(slots_b)};
+    int32_t* sb[2] = {ar.take<int32_t>(slots_a), ar.take<int32_t>(slots_b)};
+    uint8_t* sf[2] = {ar.take<uint8_t>(slots_a), ar.take<uint8_t>(slots_b)};
+    if (!sp[0] || !sp[1] || !sb[0] || !sb[1] || !sf[0] || !sf[1]) return PS_ERR_ALLOC;
+    PS_LAUNCH(MsmAccumK<F>, st, T1, nb, L, tab, (const uint32_t*)ent, (const uint32_t*)off, buckets, sp[0], sb[0], sf[0]);
+    PS_TRY(ctx_event(ctx, 2));
+    PS_LAUNCH(MsmRunMergeK<F>, st, T1, (uint32_t)T1, buckets, sp[0], sb[0], (const uint8_t*)sf[0]);
+    {
+      size_t n_in = slots_a;
+      int cur = 0;
+      for (;;) {
+        size_t threads = (n_in + CF - 1) / CF;
+        int final_pass = threads == 1;
+        PS_LAUNCH(MsmCombineK<F>, st, threads, (uint32_t)n_in, CF, (const XYZZ<F>*)sp[cur], (const int32_t*)sb[cur],
+                  (const uint8_t*)sf[cur], buckets, sp[cur ^ 1], sb[cur ^ 1], sf[cur ^ 1], final_pass);
+        if (final_pass) break;
+        n_in = 2 * threads;
+        cur ^= 1;
+      }
     }
   }
   PS_TRY(ctx_event(ctx, 3));
