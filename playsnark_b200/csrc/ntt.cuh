@@ -34,9 +34,16 @@ struct FrMulTableK {
   PS_DEV static void run(uint32_t i, Fr* a, const Fr* t) { a[i] = a[i] * t[i]; }
 };
 
+#ifndef PS_NTT_BLOCK
+#define PS_NTT_BLOCK 128
+#endif
+#ifndef PS_NTT_MINB
+#define PS_NTT_MINB 4
+#endif
 template <int R>
 struct NttDifK {
-  static constexpr int BLOCK = 256;
+  static constexpr int BLOCK = PS_NTT_BLOCK;
+  static constexpr int MIN_BLOCKS = PS_NTT_MINB;   // 8 field elements per thread: cap registers for 4 warps / scheduler
   // one launch = R stages on sub-transforms of size B (B >= 2^R); n/2^R threads
   PS_DEV static void run(uint32_t tid, Fr* a, uint32_t n, uint32_t B, const Fr* tw) {
     const uint32_t q = B >> R;
@@ -68,7 +75,8 @@ struct NttDifK {
 
 template <int R>
 struct NttDitK {
-  static constexpr int BLOCK = 256;
+  static constexpr int BLOCK = PS_NTT_BLOCK;
+  static constexpr int MIN_BLOCKS = PS_NTT_MINB;
   // one launch = R stages that grow finished sub-transforms of size B0 to B0 * 2^R
   PS_DEV static void run(uint32_t tid, Fr* a, uint32_t n, uint32_t B0, const Fr* tw_inv) {
     const uint32_t blk = tid / B0, j = tid % B0;
