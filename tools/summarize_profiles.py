@@ -42,6 +42,19 @@ def launches(src, dst, title):
         f.write("| kernel | launches | total ms | share | block | last grid |\n|---|---:|---:|---:|---|---|\n")
         for k, (c, v, blk, grd) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("| `%s` | %d | %.3f | %.1f%% | %s | %s |\n" % (k, c, v / 1e6, 100 * v / tot, blk, grd))
+        # shares inside the last complete MSM step (MsmCountK ... MsmFinalK): the timed region's unit
+        starts = [n for n, (_, k, _) in enumerate(order) if k.startswith("MsmCountK")]
+        ends = [n for n, (_, k, _) in enumerate(order) if k.startswith("MsmFinalK")]
+        if starts and ends and ends[-1] > starts[0]:
+            e = ends[-1]
+            b = max(x for x in starts if x < e)
+            step, stot = collections.OrderedDict(), 0.0
+            for _, k, v in order[b:e + 1]:
+                a = step.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += v; stot += v
+            f.write("\n## shares inside one MSM step (launch ids %s..%s, %.3f ms in total)\n\n" % (order[b][0], order[e][0], stot / 1e6))
+            f.write("| kernel | launches | total ms | share of the step |\n|---|---:|---:|---:|\n")
+            for k, (c, v) in sorted(step.items(), key=lambda kv: -kv[1][1]):
+                f.write("| `%s` | %d | %.3f | %.1f%% |\n" % (k, c, v / 1e6, 100 * v / stot))
         f.write("\n## launch sequence (id, kernel, us)\n\n```\n")
         for i, k, v in order:
             f.write("%s %s %.1f\n" % (i, k, v / 1e3))
