@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--tables", type=int, default=-1, help="precomputed window tables (-1 = all windows)")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--g2-log-n", type=int, default=20, help="also time a G2 MSM of 2^k points per GPU (0 = skip)")
     ap.add_argument("--groth16-log-n", type=int, default=20,
                     help="also time a full Groth16 prove on a sparse synthetic circuit of 2^k constraints (0 = skip)")
     args = ap.parse_args()
@@ -257,10 +258,35 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # secondary figure: G2 MSM (same pipeline over Fp2), resident scalars, every rank its own range
+    g2 = None
+    if args.g2_log_n:
+        n2 = 1 << args.g2_log_n
+        bases2 = be.bases_from_scalars(L.PS_G2, random_scalars_be(n2, 3000 + rank).tobytes(), args.window_bits, args.tables)
+        d_sc2 = torch.from_numpy(be_to_le_limbs(random_scalars_be(n2, 4000 + rank)).view(np.int32)).to(dev)
+        d_part2 = torch.zeros(384, dtype=torch.uint8, device=dev)
+        step2 = lambda: be._check(lib.ps_msm_device(be.ctx, bases2.handle, 0, C.c_void_p(d_sc2.data_ptr()), n2, C.c_void_p(d_part2.data_ptr())))
+        for _ in range(3):
+            step2()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.steps):
+            step2()
+        f1.record(stream)
+        barrier()
+        info2 = (C.c_int * 4)()
+        be._check(lib.ps_bases_info(bases2.handle, info2))
+        g2 = {"ms": f0.elapsed_time(f1), "phases": be.msm_timing(), "c": info2[0], "W": info2[1]}
+        bases2.close()
+        del d_sc2
+
+    t = torch.tensor([ms_total, e2e_s * 1e3, g2["ms"] if g2 else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms = float(t[0]), float(t[1])
+    if g2:
+        g2["ms"] = float(t[2])
     if rank != 0:
         if args.groth16_log_n:
             bases.close()
@@ -319,6 +345,14 @@ def main():
                      "hbm": {"achieved_gbs": gather_bytes / accum_s / 1e9 if accum_s else None,
                              "what": "base gather 96 B + entry 4 B per mixed add"}},
     }
+    if g2:
+        n2 = 1 << args.g2_log_n
+        acc2 = g2["phases"]["accumulate_ms"] * 1e-3
+        imad2 = float(n2) * g2["W"] * 28.0 * IMAD_PER_FP_MUL     # G2 mixed add: 8 Fp2 mul + 2 Fp2 sqr = 28 Fp mul
+        line["g2_msm"] = {"metric": "g2_msm_points_per_s", "value": float(n2) * world * args.steps / (g2["ms"] * 1e-3),
+                          "unit": UNIT, "points_per_gpu": n2, "ms_per_step": g2["ms"] / args.steps, "window_bits": g2["c"],
+                          "windows": g2["W"], "phases_ms_last_step": g2["phases"],
+                          "roofline_frac_accumulate_kernel": (imad2 / acc2) / imad_peak if acc2 > 0 and imad_peak else None}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args)
     if args.groth16_log_n:

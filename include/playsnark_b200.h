@@ -170,7 +170,8 @@ int ps_bench_fieldmul(ps_ctx* ctx, int field, int iters, double* mul_per_s, doub
  * [0] digits+sort, [1] bucket-accumulate kernel, [2] partial merge, [3] bucket reduce, [4] total */
 int ps_last_msm_timing(ps_ctx* ctx, float out_ms[5]);
 /* device time in ms of the last ps_g16_prove: [0] quotient (aggregate / interpolation / NTT division),
- * [1] MSM A (G1), [2] MSM C (G1), [3] MSM B (G2), [4] normalise + encode, [5] total                 */
+ * [1] MSM A (G1), [2] MSM C (G1), [3] what remains of MSM B (G2, which runs concurrently on a second
+ * stream) after C has finished, [4] normalise + encode, [5] total                                 */
 int ps_last_prove_timing(ps_ctx* ctx, float out_ms[6]);
 
 #ifdef __cplusplus

@@ -55,11 +55,11 @@ struct FixedBaseTableK {
     table[tid] = xyzz_to_affine_c(r);
   }
 };
-// out[i] = scalar[i] * generator  (scalars: standard-form limbs)
+// out[i] = scalar[i] * generator  (scalars: standard-form limbs), left in XYZZ form
 template <class F>
 struct FixedBaseMulK {
   static constexpr int BLOCK = 128;
-  PS_DEV static void run(uint32_t i, const uint32_t* scalars, const Affine<F>* table, Affine<F>* out) {
+  PS_DEV static void run(uint32_t i, const uint32_t* scalars, const Affine<F>* table, XYZZ<F>* out) {
     XYZZ<F> acc = XYZZ<F>::inf();
     for (int j = 0; j < 8; j++) {
       uint32_t limb = scalars[(size_t)i * 8 + j];
@@ -68,17 +68,44 @@ struct FixedBaseMulK {
         if (d) xyzz_madd_c(acc, table[(uint32_t)(4 * j + b) * 255 + d - 1]);
       }
     }
-    out[i] = xyzz_to_affine_c(acc);
+    out[i] = acc;
   }
 };
-// next[i] = 2^c * prev[i]
+// next[i] = 2^c * prev[i], left in XYZZ form
 template <class F>
 struct ShiftTableK {
   static constexpr int BLOCK = 128;
-  PS_DEV static void run(uint32_t i, const Affine<F>* prev, Affine<F>* next, int c) {
+  PS_DEV static void run(uint32_t i, const Affine<F>* prev, XYZZ<F>* next, int c) {
     XYZZ<F> r = XYZZ<F>::from_affine(prev[i]);
     for (int d = 0; d < c; d++) r = xyzz_dbl_c(r);
-    next[i] = xyzz_to_affine_c(r);
+    next[i] = r;
+  }
+};
+// XYZZ -> affine for K consecutive points per thread with ONE field inversion (Montgomery's trick on ZZZ)
+template <class F>
+struct BatchToAffineK {
+  static constexpr int BLOCK = 64;
+  static constexpr uint32_t K = sizeof(F) == sizeof(Fp) ? 8 : 4;
+  PS_DEV static void run(uint32_t t, uint32_t n, const XYZZ<F>* in, Affine<F>* out) {
+    const uint32_t i0 = t * K;
+    F pre[K];
+    F acc = F::one();
+#pragma unroll
+    for (uint32_t k = 0; k < K; k++) {
+      if (i0 + k < n) { F z = in[i0 + k].zzz; if (!in[i0 + k].zz.is_zero()) acc = acc * z; }
+      pre[k] = acc;
+    }
+    F inv = FieldInv<F>::inv(acc);
+#pragma unroll
+    for (uint32_t kk = K; kk-- > 0;) {
+      if (i0 + kk >= n) continue;
+      XYZZ<F> p = in[i0 + kk];
+      if (p.zz.is_zero()) { out[i0 + kk] = Affine<F>::inf(); continue; }
+      F zzz_inv = kk > 0 ? inv * pre[kk - 1] : inv;
+      inv = inv * p.zzz;
+      F tt = zzz_inv * p.zz;
+      out[i0 + kk] = Affine<F>{p.x * tt.sqr(), p.y * zzz_inv};
+    }
   }
 };
 
@@ -114,6 +141,7 @@ int begin_call(ps_ctx* ctx) {
 #if PS_GPU
   PS_CUDA_TRY(cudaSetDevice(ctx->device));
 #endif
+  PS_TRY(ctx->arena2.reset());
   return ctx->arena.reset();
 }
 
@@ -121,8 +149,14 @@ int begin_call(ps_ctx* ctx) {
 template <class F>
 int bases_finish(ps_ctx* ctx, ps_bases* b) {
   Affine<F>* tab = (Affine<F>*)b->tab;
-  for (int t = 1; t < b->T; t++)
-    PS_LAUNCH(ShiftTableK<F>, ctx->stream, b->n, (const Affine<F>*)(tab + (size_t)(t - 1) * b->n), tab + (size_t)t * b->n, b->c);
+  if (b->T <= 1) return PS_OK;
+  XYZZ<F>* tmp = ctx->arena.take<XYZZ<F>>(b->n);
+  if (!tmp) return PS_ERR_ALLOC;
+  const size_t groups = (b->n + BatchToAffineK<F>::K - 1) / BatchToAffineK<F>::K;
+  for (int t = 1; t < b->T; t++) {
+    PS_LAUNCH(ShiftTableK<F>, ctx->stream, b->n, (const Affine<F>*)(tab + (size_t)(t - 1) * b->n), tmp, b->c);
+    PS_LAUNCH(BatchToAffineK<F>, ctx->stream, groups, (uint32_t)b->n, (const XYZZ<F>*)tmp, tab + (size_t)t * b->n);
+  }
   return PS_OK;
 }
 
@@ -344,6 +378,14 @@ int ps_ctx_create(int device, ps_ctx** out) {
   PS_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   ctx->stream = st;
   ctx->own_stream = true;
+  cudaStream_t st2;
+  PS_CUDA_TRY(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+  ctx->stream2 = st2;
+  {
+    cudaEvent_t e;
+    PS_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_fork = e;
+    PS_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_join = e;
+  }
   for (int i = 0; i < 5; i++) {
     cudaEvent_t e;
     PS_CUDA_TRY(cudaEventCreate(&e));
@@ -356,6 +398,7 @@ int ps_ctx_create(int device, ps_ctx** out) {
   }
 #endif
   ctx->arena.stream = ctx->stream;
+  ctx->arena2.stream = ctx->stream2;
   *out = ctx;
   return PS_OK;
 }
@@ -389,7 +432,9 @@ int ps_ctx_sync(ps_ctx* ctx) { return ctx ? dev_sync(ctx->stream) : PS_ERR_ARG; 
 void ps_ctx_destroy(ps_ctx* ctx) {
   if (!ctx) return;
   dev_sync(ctx->stream);
+  dev_sync(ctx->stream2);
   ctx->arena.release();
+  ctx->arena2.release();
   for (auto& t : ctx->ntt_cache) t.release();
   dev_free(ctx->fixed_base[0]);
   dev_free(ctx->fixed_base[1]);
@@ -397,6 +442,9 @@ void ps_ctx_destroy(ps_ctx* ctx) {
   for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy((cudaEvent_t)ctx->ev[i]);
   for (int i = 0; i < 6; i++) if (ctx->evp[i]) cudaEventDestroy((cudaEvent_t)ctx->evp[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_fork) cudaEventDestroy((cudaEvent_t)ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy((cudaEvent_t)ctx->ev_join);
 #endif
   delete ctx;
 }
@@ -438,12 +486,20 @@ int ps_bases_from_scalars(ps_ctx* ctx, int group, const uint8_t* scalars_be, siz
     if (group == PS_G1) {
       const G1Affine* tbl = nullptr;
       rc = fixed_base_table<Fp>(ctx, &tbl);
-      if (rc == PS_OK) rc = ps_launch<FixedBaseMulK<Fp>>(ctx->stream, n, (const uint32_t*)d_sc, tbl, (G1Affine*)b->tab);
+      G1XYZZ* tmp = ctx->arena.take<G1XYZZ>(n);
+      if (rc == PS_OK && !tmp) rc = PS_ERR_ALLOC;
+      if (rc == PS_OK) rc = ps_launch<FixedBaseMulK<Fp>>(ctx->stream, n, (const uint32_t*)d_sc, tbl, tmp);
+      if (rc == PS_OK) rc = ps_launch<BatchToAffineK<Fp>>(ctx->stream, (n + BatchToAffineK<Fp>::K - 1) / BatchToAffineK<Fp>::K, (uint32_t)n,
+                                                       (const G1XYZZ*)tmp, (G1Affine*)b->tab);
       if (rc == PS_OK) rc = bases_finish<Fp>(ctx, b);
     } else {
       const G2Affine* tbl = nullptr;
       rc = fixed_base_table<Fp2>(ctx, &tbl);
-      if (rc == PS_OK) rc = ps_launch<FixedBaseMulK<Fp2>>(ctx->stream, n, (const uint32_t*)d_sc, tbl, (G2Affine*)b->tab);
+      G2XYZZ* tmp = ctx->arena.take<G2XYZZ>(n);
+      if (rc == PS_OK && !tmp) rc = PS_ERR_ALLOC;
+      if (rc == PS_OK) rc = ps_launch<FixedBaseMulK<Fp2>>(ctx->stream, n, (const uint32_t*)d_sc, tbl, tmp);
+      if (rc == PS_OK) rc = ps_launch<BatchToAffineK<Fp2>>(ctx->stream, (n + BatchToAffineK<Fp2>::K - 1) / BatchToAffineK<Fp2>::K, (uint32_t)n,
+                                                        (const G2XYZZ*)tmp, (G2Affine*)b->tab);
       if (rc == PS_OK) rc = bases_finish<Fp2>(ctx, b);
     }
   }
@@ -777,11 +833,18 @@ int ps_g16_prove(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const ui
   G1XYZZ* resG1 = ctx->arena.take<G1XYZZ>(2);
   G2XYZZ* resG2 = ctx->arena.take<G2XYZZ>(1);
   if (!resG1 || !resG2) return PS_ERR_ALLOC;
+  // the G2 MSM is independent of the two G1 ones: it runs on the secondary stream so that its serial
+  // tails and its register-bound accumulate kernel overlap with the G1 work
+  PS_TRY(ctx_fork(ctx));
+  {
+    SecondaryScope scope(ctx);
+    PS_TRY(msm_on_bases<Fp2>(ctx, key->B, 0, (const uint32_t*)sc.scB, sc.nB, 1, resG2));
+  }
   PS_TRY(msm_on_bases<Fp>(ctx, key->A, 0, (const uint32_t*)sc.scA, sc.nA, 1, resG1));
   PS_TRY(ctx_prove_event(ctx, 2));
   PS_TRY(msm_on_bases<Fp>(ctx, key->C, 0, (const uint32_t*)sc.scC, sc.nC, 1, resG1 + 1));
   PS_TRY(ctx_prove_event(ctx, 3));
-  PS_TRY(msm_on_bases<Fp2>(ctx, key->B, 0, (const uint32_t*)sc.scB, sc.nB, 1, resG2));
+  PS_TRY(ctx_join(ctx));
   PS_TRY(ctx_prove_event(ctx, 4));
   uint8_t ac[96];
   PS_TRY(encode_points<Fp>(ctx, resG1, 2, ac));

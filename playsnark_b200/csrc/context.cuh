@@ -2,6 +2,7 @@
 #pragma once
 #include "backend.cuh"
 #include "ntt.cuh"
+#include <utility>
 
 struct ps_ctx {
   int device = 0;
@@ -9,6 +10,12 @@ struct ps_ctx {
   bool own_stream = false;
   int sm_count = 148;
   ps::Arena arena;                 // per-call scratch, persists across calls
+  // secondary stream + scratch: lets an independent MSM (Groth16's G2 one) overlap the others
+  ps::ps_stream_t stream2 = nullptr;
+  ps::Arena arena2;
+  void* ev_fork = nullptr;         // cudaEvent_t: inputs ready on `stream`
+  void* ev_join = nullptr;         // cudaEvent_t: secondary work done on `stream2`
+  bool timing_events = true;       // phase events are only recorded for work on the primary stream
   ps::NttTables ntt_cache[31];     // twiddles by log2(size), built on first use
   void* fixed_base[2] = {nullptr, nullptr};  // 32 x 255 affine multiples of the G1 / G2 generator
   // phase events of the last MSM (cudaEvent_t): start, sorted, accumulated, combined, reduced
@@ -30,6 +37,7 @@ inline int ctx_ntt_tables(ps_ctx* ctx, int log_n, const NttTables** out) {
   return PS_OK;
 }
 inline int ctx_event(ps_ctx* ctx, int i) {
+  if (!ctx->timing_events) return PS_OK;
 #if PS_GPU
   if (ctx->ev[i]) PS_CUDA_TRY(cudaEventRecord((cudaEvent_t)ctx->ev[i], ctx->stream));
 #else
@@ -42,6 +50,39 @@ inline int ctx_prove_event(ps_ctx* ctx, int i) {
   if (ctx->evp[i]) PS_CUDA_TRY(cudaEventRecord((cudaEvent_t)ctx->evp[i], ctx->stream));
 #else
   (void)ctx; (void)i;
+#endif
+  return PS_OK;
+}
+
+// Runs the enclosed calls on the context's secondary stream / arena (host code is sequential, so
+// swapping the two fields is enough); the destructor swaps back.
+struct SecondaryScope {
+  ps_ctx* ctx;
+  explicit SecondaryScope(ps_ctx* c) : ctx(c) { swap(); ctx->timing_events = false; }
+  ~SecondaryScope() { swap(); ctx->timing_events = true; }
+  void swap() {
+    ps_stream_t s = ctx->stream; ctx->stream = ctx->stream2; ctx->stream2 = s;
+    std::swap(ctx->arena.blocks, ctx->arena2.blocks);
+    std::swap(ctx->arena.stream, ctx->arena2.stream);
+  }
+};
+// secondary stream waits for everything enqueued so far on the primary one
+inline int ctx_fork(ps_ctx* ctx) {
+#if PS_GPU
+  PS_CUDA_TRY(cudaEventRecord((cudaEvent_t)ctx->ev_fork, ctx->stream));
+  PS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream2, (cudaEvent_t)ctx->ev_fork, 0));
+#else
+  (void)ctx;
+#endif
+  return PS_OK;
+}
+// primary stream waits for everything enqueued so far on the secondary one
+inline int ctx_join(ps_ctx* ctx) {
+#if PS_GPU
+  PS_CUDA_TRY(cudaEventRecord((cudaEvent_t)ctx->ev_join, ctx->stream2));
+  PS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, (cudaEvent_t)ctx->ev_join, 0));
+#else
+  (void)ctx;
 #endif
   return PS_OK;
 }
