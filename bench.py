@@ -391,7 +391,7 @@ def groth16_section(be, args, dist=None, dev="cuda"):
     r, s = smp.fr(), smp.fr()
     wb = b"".join(v.to_bytes(32, "big") for v in wit)
     t0 = time.perf_counter()
-    if rank == 0:
+    if rank in (0, 1):       # rank 1 shares the quotient work (second aggregate polynomial)
         sq._resident(be)
     tr._resident(be); be.sync()
     t_load = time.perf_counter() - t0

@@ -146,6 +146,19 @@ const ps_bases* ps_g16_key_bases(const ps_g16_key* key, int which);
 int ps_g16_scalars(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const uint8_t* witness_be,
                    const uint8_t* r_be, const uint8_t* s_be, void* d_scA, void* d_scC, void* d_scB);
 
+/* the three partial MSMs of one rank in one call (G2 on the context's second stream):
+ * first[i] / count[i] = index range of MSM i (0 = A, 1 = C, 2 = B) inside the key's base sets, scalar
+ * pointers already offset to that range; d_partials receives [A 192 B | C 192 B | B 384 B] (XYZZ).    */
+int ps_g16_msm_partials(ps_ctx* ctx, const ps_g16_key* key, const void* d_scA, const void* d_scC, const void* d_scB,
+                        const size_t first[3], const size_t count[3], void* d_partials);
+/* splitting the quotient over two GPUs (sparse QAP): ps_qap_aggregate_one interpolates one aggregate
+ * polynomial (which = 0: a, 1: b; n Montgomery coefficients in device memory); after the exchange
+ * ps_g16_scalars_from_ab does the gate check, the division and the scalar assembly.               */
+int ps_qap_aggregate_one(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_be, int which, void* d_out_coef);
+int ps_g16_scalars_from_ab(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const uint8_t* witness_be,
+                           const uint8_t* r_be, const uint8_t* s_be, const void* d_a, const void* d_b,
+                           void* d_scA, void* d_scC, void* d_scB);
+
 /* ---- PHGR13 / Pinocchio (pinochio.go) ------------------------------------------------------------ */
 /* PHGR13EvalKey (pinochio.go:37-62): gsi[n-1]; vs, ys, vas, was, yas, vbs, wbs, ybs [n_mid] in G1
  * (wbs is typed []G2 in the reference but holds G1 points, pinochio.go:114,136); ws [n_mid] G2. */

@@ -50,6 +50,9 @@ SYMBOLS = [
     ("ps_g16_scalar_count", _SZ, [_P, _I]),
     ("ps_g16_key_bases", _P, [_P, _I]),
     ("ps_g16_scalars", _I, [_P, _P, _P, _P, _B, _B, _P, _P, _P]),
+    ("ps_g16_msm_partials", _I, [_P, _P, _P, _P, _P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _P]),
+    ("ps_qap_aggregate_one", _I, [_P, _P, _B, _I, _P]),
+    ("ps_g16_scalars_from_ab", _I, [_P, _P, _P, _B, _B, _B, _P, _P, _P, _P, _P]),
     ("ps_phgr13_key_load", _I, [_P, _SZ, _SZ, _I] + [_B] * 10 + [C.POINTER(_P)]),
     ("ps_phgr13_key_free", None, [_P]),
     ("ps_phgr13_prove", _I, [_P, _P, _P, _P, _P, _P]),

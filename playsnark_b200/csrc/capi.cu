@@ -870,6 +870,96 @@ const ps_bases* ps_g16_key_bases(const ps_g16_key* key, int which) {
   return which == 0 ? key->A : (which == 1 ? key->C : (which == 2 ? key->B : nullptr));
 }
 
+int ps_g16_msm_partials(ps_ctx* ctx, const ps_g16_key* key, const void* d_scA, const void* d_scC, const void* d_scB,
+                        const size_t first[3], const size_t count[3], void* d_partials) {
+  if (!ctx || !key || !d_scA || !d_scC || !d_scB || !first || !count || !d_partials) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  uint8_t* out = (uint8_t*)d_partials;  // [A: 192 B | C: 192 B | B: 384 B]
+  PS_TRY(ctx_fork(ctx));
+  {
+    SecondaryScope scope(ctx);
+    PS_TRY(msm_on_bases<Fp2>(ctx, key->B, first[2], (const uint32_t*)d_scB, count[2], 0, (G2XYZZ*)(out + 384)));
+  }
+  PS_TRY(msm_on_bases<Fp>(ctx, key->A, first[0], (const uint32_t*)d_scA, count[0], 0, (G1XYZZ*)out));
+  PS_TRY(msm_on_bases<Fp>(ctx, key->C, first[1], (const uint32_t*)d_scC, count[1], 0, (G1XYZZ*)(out + 192)));
+  return ctx_join(ctx);
+}
+
+// One aggregate polynomial of the sparse QAP in coefficient form (which = 0: a, 1: b): the SpMV and
+// the interpolation on {1..n} for that polynomial only, so that two GPUs can share the work.
+int ps_qap_aggregate_one(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_be, int which, void* d_out_coef) {
+  if (!ctx || !qap || !witness_be || !d_out_coef || which < 0 || which > 1) return PS_ERR_ARG;
+  if (qap->dense) return PS_ERR_UNSUPPORTED;
+  PS_TRY(begin_call(ctx));
+  const SparseQap* sq = (const SparseQap*)qap->sparse;
+  const uint32_t n = (uint32_t)qap->n;
+  ps_stream_t st = ctx->stream;
+  uint32_t *d_w = nullptr, *d_err = nullptr;
+  PS_TRY(stage_scalars(ctx, witness_be, qap->m, 1, &d_w, &d_err));
+  Fr* ev = ctx->arena.take<Fr>((size_t)3 * n);
+  if (!ev) return PS_ERR_ALLOC;
+  PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
+            (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
+            (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, (const Fr*)d_w, ev);
+  PS_TRY(interpolate_ap(ctx, sq, n, qap->log_np, 1, ev + (size_t)which * n, (Fr*)d_out_coef));
+  return check_err_flag(ctx, d_err, PS_ERR_ENCODING);
+}
+
+// ps_g16_scalars with the aggregate polynomials a, b already interpolated (device, n Montgomery
+// coefficients each, e.g. by ps_qap_aggregate_one on two GPUs): gate check, series division, assembly.
+int ps_g16_scalars_from_ab(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const uint8_t* witness_be, const uint8_t* r_be,
+                           const uint8_t* s_be, const void* d_a, const void* d_b, void* d_scA, void* d_scC, void* d_scB) {
+  if (!key || !qap || !witness_be || !r_be || !s_be || !d_a || !d_b || !d_scA || !d_scC || !d_scB) return PS_ERR_ARG;
+  if (qap->dense) return PS_ERR_UNSUPPORTED;
+  if (key->n != qap->n || key->n_nio != qap->n_io) return PS_ERR_LENGTH;
+  PS_TRY(begin_call(ctx));
+  ps_stream_t st = ctx->stream;
+  const SparseQap* sq = (const SparseQap*)qap->sparse;
+  const uint32_t n = (uint32_t)qap->n;
+  const size_t nio = qap->n_io, diff = qap->m - qap->n_io;
+  uint32_t *d_w = nullptr, *d_err = nullptr;
+  PS_TRY(stage_scalars(ctx, witness_be, qap->m, 1, &d_w, &d_err));
+  Fr* w = (Fr*)d_w;
+  Fr* ev = ctx->arena.take<Fr>((size_t)3 * n);
+  Fr* h = ctx->arena.take<Fr>(n);
+  uint32_t* flag = ctx->arena.take<uint32_t>(1);
+  if (!ev || !h || !flag) return PS_ERR_ALLOC;
+  PS_TRY(dev_memset(flag, 0, 4, st));
+  PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
+            (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
+            (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, (const Fr*)w, ev);
+  PS_LAUNCH(GateCheckK, st, n, n, (const Fr*)ev, flag);
+  const Fr* a = (const Fr*)d_a;
+  const Fr* b = (const Fr*)d_b;
+  PS_TRY(quotient_series(ctx, sq, n, qap->log_np, a, b, h, (Fr*)nullptr));
+  Fr hrs[2];
+  for (int t = 0; t < 2; t++) {
+    const uint8_t* src = t == 0 ? r_be : s_be;
+    Fr x;
+    for (int j = 0; j < 8; j++) {
+      const uint8_t* p = src + 4 * (7 - j);
+      x.v[j] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+    }
+    if (!limbs_lt_mod<FrParams>(x.v)) return PS_ERR_ENCODING;
+    hrs[t] = x.to_mont();
+  }
+  const Fr r = hrs[0], s = hrs[1], rs = hrs[0] * hrs[1];
+  Fr* scA = (Fr*)d_scA; Fr* scB = (Fr*)d_scB; Fr* scC = (Fr*)d_scC;
+  PS_LAUNCH(FrCopyK, st, n, a, scA);
+  PS_LAUNCH(FrSet3K, st, 2, r, Fr::one(), Fr::zero(), 2, scA + n);
+  PS_LAUNCH(FrCopyK, st, n, b, scB);
+  PS_LAUNCH(FrSet3K, st, 2, s, Fr::one(), Fr::zero(), 2, scB + n);
+  PS_LAUNCH(FrCopyK, st, nio, (const Fr*)(w + diff), scC);
+  PS_LAUNCH(FrCopyK, st, (size_t)n - 1, (const Fr*)h, scC + nio);
+  PS_LAUNCH(FrAxpbyK, st, n, s, a, r, b, scC + nio + (n - 1));
+  PS_LAUNCH(FrSet3K, st, 3, s, r, rs, 3, scC + nio + (n - 1) + n);
+  PS_LAUNCH(FrFromMontK, st, (size_t)n + 2, scA);
+  PS_LAUNCH(FrFromMontK, st, (size_t)n + 2, scB);
+  PS_LAUNCH(FrFromMontK, st, nio + (n - 1) + n + 3, scC);
+  PS_TRY(check_err_flag(ctx, d_err, PS_ERR_ENCODING));
+  return check_err_flag(ctx, flag, PS_ERR_REMAINDER);
+}
+
 int ps_g16_scalars(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const uint8_t* witness_be, const uint8_t* r_be,
                    const uint8_t* s_be, void* d_scA, void* d_scC, void* d_scB) {
   if (!key || !qap || !witness_be || !r_be || !s_be || !d_scA || !d_scC || !d_scB) return PS_ERR_ARG;

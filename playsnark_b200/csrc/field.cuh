@@ -234,6 +234,24 @@ struct alignas(16) Fe {
 using Fp = Fe<FpParams>;
 using Fr = Fe<FrParams>;
 
+// explicit 128-bit loads of a field element (the compiler otherwise tends to issue one 32-bit load per
+// limb when the value feeds multiplier operands directly, e.g. NTT twiddles)
+template <class P>
+PS_DEV Fe<P> fe_ld(const Fe<P>* p) {
+#ifdef __CUDA_ARCH__
+  Fe<P> r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < P::N / 4; i++) {
+    uint4 t = __ldg(q + i);
+    r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w;
+  }
+  return r;
+#else
+  return *p;
+#endif
+}
+
 // Out-of-line product: one copy of the ~300-instruction multiplier per field instead of one per call
 // site.  Used wherever code size / compile time matters more than the call overhead (Fp2 towers,
 // cold paths); the hot G1 kernels use the inlined operator*.

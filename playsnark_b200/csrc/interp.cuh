@@ -177,7 +177,7 @@ struct InterpTwistK {
   static constexpr int BLOCK = 256;
   PS_DEV static void run(uint32_t idx, uint32_t two_s, uint32_t tw_step, Fr scale, const Fr* tw, Fr* Cbuf) {
     uint32_t t = idx % two_s;
-    Cbuf[idx] = Cbuf[idx] * scale * tw[(size_t)t * tw_step];
+    Cbuf[idx] = Cbuf[idx] * scale * fe_ld(tw + (size_t)t * tw_step);
   }
 };
 // odd halves: Enext[poly][p][2s + e] = C[poly][p][e]                                     (thread over P*n)

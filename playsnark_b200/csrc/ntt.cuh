@@ -64,7 +64,7 @@ struct NttDifK {
           uint32_t p = j + (uint32_t)i * q;
           Fr u = x[k], v = x[k2];
           x[k] = u + v;
-          x[k2] = (u - v) * tw[(size_t)p * tw_mul];
+          x[k2] = (u - v) * fe_ld(tw + (size_t)p * tw_mul);
         }
       }
     }
@@ -94,7 +94,7 @@ struct NttDitK {
         for (int i = 0; i < hl; i++) {
           const int k = grp * 2 * hl + i, k2 = k + hl;
           uint32_t p = j + (uint32_t)i * B0;
-          Fr u = x[k], v = x[k2] * tw_inv[(size_t)p * tw_mul];
+          Fr u = x[k], v = x[k2] * fe_ld(tw_inv + (size_t)p * tw_mul);
           x[k] = u + v;
           x[k2] = u - v;
         }
@@ -134,10 +134,13 @@ inline Fr fr_root_of_unity(int log_n) {
 // Batched forward DIF: `len` elements = len / 2^log_block independent transforms of size 2^log_block
 // laid out back to back (natural -> bit-reversed inside each block).  tw[i] = omega_{n_tw}^i for
 // i < n_tw/2 with n_tw >= 2^log_block (a block transform is the tail of a larger transform's stages).
+#ifndef PS_NTT_MAXR
+#define PS_NTT_MAXR 3
+#endif
 inline int ntt_forward_blocks(ps_stream_t st, Fr* a, size_t len, int log_block, const Fr* tw, uint32_t n_tw) {
   int done = 0;
   while (done < log_block) {
-    int r = log_block - done >= 3 ? 3 : log_block - done;
+    int r = log_block - done >= PS_NTT_MAXR ? PS_NTT_MAXR : log_block - done;
     uint32_t B = 1u << (log_block - done);
     if (r == 3) PS_LAUNCH(NttDifK<3>, st, len >> 3, a, n_tw, B, tw);
     else if (r == 2) PS_LAUNCH(NttDifK<2>, st, len >> 2, a, n_tw, B, tw);
@@ -150,7 +153,7 @@ inline int ntt_forward_blocks(ps_stream_t st, Fr* a, size_t len, int log_block, 
 inline int ntt_inverse_blocks_unscaled(ps_stream_t st, Fr* a, size_t len, int log_block, const Fr* tw_inv, uint32_t n_tw) {
   int done = 0;
   while (done < log_block) {
-    int r = log_block - done >= 3 ? 3 : log_block - done;
+    int r = log_block - done >= PS_NTT_MAXR ? PS_NTT_MAXR : log_block - done;
     uint32_t B0 = 1u << done;
     if (r == 3) PS_LAUNCH(NttDitK<3>, st, len >> 3, a, n_tw, B0, tw_inv);
     else if (r == 2) PS_LAUNCH(NttDitK<2>, st, len >> 2, a, n_tw, B0, tw_inv);

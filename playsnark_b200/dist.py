@@ -61,11 +61,12 @@ class _KeyBases:
         self.handle, self.group = handle, group
 
 
-def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device="cpu"):
-    """Groth16Prove (groth16.go:122-211) with its three MSMs sharded by point range over the ranks
-    of `dist`.  Every rank holds the proving key; rank 0 holds the QAP, runs the quotient and
-    broadcasts the scalar vectors; partial points are all-gathered and summed on rank 0, which
-    returns (A, B, C) as compressed bytes (other ranks return None).  `witness` is only read on rank 0."""
+def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device="cpu", split_quotient: bool = True):
+    """Groth16Prove (groth16.go:122-211) over the ranks of `dist`.  Every rank holds the proving key.
+    Quotient: rank 0 (and, with split_quotient and a sparse QAP, rank 1 for the second aggregate
+    polynomial) -- `q` and `witness` are only read there.  The three scalar vectors are broadcast, every
+    rank sums its index range of each MSM (G2 on its second stream), the 768-byte partials are
+    all-gathered and rank 0 adds and encodes.  Returns (A, B, C) compressed on rank 0, None elsewhere."""
     import torch
     from .api import _fr_bytes
     lib = be.lib
@@ -76,12 +77,35 @@ def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device=
     groups = [L.PS_G1, L.PS_G1, L.PS_G2]
     bufs = [torch.zeros((c, 8), dtype=torch.int32, device=device) for c in counts]
     status = torch.zeros(1, dtype=torch.int32, device=device)
-    if rank == 0:
-        st = lib.ps_g16_scalars(be.ctx, kh, q._resident(be), _fr_bytes(witness), _fr_bytes([r]), _fr_bytes([s]),
-                                C.c_void_p(bufs[0].data_ptr()), C.c_void_p(bufs[1].data_ptr()), C.c_void_p(bufs[2].data_ptr()))
-        status[0] = st
-    if world > 1:
+    split = bool(split_quotient and world > 1 and not getattr(q, "left", None) is None and type(q).__name__ == "SparseQAP")
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    if split:
+        n = q.nbGates
+        wb = _fr_bytes(witness) if rank in (0, 1) else None
+        coef_b = torch.zeros((n, 8), dtype=torch.int32, device=device)
+        if rank == 1:
+            status[0] = lib.ps_qap_aggregate_one(be.ctx, q._resident(be), wb, 1, ptr(coef_b))
+            be.sync()
+        if rank == 0:
+            coef_a = torch.zeros((n, 8), dtype=torch.int32, device=device)
+            st0 = lib.ps_qap_aggregate_one(be.ctx, q._resident(be), wb, 0, ptr(coef_a))
+            be.sync()
+        dist.broadcast(coef_b, src=1)
+        if rank == 0:
+            st = st0 or lib.ps_g16_scalars_from_ab(be.ctx, kh, q._resident(be), wb, _fr_bytes([r]), _fr_bytes([s]), ptr(coef_a),
+                                                   ptr(coef_b), ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]))
+            status[0] = st
+        st1 = status.clone()
+        dist.broadcast(st1, src=1)
         dist.broadcast(status, src=0)
+        if int(status[0]) == 0 and int(st1[0]) != 0:
+            status = st1
+    else:
+        if rank == 0:
+            status[0] = lib.ps_g16_scalars(be.ctx, kh, q._resident(be), _fr_bytes(witness), _fr_bytes([r]), _fr_bytes([s]),
+                                           ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]))
+        if world > 1:
+            dist.broadcast(status, src=0)
     st = int(status[0])
     if st == L.PS_ERR_REMAINDER:
         raise ArithmeticError("apocalypse")
@@ -91,16 +115,17 @@ def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device=
             dist.broadcast(b, src=0)
     sizes = [PARTIAL_BYTES[g] for g in groups]
     part = torch.zeros(sum(sizes), dtype=torch.uint8, device=device)
-    off = 0
-    for w in range(3):
-        lo, hi = shard_range(counts[w], rank, world)
-        kb = _KeyBases(C.c_void_p(lib.ps_g16_key_bases(kh, w)), groups[w])
-        msm_partial(be, kb, bufs[w][lo:hi], hi - lo, part[off:off + sizes[w]], first=lo)
-        off += sizes[w]
+    ranges = [shard_range(counts[w], rank, world) for w in range(3)]
+    first = (C.c_size_t * 3)(*[lo for lo, _ in ranges])
+    cnt = (C.c_size_t * 3)(*[hi - lo for lo, hi in ranges])
+    views = [bufs[w][ranges[w][0]:ranges[w][1]] for w in range(3)]
+    be._check(lib.ps_g16_msm_partials(be.ctx, kh, ptr(views[0]) if cnt[0] else ptr(bufs[0]), ptr(views[1]) if cnt[1] else ptr(bufs[1]),
+                                      ptr(views[2]) if cnt[2] else ptr(bufs[2]), first, cnt, ptr(part)))
     if world > 1:
         parts = [torch.zeros_like(part) for _ in range(world)]
         dist.all_gather(parts, part)
     else:
+        be.sync()
         parts = [part]
     if rank != 0:
         return None

@@ -43,6 +43,23 @@ res = D.groth16_prove_sharded(be, H.mirror_g16_setup(tr), H.mirror_qap(oq), wit,
 if rank == 0:
     want = O.groth16_prove(tr, oq, wit, rr, ss)
     assert res == (O.g1_compress(want["A"]), O.g2_compress(want["B"]), O.g1_compress(want["C"]))
+# the same through the sparse form with the quotient split over ranks 0 and 1
+r2, wit2 = H.mixed_circuit(16, 9, 8)
+oq2 = O.to_qap(r2)
+sq2 = api.SparseQAP.from_dense_rows(len(r2.vars), r2.nb_io(), r2.left, r2.right, r2.out)
+smp2 = O.Sampler(9)
+tr2 = O.groth16_setup(oq2, smp2)
+r3, s3 = smp2.fr(), smp2.fr()
+res2 = D.groth16_prove_sharded(be, H.mirror_g16_setup(tr2), sq2, wit2, r3, s3, dist)
+if rank == 0:
+    want2 = O.groth16_prove(tr2, oq2, wit2, r3, s3)
+    assert res2 == (O.g1_compress(want2["A"]), O.g2_compress(want2["B"]), O.g1_compress(want2["C"]))
+bad2 = list(wit2); bad2[-1] = (bad2[-1] + 1) %% O.R
+try:
+    D.groth16_prove_sharded(be, H.mirror_g16_setup(tr2), sq2, bad2, r3, s3, dist)
+    raise SystemExit("expected apocalypse on every rank (split quotient)")
+except ArithmeticError:
+    pass
 bad = list(wit); bad[-1] = (bad[-1] + 1) %% O.R
 try:
     D.groth16_prove_sharded(be, H.mirror_g16_setup(tr), H.mirror_qap(oq), bad, rr, ss, dist)
