@@ -11,6 +11,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libplaysnark_b200.so")
 
+CU_SOURCES = [os.path.join(CSRC, "capi.cu"), os.path.join(CSRC, "accum_g2.cu")]
+
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
     "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
@@ -34,7 +36,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale(LIB, srcs):
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "capi.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["--threads", "2", "-o", LIB] + CU_SOURCES
     print("[playsnark_b200] " + " ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd, cwd=ROOT)
     return LIB
@@ -45,8 +47,8 @@ def build_host_emulation(out_dir: str) -> str:
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libps_hostemu.so")
     if stale(so, _sources()):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-DPS_HOST_EMU", "-shared", "-fPIC", "-o", so,
-                               os.path.join(CSRC, "capi.cu")], cwd=ROOT)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-DPS_HOST_EMU", "-shared", "-fPIC", "-o", so] + CU_SOURCES,
+                              cwd=ROOT)
     return so
 
 

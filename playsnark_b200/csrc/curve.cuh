@@ -12,31 +12,38 @@
 namespace ps {
 
 // ---- Fp2 ---------------------------------------------------------------------------------------
-struct alignas(16) Fp2 {
+// INLINE = false: base-field products are out-of-line calls (small code; used everywhere except the
+// G2 bucket-accumulation hot loop).  INLINE = true: products are inlined (no argument traffic through
+// the stack); same memory layout, so arrays of one kind can be viewed as the other.
+template <bool INLINE>
+struct alignas(16) Fp2T {
   Fp c0, c1;
-  PS_DEV static Fp2 zero() { return Fp2{Fp::zero(), Fp::zero()}; }
-  PS_DEV static Fp2 one() { return Fp2{Fp::one(), Fp::zero()}; }
+  PS_DEV static Fp mulp(const Fp& a, const Fp& b) { if (INLINE) return a * b; else return fe_mul_call(a, b); }
+  PS_DEV static Fp2T zero() { return Fp2T{Fp::zero(), Fp::zero()}; }
+  PS_DEV static Fp2T one() { return Fp2T{Fp::one(), Fp::zero()}; }
   PS_DEV bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
-  PS_DEV bool operator==(const Fp2& b) const { return c0 == b.c0 && c1 == b.c1; }
-  PS_DEV bool operator!=(const Fp2& b) const { return !(*this == b); }
-  PS_DEV friend Fp2 operator+(const Fp2& a, const Fp2& b) { return Fp2{a.c0 + b.c0, a.c1 + b.c1}; }
-  PS_DEV friend Fp2 operator-(const Fp2& a, const Fp2& b) { return Fp2{a.c0 - b.c0, a.c1 - b.c1}; }
-  PS_DEV Fp2 neg() const { return Fp2{c0.neg(), c1.neg()}; }
-  PS_DEV Fp2 dbl() const { return Fp2{c0.dbl(), c1.dbl()}; }
+  PS_DEV bool operator==(const Fp2T& b) const { return c0 == b.c0 && c1 == b.c1; }
+  PS_DEV bool operator!=(const Fp2T& b) const { return !(*this == b); }
+  PS_DEV friend Fp2T operator+(const Fp2T& a, const Fp2T& b) { return Fp2T{a.c0 + b.c0, a.c1 + b.c1}; }
+  PS_DEV friend Fp2T operator-(const Fp2T& a, const Fp2T& b) { return Fp2T{a.c0 - b.c0, a.c1 - b.c1}; }
+  PS_DEV Fp2T neg() const { return Fp2T{c0.neg(), c1.neg()}; }
+  PS_DEV Fp2T dbl() const { return Fp2T{c0.dbl(), c1.dbl()}; }
   // Karatsuba: 3 base-field products
-  PS_DEV friend Fp2 operator*(const Fp2& a, const Fp2& b) {
-    Fp t0 = fe_mul_call(a.c0, b.c0);
-    Fp t1 = fe_mul_call(a.c1, b.c1);
-    Fp t2 = fe_mul_call(a.c0 + a.c1, b.c0 + b.c1);
-    return Fp2{t0 - t1, t2 - t0 - t1};
+  PS_DEV friend Fp2T operator*(const Fp2T& a, const Fp2T& b) {
+    Fp t0 = mulp(a.c0, b.c0);
+    Fp t1 = mulp(a.c1, b.c1);
+    Fp t2 = mulp(a.c0 + a.c1, b.c0 + b.c1);
+    return Fp2T{t0 - t1, t2 - t0 - t1};
   }
   // (c0 + c1 u)^2 = (c0+c1)(c0-c1) + 2 c0 c1 u: 2 base-field products
-  PS_DEV Fp2 sqr() const {
+  PS_DEV Fp2T sqr() const {
     Fp s = c0 + c1, d = c0 - c1;
-    Fp m = fe_mul_call(c0, c1);
-    return Fp2{fe_mul_call(s, d), m.dbl()};
+    Fp m = mulp(c0, c1);
+    return Fp2T{mulp(s, d), m.dbl()};
   }
 };
+using Fp2 = Fp2T<false>;
+using Fp2I = Fp2T<true>;
 
 PS_DEV Fp2 fp2_inv(const Fp2& a) {
   Fp d = fp_inv(fe_mul_call(a.c0, a.c0) + fe_mul_call(a.c1, a.c1));
@@ -46,6 +53,9 @@ PS_DEV Fp2 fp2_inv(const Fp2& a) {
 template <class F> struct FieldInv;
 template <> struct FieldInv<Fp> { PS_DEV static Fp inv(const Fp& a) { return fp_inv(a); } };
 template <> struct FieldInv<Fp2> { PS_DEV static Fp2 inv(const Fp2& a) { return fp2_inv(a); } };
+template <> struct FieldInv<Fp2I> {
+  PS_DEV static Fp2I inv(const Fp2I& a) { Fp2 r = fp2_inv(Fp2{a.c0, a.c1}); return Fp2I{r.c0, r.c1}; }
+};
 
 // ---- points --------------------------------------------------------------------------------------
 template <class F>

@@ -147,6 +147,7 @@ struct MsmAccumK {
   static constexpr int BLOCK = 128;
   // registers: G1 fits 3 resident blocks per SM without spilling; G2 (Fp2) is register-bound
   static constexpr int MIN_BLOCKS = sizeof(F) == sizeof(Fp) ? PS_G1_MINB : PS_G2_MINB;
+  using Self = MsmAccumK<F>;
   PS_DEV static void run(uint32_t tid, uint32_t nb, uint32_t L, const Affine<F>* tab, const uint32_t* ent,
                          const uint32_t* off, XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid,
                          uint8_t* slot_fl) {
@@ -378,7 +379,7 @@ static constexpr int SCAN_THREADS = 256;
 static constexpr int SCAN_ITEMS = 8;
 static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* in, uint32_t* out, uint32_t* tile_sums, uint32_t n) {
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* in, uint32_t* out, uint32_t* tile_sums, uint32_t n) {
   __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
   uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS];
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* in,
   for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) out[base + i] = excl; excl += v[i]; }
   if (threadIdx.x == SCAN_THREADS - 1) tile_sums[blockIdx.x] = warp_sums[SCAN_THREADS / 32 - 1];
 }
-__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* sums, uint32_t n) {
+static __global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* sums, uint32_t n) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* sums, uint32_t n) 
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* out, const uint32_t* tile_sums, uint32_t n) {
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* out, const uint32_t* tile_sums, uint32_t n) {
   uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   uint32_t add = tile_sums[blockIdx.x];
 #pragma unroll
@@ -489,6 +490,22 @@ template <class F>
 int msm_accumulate_affine(ps_ctx* ctx, uint32_t nb, size_t max_ent, const Affine<F>* tab, const uint32_t* ent, const uint32_t* off0,
                           XYZZ<F>* buckets);
 
+// the hot kernel: G1 as is; G2 through the layout-identical Fp2I (inlined base-field products)
+template <class F>
+inline int launch_accum(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const Affine<F>* tab, const uint32_t* ent, const uint32_t* off,
+                        XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid, uint8_t* slot_fl) {
+  PS_LAUNCH(MsmAccumK<F>, st, T1, nb, L, tab, ent, off, buckets, slot_pt, slot_bid, slot_fl);
+  return PS_OK;
+}
+// defined in accum_g2.cu (its own translation unit: the fully inlined kernel dominates compile time)
+int launch_accum_g2(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const Affine<Fp2>* tab, const uint32_t* ent, const uint32_t* off,
+                    XYZZ<Fp2>* buckets, XYZZ<Fp2>* slot_pt, int32_t* slot_bid, uint8_t* slot_fl);
+template <>
+inline int launch_accum<Fp2>(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const Affine<Fp2>* tab, const uint32_t* ent,
+                             const uint32_t* off, XYZZ<Fp2>* buckets, XYZZ<Fp2>* slot_pt, int32_t* slot_bid, uint8_t* slot_fl) {
+  return launch_accum_g2(st, T1, nb, L, tab, ent, off, buckets, slot_pt, slot_bid, slot_fl);
+}
+
 template <class F>
 int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scalars, int mont, XYZZ<F>* d_out) {
   ps_stream_t st = ctx->stream;
@@ -535,7 +552,7 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
     int32_t* sb[2] = {ar.take<int32_t>(slots_a), ar.take<int32_t>(slots_b)};
     uint8_t* sf[2] = {ar.take<uint8_t>(slots_a), ar.take<uint8_t>(slots_b)};
     if (!sp[0] || !sp[1] || !sb[0] || !sb[1] || !sf[0] || !sf[1]) return PS_ERR_ALLOC;
-    PS_LAUNCH(MsmAccumK<F>, st, T1, nb, L, tab, (const uint32_t*)ent, (const uint32_t*)off, buckets, sp[0], sb[0], sf[0]);
+    PS_TRY((launch_accum<F>(st, T1, nb, L, tab, ent, off, buckets, sp[0], sb[0], sf[0])));
     PS_TRY(ctx_event(ctx, 2));
     PS_LAUNCH(MsmRunMergeK<F>, st, T1, (uint32_t)T1, buckets, sp[0], sb[0], (const uint8_t*)sf[0]);
     {
