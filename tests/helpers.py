@@ -210,3 +210,57 @@ def sparse_groth16_expected(sq, wit, tw, r: int, s: int):
     ec = sum(wv * e for wv, e in zip(wit[tw["diff"]:], tw["nio"])) % O.R
     ec = (ec + (ax * bx - cx) * dinv + s * ea + r * eb - r * s % O.R * tw["Delta"]) % O.R
     return O.g1_compress(O.g1_mul(ea)), O.g2_compress(O.g2_mul(eb)), O.g1_compress(O.g1_mul(ec)), (ax, bx, cx)
+
+
+def sparse_phgr13_setup(be, sq, seed: int):
+    """NewPHGR13TrustedSetup's evaluation key (pinochio.go:93-141) for a sparse circuit: exponents in
+    Python, points by the device's fixed-base kernel.  Returns (api.PHGR13EvalKey, toxic dict)."""
+    from playsnark_b200 import _lib as L
+    smp = O.Sampler(seed)
+    s = smp.fr()
+    av, aw, ay = smp.fr(), smp.fr(), smp.fr()
+    rv, rw = smp.fr(), smp.fr()
+    ry = rv * rw % O.R
+    beta = smp.fr()
+    n, m = sq.nbGates, sq.nbVars
+    lag, zs = lagrange_at(n, s)
+    u, v, w = sparse_eval_all(sq, lag)
+    diff = m - sq.nbIO
+    pw = [1] * (n - 1)
+    for i in range(1, n - 1):
+        pw[i] = pw[i - 1] * s % O.R
+    g1 = lambda exps: be.bases_from_scalars(L.PS_G1, exps).export()
+    g2 = lambda exps: be.bases_from_scalars(L.PS_G2, exps).export()
+    mid = range(diff, m)
+    ek = api.PHGR13EvalKey(
+        vs=g1([rv * u[i] % O.R for i in mid]), ws=g2([rw * v[i] % O.R for i in mid]), ys=g1([ry * w[i] % O.R for i in mid]),
+        vas=g1([rv * u[i] * av % O.R for i in mid]), was=g1([rw * v[i] * aw % O.R for i in mid]),
+        yas=g1([ry * w[i] * ay % O.R for i in mid]), gsi=g1(pw),
+        vbs=g1([rv * u[i] * beta % O.R for i in mid]), wbs=g1([rw * v[i] * beta % O.R for i in mid]),
+        ybs=g1([ry * w[i] * beta % O.R for i in mid]))
+    tw = dict(s=s, av=av, aw=aw, ay=ay, rv=rv, rw=rw, ry=ry, beta=beta, u=u, v=v, w=w, diff=diff, lag=lag, zs=zs)
+    return ek, tw
+
+
+def sparse_phgr13_expected(sq, wit, tw):
+    """the eight proof elements recomputed in the exponent (pinocchio_test.go:31-110 at scale)"""
+    n, diff = sq.nbGates, tw["diff"]
+    lag = tw["lag"]
+    ev = []
+    for rp, col, val in (sq.left, sq.right, sq.out):
+        e = 0
+        for j in range(n):
+            rowv = 0
+            for k in range(rp[j], rp[j + 1]):
+                rowv += val[k] * wit[col[k]]
+            e = (e + rowv % O.R * lag[j]) % O.R
+        ev.append(e)
+    ax, bx, cx = ev
+    hs = (ax * bx - cx) * pow(tw["zs"], -1, O.R) % O.R
+    dot = lambda vec: sum(wit[i] * vec[i] for i in range(diff, sq.nbVars)) % O.R
+    vm, wm, ym = dot(tw["u"]), dot(tw["v"]), dot(tw["w"])
+    rv, rw, ry, beta = tw["rv"], tw["rw"], tw["ry"], tw["beta"]
+    g1 = lambda e: O.g1_compress(O.g1_mul(e % O.R))
+    return {"hs": g1(hs), "vss": g1(rv * vm), "wss": O.g2_compress(O.g2_mul(rw * wm % O.R)), "yss": g1(ry * ym),
+            "vass": g1(rv * vm * tw["av"]), "wass": g1(rw * wm * tw["aw"]), "yass": g1(ry * ym * tw["ay"]),
+            "gz": g1(beta * (rv * vm + rw * wm + ry * ym))}

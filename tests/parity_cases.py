@@ -388,3 +388,16 @@ def readme_flow_through_api(be):
     c5 = api.R1CS(); c5.NewInput("x"); c5.NewOutput("o"); c5.Mul("x", "x", "o"); c5.Mul("x", "x", "o"); c5.Mul("x", "x", "o")
     with pytest.raises(NotImplementedError):
         api.ToQAP(c5)
+
+
+def phgr13_sparse_exponent_check(be, log_n, seed):
+    """PHGR13 prove on a sparse synthetic circuit of 2^log_n gates: all eight proof elements must equal
+    their exponent-level recomputation from the toxic waste (pinocchio_test.go:23-196 at scale)."""
+    n = 1 << log_n
+    sq, wit = H.sparse_circuit(n, seed, n // 2)
+    ek, tw = H.sparse_phgr13_setup(be, sq, seed)
+    pp = api.PHGR13Prove(ek, sq, wit, backend=be, want_h=True)
+    want = H.sparse_phgr13_expected(sq, wit, tw)
+    for f in O.PHGR13_FIELDS:
+        assert getattr(pp, f) == want[f], f
+    assert len(pp.h) == n - 1

@@ -89,3 +89,6 @@ def test_msm_batched_affine_option(be):
         P.readme_groth16(be)
     finally:
         be.set_option("msm_accumulate", 0)
+
+
+def test_sparse_phgr13_exponent_check(be): P.phgr13_sparse_exponent_check(be, 4, seed=11)

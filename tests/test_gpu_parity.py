@@ -111,6 +111,10 @@ def test_sparse_groth16_exponent_check(be, log_n):
     P.groth16_sparse_exponent_check(be, log_n, seed=log_n)
 
 
+@pytest.mark.parametrize("log_n", [6, 12])
+def test_sparse_phgr13_exponent_check(be, log_n): P.phgr13_sparse_exponent_check(be, log_n, seed=log_n)
+
+
 def test_config_c2_dense_2p10(be):
     # BASELINE configs[1]: 2^10 multiplication gates, dense QAP (101 MB), Groth16 + PHGR13
     P.config_c2(be)
