@@ -198,7 +198,7 @@ struct MsmAccumK {
 template <class F>
 struct MsmRunMergeK {
   static constexpr int BLOCK = 128;
-  static constexpr uint32_t RUN_MAX = 8;
+  static constexpr uint32_t RUN_MAX = 32;
   PS_DEV static void run(uint32_t t, uint32_t n_chunks, XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid,
                          const uint8_t* slot_fl) {
     const uint32_t a = 2 * t + 1;  // tail of chunk t
