@@ -54,7 +54,9 @@ const char* ps_version(void);
 int ps_ctx_create(int device, ps_ctx** out);
 /* run on a caller-provided CUDA stream (cudaStream_t passed as void*), e.g. torch's current one */
 int ps_ctx_set_stream(ps_ctx* ctx, void* cuda_stream);
-/* tuning knobs: "msm_accumulate" = 0 (XYZZ accumulator chains, default) | 1 (batched affine tree rounds) */
+/* tuning knobs: "msm_accumulate" = 0 (XYZZ accumulator chains, default) | 1 (batched affine tree rounds);
+ * "msm_team" = 1 (latency-bound tail kernels of the MSM use a team of four lanes per group operation,
+ * default) | 0 (one thread per operation) */
 int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value);
 int ps_ctx_sync(ps_ctx* ctx);
 void ps_ctx_destroy(ps_ctx* ctx);

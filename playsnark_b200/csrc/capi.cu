@@ -424,6 +424,11 @@ int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value) {
     ctx->accum_mode = value;
     return PS_OK;
   }
+  if (!strcmp(name, "msm_team")) {
+    if (value != 0 && value != 1) return PS_ERR_ARG;
+    ctx->msm_team = value;
+    return PS_OK;
+  }
   return PS_ERR_ARG;
 }
 
@@ -555,12 +560,12 @@ int ps_msm_combine(ps_ctx* ctx, int group, const void* d_partials_xyzz, size_t c
   if (group == PS_G1) {
     G1XYZZ* d_res = ctx->arena.take<G1XYZZ>(1);
     if (!d_res) return PS_ERR_ALLOC;
-    PS_LAUNCH(MsmSumK<Fp>, ctx->stream, 1, (uint32_t)count, (const G1XYZZ*)d_partials_xyzz, d_res);
+    PS_TRY((launch_coop<MsmSumK, Fp>(ctx->msm_team != 0, ctx->stream, 1, (uint32_t)count, (const G1XYZZ*)d_partials_xyzz, d_res)));
     PS_TRY(encode_points<Fp>(ctx, d_res, 1, out));
   } else {
     G2XYZZ* d_res = ctx->arena.take<G2XYZZ>(1);
     if (!d_res) return PS_ERR_ALLOC;
-    PS_LAUNCH(MsmSumK<Fp2>, ctx->stream, 1, (uint32_t)count, (const G2XYZZ*)d_partials_xyzz, d_res);
+    PS_TRY((launch_coop<MsmSumK, Fp2>(ctx->msm_team != 0, ctx->stream, 1, (uint32_t)count, (const G2XYZZ*)d_partials_xyzz, d_res)));
     PS_TRY(encode_points<Fp2>(ctx, d_res, 1, out));
   }
   return dev_sync(ctx->stream);

@@ -26,6 +26,8 @@ struct ps_ctx {
   bool evp_valid = false;
   // bucket accumulation: 0 = XYZZ chains (MsmAccumK), 1 = batched affine tree rounds (msm_affine.cuh)
   int accum_mode = 0;
+  // latency-bound tail kernels of the MSM: 1 = a team of four lanes per group operation (team.cuh), 0 = one thread
+  int msm_team = 1;
 };
 
 namespace ps {

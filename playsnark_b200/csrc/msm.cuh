@@ -25,6 +25,7 @@
 #pragma once
 #include "context.cuh"
 #include "curve.cuh"
+#include "team.cuh"
 
 namespace ps {
 
@@ -190,17 +191,51 @@ struct MsmAccumK {
   }
 };
 
+// The tail kernels below are written once against Coop<T>: T = false is one thread per work item (plain
+// serial group law), T = true a team of four lanes per work item (team.cuh).  A kernel launched over
+// `items` work items needs items * Coop<T>::LANES threads; only the team's first lane stores results.
+template <bool T> struct Coop;
+template <> struct Coop<false> {
+  static constexpr uint32_t LANES = 1;
+  PS_DEV explicit Coop(uint32_t&) {}
+  template <class F> PS_DEV void add(XYZZ<F>& acc, const XYZZ<F>& q) const { xyzz_add_c(acc, q); }
+  template <class F> PS_DEV void dbl(XYZZ<F>& p) const { p = xyzz_dbl_c(p); }
+  PS_DEV bool writer() const { return true; }
+  PS_DEV bool idle() const { return false; }
+  PS_DEV void sync() const {}
+};
+template <> struct Coop<true> {
+  static constexpr uint32_t LANES = TEAM;
+  TeamCtx tc;
+  PS_DEV explicit Coop(uint32_t& tid) : tc(TeamCtx::of(tid)) { tid >>= 2; }
+  template <class F> PS_DEV void add(XYZZ<F>& acc, const XYZZ<F>& q) const { xyzz_add_t(acc, q, tc); }
+  template <class F> PS_DEV void dbl(XYZZ<F>& p) const { xyzz_dbl_t(p, tc); }
+  PS_DEV bool writer() const { return tc.tl == 0; }
+  // host emulation runs the lanes one after the other, each with the plain serial formulas: lanes 1..3
+  // would only repeat lane 0's work
+  PS_DEV bool idle() const {
+#ifdef __CUDA_ARCH__
+    return false;
+#else
+    return tc.tl != 0;
+#endif
+  }
+  PS_DEV void sync() const { tc.sync(); }
+};
+
 // Boundary partials of one bucket sit in consecutive chunks: the tail of the chunk where the bucket
 // starts, the heads of the chunks it covers entirely, and the head of the chunk where it ends.  The
-// thread that owns the starting tail walks that run (up to RUN_MAX chunks), adds it up into the
-// bucket and blanks the slots; every run is owned by exactly one thread, so the pass is fully
+// work item that owns the starting tail walks that run (up to RUN_MAX chunks), adds it up into the
+// bucket and blanks the slots; every run is owned by exactly one item, so the pass is fully
 // parallel.  Longer runs (heavily repeated scalars) are left to the log-depth merge below.
-template <class F>
+template <class F, bool T>
 struct MsmRunMergeK {
   static constexpr int BLOCK = 128;
   static constexpr uint32_t RUN_MAX = 32;
   PS_DEV static void run(uint32_t t, uint32_t n_chunks, XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid,
                          const uint8_t* slot_fl) {
+    Coop<T> co(t);
+    if (co.idle()) return;
     const uint32_t a = 2 * t + 1;  // tail of chunk t
     int32_t bid = slot_bid[a];
     if (bid < 0 || slot_fl[a] != 2) return;  // not the start of a run
@@ -212,14 +247,16 @@ struct MsmRunMergeK {
     }
     if (!len) return;
     XYZZ<F> acc = slot_pt[a];
-    for (uint32_t j = 1; j <= len; j++) xyzz_add_c(acc, slot_pt[2 * (t + j)]);
+    for (uint32_t j = 1; j <= len; j++) co.add(acc, slot_pt[2 * (t + j)]);
+    co.sync();  // every lane has read the run before it is blanked
+    if (!co.writer()) return;
     buckets[bid] = acc;
     slot_bid[a] = -1;
     for (uint32_t j = 1; j <= len; j++) slot_bid[2 * (t + j)] = -1;
   }
 };
 
-template <class F>
+template <class F, bool T>
 struct MsmCombineK {
   static constexpr int BLOCK = 128;
   PS_DEV static void flush(int32_t bid, const XYZZ<F>& acc, bool cl, bool cr, int final_pass, uint32_t tid,
@@ -232,7 +269,10 @@ struct MsmCombineK {
   PS_DEV static void run(uint32_t tid, uint32_t n_in, uint32_t f, const XYZZ<F>* in_pt, const int32_t* in_bid,
                          const uint8_t* in_fl, XYZZ<F>* buckets, XYZZ<F>* out_pt, int32_t* out_bid,
                          uint8_t* out_fl, int final_pass) {
-    out_bid[2 * tid] = -1; out_bid[2 * tid + 1] = -1;
+    Coop<T> co(tid);
+    if (co.idle()) return;
+    const bool wr = co.writer();
+    if (wr) { out_bid[2 * tid] = -1; out_bid[2 * tid + 1] = -1; }
     int32_t cur = -1; bool cl = false, cr = false;
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t i = 0; i < f; i++) {
@@ -242,54 +282,58 @@ struct MsmCombineK {
       if (bid < 0) continue;
       uint8_t fl = in_fl[j];
       if (bid != cur) {
-        flush(cur, acc, cl, cr, final_pass, tid, buckets, out_pt, out_bid, out_fl);
+        if (wr) flush(cur, acc, cl, cr, final_pass, tid, buckets, out_pt, out_bid, out_fl);
         cur = bid; acc = in_pt[j]; cl = fl & 1; cr = (fl & 2) != 0;
       } else {
-        xyzz_add_c(acc, in_pt[j]); cr = (fl & 2) != 0;
+        co.add(acc, in_pt[j]); cr = (fl & 2) != 0;
       }
     }
-    flush(cur, acc, cl, cr, final_pass, tid, buckets, out_pt, out_bid, out_fl);
+    if (wr) flush(cur, acc, cl, cr, final_pass, tid, buckets, out_pt, out_bid, out_fl);
   }
 };
 
-// First level of sum_{d=1..D} d * B_d : thread (s, j) covers buckets [j*g, (j+1)*g) of set s and
+// First level of sum_{d=1..D} d * B_d : item (s, j) covers buckets [j*g, (j+1)*g) of set s and
 // emits acc = sum_{i<g} (i+1) * B_{jg+i}, run = sum_i B_{jg+i}.
-template <class F>
+template <class F, bool T>
 struct MsmReduceFirstK {
   static constexpr int BLOCK = 128;
   PS_DEV static void run(uint32_t tid, uint32_t D, uint32_t G, uint32_t g, const XYZZ<F>* buckets, XYZZ<F>* acc_out,
                          XYZZ<F>* run_out) {
+    Coop<T> co(tid);
+    if (co.idle()) return;
     uint32_t s = tid / G, j = tid % G;
     const XYZZ<F>* B = buckets + (size_t)s * D + (size_t)j * g;
     XYZZ<F> rr = XYZZ<F>::inf(), ww = XYZZ<F>::inf();
     for (uint32_t i = g; i-- > 0;) {
-      xyzz_add_c(rr, B[i]);
-      xyzz_add_c(ww, rr);
+      co.add(rr, B[i]);
+      co.add(ww, rr);
     }
-    acc_out[tid] = ww; run_out[tid] = rr;
+    if (co.writer()) { acc_out[tid] = ww; run_out[tid] = rr; }
   }
 };
 
-// Next levels: thread (s, j) merges f consecutive (acc, run) elements, each spanning 2^log_len
+// Next levels: item (s, j) merges f consecutive (acc, run) elements, each spanning 2^log_len
 // buckets:  acc = sum_i acc_i + 2^log_len * sum_i i * run_i ,  run = sum_i run_i.
-template <class F>
+template <class F, bool T>
 struct MsmReduceK {
   static constexpr int BLOCK = 64;
   PS_DEV static void run(uint32_t tid, uint32_t n_in, uint32_t n_out, uint32_t f, int log_len, const XYZZ<F>* acc_in,
                          const XYZZ<F>* run_in, XYZZ<F>* acc_out, XYZZ<F>* run_out) {
+    Coop<T> co(tid);
+    if (co.idle()) return;
     uint32_t s = tid / n_out, j = tid % n_out;
     const XYZZ<F>* A = acc_in + (size_t)s * n_in + (size_t)j * f;
     const XYZZ<F>* R = run_in + (size_t)s * n_in + (size_t)j * f;
     XYZZ<F> asum = XYZZ<F>::inf(), rr = XYZZ<F>::inf(), ww = XYZZ<F>::inf();
     for (uint32_t i = f; i-- > 0;) {
       if ((size_t)j * f + i >= n_in) continue;
-      xyzz_add_c(asum, A[i]);
-      xyzz_add_c(rr, R[i]);
-      if (i > 0) xyzz_add_c(ww, rr);
+      co.add(asum, A[i]);
+      co.add(rr, R[i]);
+      if (i > 0) co.add(ww, rr);
     }
-    for (int d = 0; d < log_len; d++) ww = xyzz_dbl_c(ww);
-    xyzz_add_c(asum, ww);
-    acc_out[tid] = asum; run_out[tid] = rr;
+    for (int d = 0; d < log_len; d++) co.dbl(ww);
+    co.add(asum, ww);
+    if (co.writer()) { acc_out[tid] = asum; run_out[tid] = rr; }
   }
 };
 
@@ -298,78 +342,88 @@ struct MsmReduceK {
 // so the tail is g+1 independent plain sums (pairwise trees, one addition deep per launch) and a
 // short Horner, instead of a chain of weighted merges with growing doubling counts.
 // Y rows per set: row 0 = acc pairs already added, row k+1 = the run_j with bit k of j set; G/2 entries each.
-template <class F>
+template <class F, bool T>
 struct MsmBitGatherK {
   static constexpr int BLOCK = 64;
   PS_DEV static void run(uint32_t tid, uint32_t G, int g, const XYZZ<F>* acc, const XYZZ<F>* run, XYZZ<F>* Y) {
+    Coop<T> co(tid);
+    if (co.idle()) return;
     const uint32_t half = G / 2;
     uint32_t s = tid / ((uint32_t)(g + 1) * half), rem = tid % ((uint32_t)(g + 1) * half);
     uint32_t r = rem / half, i = rem % half;
     XYZZ<F> y;
     if (r == 0) {
       y = acc[(size_t)s * G + 2 * i];
-      xyzz_add_c(y, acc[(size_t)s * G + 2 * i + 1]);
+      co.add(y, acc[(size_t)s * G + 2 * i + 1]);
     } else {
       uint32_t k = r - 1;
       uint32_t j = ((i >> k) << (k + 1)) | (1u << k) | (i & ((1u << k) - 1));
       y = run[(size_t)s * G + j];
     }
-    Y[tid] = y;
+    if (co.writer()) Y[tid] = y;
   }
 };
 // out[row][i] = in[row][2i] + in[row][2i+1];  rows of n_in entries -> rows of n_in/2
-template <class F>
+template <class F, bool T>
 struct MsmPairSumK {
   static constexpr int BLOCK = 64;
   PS_DEV static void run(uint32_t tid, uint32_t n_in, const XYZZ<F>* in, XYZZ<F>* out) {
+    Coop<T> co(tid);
+    if (co.idle()) return;
     uint32_t half = n_in / 2;
     uint32_t row = tid / half, i = tid % half;
     XYZZ<F> y = in[(size_t)row * n_in + 2 * i];
-    xyzz_add_c(y, in[(size_t)row * n_in + 2 * i + 1]);
-    out[tid] = y;
+    co.add(y, in[(size_t)row * n_in + 2 * i + 1]);
+    if (co.writer()) out[tid] = y;
   }
 };
 // per set: R = sum_k 2^k T_k (Horner), out = A + 2^log_len R;  Y holds g+1 single-entry rows per set
-template <class F>
+template <class F, bool T>
 struct MsmBitFinalK {
   static constexpr int BLOCK = 32;
   PS_DEV static void run(uint32_t s, int g, int log_len, const XYZZ<F>* Y, XYZZ<F>* out) {
+    Coop<T> co(s);
+    if (co.idle()) return;
     const XYZZ<F>* row = Y + (size_t)s * (g + 1);
     XYZZ<F> r = XYZZ<F>::inf();
     for (int k = g - 1; k >= 0; k--) {
-      r = xyzz_dbl_c(r);
-      xyzz_add_c(r, row[k + 1]);
+      co.dbl(r);
+      co.add(r, row[k + 1]);
     }
-    for (int d = 0; d < log_len; d++) r = xyzz_dbl_c(r);
-    xyzz_add_c(r, row[0]);
-    out[s] = r;
+    for (int d = 0; d < log_len; d++) co.dbl(r);
+    co.add(r, row[0]);
+    if (co.writer()) out[s] = r;
   }
 };
 
-// Horner over the bucket sets: R = sum_s 2^(shift*s) * set[s]; optionally adds into *out.
-template <class F>
+// Horner over the bucket sets: R = sum_s 2^(shift*s) * set[s]   (one work item)
+template <class F, bool T>
 struct MsmFinalK {
   static constexpr int BLOCK = 32;
   PS_DEV static void run(uint32_t tid, int S, int shift, const XYZZ<F>* sets, XYZZ<F>* out) {
+    Coop<T> co(tid);
+    if (co.idle()) return;
     if (tid != 0) return;
     XYZZ<F> r = XYZZ<F>::inf();
     for (int s = S - 1; s >= 0; s--) {
-      for (int d = 0; d < shift; d++) r = xyzz_dbl_c(r);
-      xyzz_add_c(r, sets[s]);
+      for (int d = 0; d < shift; d++) co.dbl(r);
+      co.add(r, sets[s]);
     }
-    *out = r;
+    if (co.writer()) *out = r;
   }
 };
 
-// sums `count` XYZZ points (multi-GPU partials) into out
-template <class F>
+// sums `count` XYZZ points (multi-GPU partials) into out   (one work item)
+template <class F, bool T>
 struct MsmSumK {
   static constexpr int BLOCK = 32;
   PS_DEV static void run(uint32_t tid, uint32_t count, const XYZZ<F>* in, XYZZ<F>* out) {
+    Coop<T> co(tid);
+    if (co.idle()) return;
     if (tid != 0) return;
     XYZZ<F> r = XYZZ<F>::inf();
-    for (uint32_t i = 0; i < count; i++) xyzz_add_c(r, in[i]);
-    *out = r;
+    for (uint32_t i = 0; i < count; i++) co.add(r, in[i]);
+    if (co.writer()) *out = r;
   }
 };
 
@@ -506,6 +560,17 @@ inline int launch_accum<Fp2>(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L,
   return launch_accum_g2(st, T1, nb, L, tab, ent, off, buckets, slot_pt, slot_bid, slot_fl);
 }
 
+// Launches tail kernel K over `items` work items: a team of four lanes per item when the grid is small
+// enough to be latency-bound (a few waves), one thread per item when it is throughput-bound.
+#ifndef PS_TEAM_MAX_ITEMS
+#define PS_TEAM_MAX_ITEMS 65536
+#endif
+template <template <class, bool> class K, class F, class... Args>
+inline int launch_coop(bool team, ps_stream_t st, size_t items, Args... args) {
+  if (team && items <= PS_TEAM_MAX_ITEMS) return ps_launch<K<F, true>>(st, items * TEAM, args...);
+  return ps_launch<K<F, false>>(st, items, args...);
+}
+
 template <class F>
 int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scalars, int mont, XYZZ<F>* d_out) {
   ps_stream_t st = ctx->stream;
@@ -526,6 +591,7 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   while (L > 8 && max_ent / L < 24576) L >>= 1;
   const size_t T1 = (max_ent + L - 1) / L;
   const uint32_t CF = 64;  // slots merged per combine thread (most are empty after the pair merge)
+  const bool team = ctx->msm_team != 0;
 
   uint32_t* count = ar.take<uint32_t>((size_t)nb + 1);
   uint32_t* off = ar.take<uint32_t>((size_t)nb + 1);
@@ -554,15 +620,15 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
     if (!sp[0] || !sp[1] || !sb[0] || !sb[1] || !sf[0] || !sf[1]) return PS_ERR_ALLOC;
     PS_TRY((launch_accum<F>(st, T1, nb, L, tab, ent, off, buckets, sp[0], sb[0], sf[0])));
     PS_TRY(ctx_event(ctx, 2));
-    PS_LAUNCH(MsmRunMergeK<F>, st, T1, (uint32_t)T1, buckets, sp[0], sb[0], (const uint8_t*)sf[0]);
+    PS_TRY((launch_coop<MsmRunMergeK, F>(team, st, T1, (uint32_t)T1, buckets, sp[0], sb[0], (const uint8_t*)sf[0])));
     {
       size_t n_in = slots_a;
       int cur = 0;
       for (;;) {
         size_t threads = (n_in + CF - 1) / CF;
         int final_pass = threads == 1;
-        PS_LAUNCH(MsmCombineK<F>, st, threads, (uint32_t)n_in, CF, (const XYZZ<F>*)sp[cur], (const int32_t*)sb[cur],
-                  (const uint8_t*)sf[cur], buckets, sp[cur ^ 1], sb[cur ^ 1], sf[cur ^ 1], final_pass);
+        PS_TRY((launch_coop<MsmCombineK, F>(team, st, threads, (uint32_t)n_in, CF, (const XYZZ<F>*)sp[cur], (const int32_t*)sb[cur],
+                                            (const uint8_t*)sf[cur], buckets, sp[cur ^ 1], sb[cur ^ 1], sf[cur ^ 1], final_pass)));
         if (final_pass) break;
         n_in = 2 * threads;
         cur ^= 1;
@@ -582,7 +648,7 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
     XYZZ<F>* accv[2] = {ar.take<XYZZ<F>>(e0), ar.take<XYZZ<F>>(e0 / 2 + g.S)};
     XYZZ<F>* runv[2] = {ar.take<XYZZ<F>>(e0), ar.take<XYZZ<F>>(e0 / 2 + g.S)};
     if (!accv[0] || !accv[1] || !runv[0] || !runv[1]) return PS_ERR_ALLOC;
-    PS_LAUNCH(MsmReduceFirstK<F>, st, e0, g.D, G, gsz, (const XYZZ<F>*)buckets, accv[0], runv[0]);
+    PS_TRY((launch_coop<MsmReduceFirstK, F>(team && e0 <= 32768, st, e0, g.D, G, gsz, (const XYZZ<F>*)buckets, accv[0], runv[0])));
     uint32_t n_in = G;
     int log_len = 0;
     while ((1u << log_len) < gsz) log_len++;
@@ -590,8 +656,8 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
     // a few 4-way weighted merges while plenty of elements remain (work-bound levels)
     while (n_in > 8192) {
       uint32_t f = 4, n_out = n_in / f;
-      PS_LAUNCH(MsmReduceK<F>, st, (size_t)g.S * n_out, n_in, n_out, f, log_len, (const XYZZ<F>*)accv[cur],
-                (const XYZZ<F>*)runv[cur], accv[cur ^ 1], runv[cur ^ 1]);
+      PS_TRY((launch_coop<MsmReduceK, F>(team, st, (size_t)g.S * n_out, n_in, n_out, f, log_len, (const XYZZ<F>*)accv[cur],
+                                         (const XYZZ<F>*)runv[cur], accv[cur ^ 1], runv[cur ^ 1])));
       log_len += 2;
       n_in = n_out;
       cur ^= 1;
@@ -606,16 +672,16 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
       XYZZ<F>* Y[2] = {ar.take<XYZZ<F>>(rows * half), ar.take<XYZZ<F>>(rows * (half / 2 + 1))};
       XYZZ<F>* set_out = ar.take<XYZZ<F>>(g.S);
       if (!Y[0] || !Y[1] || !set_out) return PS_ERR_ALLOC;
-      PS_LAUNCH(MsmBitGatherK<F>, st, rows * half, n_in, gb, (const XYZZ<F>*)accv[cur], (const XYZZ<F>*)runv[cur], Y[0]);
+      PS_TRY((launch_coop<MsmBitGatherK, F>(team, st, rows * half, n_in, gb, (const XYZZ<F>*)accv[cur], (const XYZZ<F>*)runv[cur], Y[0])));
       int yc = 0;
       for (uint32_t w = half; w > 1; w >>= 1) {
-        PS_LAUNCH(MsmPairSumK<F>, st, rows * (w / 2), w, (const XYZZ<F>*)Y[yc], Y[yc ^ 1]);
+        PS_TRY((launch_coop<MsmPairSumK, F>(team, st, rows * (w / 2), w, (const XYZZ<F>*)Y[yc], Y[yc ^ 1])));
         yc ^= 1;
       }
-      PS_LAUNCH(MsmBitFinalK<F>, st, (size_t)g.S, gb, log_len, (const XYZZ<F>*)Y[yc], set_out);
+      PS_TRY((launch_coop<MsmBitFinalK, F>(team, st, (size_t)g.S, gb, log_len, (const XYZZ<F>*)Y[yc], set_out)));
       sets = set_out;
     }
-    PS_LAUNCH(MsmFinalK<F>, st, 1, g.S, g.c * g.T, (const XYZZ<F>*)sets, d_out);
+    PS_TRY((launch_coop<MsmFinalK, F>(team, st, 1, g.S, g.c * g.T, (const XYZZ<F>*)sets, d_out)));
   }
   PS_TRY(ctx_event(ctx, 4));
   ctx->ev_valid = true;
