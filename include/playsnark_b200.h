@@ -161,6 +161,32 @@ int ps_g16_scalars_from_ab(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap
                            const uint8_t* r_be, const uint8_t* s_be, const void* d_a, const void* d_b,
                            void* d_scA, void* d_scC, void* d_scB);
 
+/* Groth16 over 2 * parts GPUs (parts a power of two; sparse QAP), no host round trip between the
+ * steps (errors are OR-ed into a device status word: bit 0 = scalar encoding, bit 1 = remainder, i.e.
+ * the reference's "apocalypse" qap.go:159):
+ *  - ps_qap_interp_part: rank (which, part) evaluates its n/parts gates (all three matrices, gate check
+ *    a(j) b(j) = c(j) on them), and folds the subtree over those gates of polynomial `which` (0 = a,
+ *    1 = b) up to one node: d_out_evals receives its 2n/parts evaluations (Montgomery); with parts = 1
+ *    it receives the n coefficients directly and no finish step is needed.  d_w_nio_out (optional)
+ *    receives the last n_io witness values in standard form (head of C's scalar vector).
+ *  - after an all-gather of the parts, ps_qap_interp_finish runs the top log2(parts) levels on the 2n
+ *    gathered evaluations and emits the n coefficients (Montgomery).
+ *  - ps_g16_scalars_ab (every rank, from the broadcast a and b): scA = [a | r | 1], scB = [b | s | 1],
+ *    scC_tail = [s a + r b | s | r | r s] (standard form; C's scalar vector is [w_nio | h | tail]), so
+ *    that the MSMs A, B and the tail of C run while one rank divides;
+ *  - ps_g16_h_from_ab: h = floor(a b / z), n - 1 standard-form values (to be broadcast into C's vector). */
+int ps_qap_interp_part(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_be, int which, size_t part,
+                       size_t parts, void* d_out_evals, void* d_w_nio_out, void* d_status);
+int ps_qap_interp_finish(ps_ctx* ctx, const ps_qap* qap, size_t parts, const void* d_evals_all, void* d_out_coef);
+int ps_g16_scalars_ab(ps_ctx* ctx, const ps_g16_key* key, const uint8_t* r_be, const uint8_t* s_be, const void* d_a,
+                      const void* d_b, void* d_scA, void* d_scB, void* d_scC_tail);
+int ps_g16_h_from_ab(ps_ctx* ctx, const ps_qap* qap, const void* d_a, const void* d_b, void* d_h_out);
+
+/* Page-locked host memory for call arguments (witness, scalars): host-to-device copies from it run at
+ * link speed and asynchronously; plain pageable buffers are accepted everywhere as well.          */
+int ps_host_alloc(size_t bytes, void** out);
+void ps_host_free(void* p);
+
 /* ---- PHGR13 / Pinocchio (pinochio.go) ------------------------------------------------------------ */
 /* PHGR13EvalKey (pinochio.go:37-62): gsi[n-1]; vs, ys, vas, was, yas, vbs, wbs, ybs [n_mid] in G1
  * (wbs is typed []G2 in the reference but holds G1 points, pinochio.go:114,136); ws [n_mid] G2. */

@@ -43,7 +43,7 @@ SYMBOLS = [
     ("ps_qap_load_dense", _I, [_P, _SZ, _SZ, _SZ, _B, _B, _B, _B, C.POINTER(_P)]),
     ("ps_qap_load_r1cs", _I, [_P, _SZ, _SZ, _SZ] + [_P] * 9 + [C.POINTER(_P)]),
     ("ps_qap_free", None, [_P]),
-    ("ps_quotient", _I, [_P, _P, _B, _P, _P]),
+    ("ps_quotient", _I, [_P, _P, _P, _P, _P]),
     ("ps_g16_key_load", _I, [_P, _SZ, _SZ, _I] + [_B] * 9 + [C.POINTER(_P)]),
     ("ps_g16_key_free", None, [_P]),
     ("ps_g16_prove", _I, [_P, _P, _P, _P, _B, _B, _P, _P, _P, _P]),
@@ -51,8 +51,14 @@ SYMBOLS = [
     ("ps_g16_key_bases", _P, [_P, _I]),
     ("ps_g16_scalars", _I, [_P, _P, _P, _P, _B, _B, _P, _P, _P]),
     ("ps_g16_msm_partials", _I, [_P, _P, _P, _P, _P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _P]),
-    ("ps_qap_aggregate_one", _I, [_P, _P, _B, _I, _P]),
-    ("ps_g16_scalars_from_ab", _I, [_P, _P, _P, _B, _B, _B, _P, _P, _P, _P, _P]),
+    ("ps_qap_aggregate_one", _I, [_P, _P, _P, _I, _P]),
+    ("ps_g16_scalars_from_ab", _I, [_P, _P, _P, _P, _B, _B, _P, _P, _P, _P, _P]),
+    ("ps_qap_interp_part", _I, [_P, _P, _P, _I, _SZ, _SZ, _P, _P, _P]),
+    ("ps_qap_interp_finish", _I, [_P, _P, _SZ, _P, _P]),
+    ("ps_g16_scalars_ab", _I, [_P, _P, _B, _B, _P, _P, _P, _P, _P]),
+    ("ps_g16_h_from_ab", _I, [_P, _P, _P, _P, _P]),
+    ("ps_host_alloc", _I, [_SZ, C.POINTER(_P)]),
+    ("ps_host_free", None, [_P]),
     ("ps_phgr13_key_load", _I, [_P, _SZ, _SZ, _I] + [_B] * 10 + [C.POINTER(_P)]),
     ("ps_phgr13_key_free", None, [_P]),
     ("ps_phgr13_prove", _I, [_P, _P, _P, _P, _P, _P]),

@@ -25,9 +25,39 @@ Vector = List[int]
 Poly = List[int]
 
 
-def _fr_bytes(vals) -> bytes:
+class HostBuffer:
+    """Wire-format values in page-locked host memory (ps_host_alloc): what a caller who proves repeatedly
+    marshals its witness into, so that the host-to-device copy runs at link speed.  Accepted wherever a
+    Vector of Fr values is; len() is the number of 32-byte values."""
+
+    def __init__(self, backend: "Backend", data):
+        raw = _fr_bytes(data)
+        self.lib, self.nbytes = backend.lib, len(raw)
+        p = C.c_void_p()
+        backend._check(self.lib.ps_host_alloc(max(1, self.nbytes), C.byref(p)))
+        self.ptr = p
+        C.memmove(p, raw, self.nbytes)
+
+    def __len__(self):
+        return self.nbytes // 32
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.lib.ps_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _fr_bytes(vals):
     """Fr values (ints, reduced mod r like Value.ToFieldElement) -> 32-byte big-endian rows; byte strings
-    that are already in wire format pass through."""
+    that are already in wire format pass through, a HostBuffer passes as its pointer."""
+    if isinstance(vals, HostBuffer):
+        return vals.ptr
     if isinstance(vals, (bytes, bytearray, memoryview)):
         return bytes(vals)
     return b"".join((int(v) % R).to_bytes(32, "big") for v in vals)

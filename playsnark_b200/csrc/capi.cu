@@ -282,7 +282,7 @@ int run_quotient_sparse(ps_ctx* ctx, const ps_qap* q, const uint8_t* witness_be,
   o->flag = ctx->arena.take<uint32_t>(1);
   if (!ev || !coef || !o->h || !o->flag) return PS_ERR_ALLOC;
   PS_TRY(dev_memset(o->flag, 0, 4, st));
-  PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
+  PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, 0u, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
             (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
             (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, (const Fr*)o->w, ev);
   PS_LAUNCH(GateCheckK, st, n, n, (const Fr*)ev, o->flag);
@@ -903,7 +903,7 @@ int ps_qap_aggregate_one(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_
   PS_TRY(stage_scalars(ctx, witness_be, qap->m, 1, &d_w, &d_err));
   Fr* ev = ctx->arena.take<Fr>((size_t)3 * n);
   if (!ev) return PS_ERR_ALLOC;
-  PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
+  PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, 0u, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
             (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
             (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, (const Fr*)d_w, ev);
   PS_TRY(interpolate_ap(ctx, sq, n, qap->log_np, 1, ev + (size_t)which * n, (Fr*)d_out_coef));
@@ -930,7 +930,7 @@ int ps_g16_scalars_from_ab(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap
   uint32_t* flag = ctx->arena.take<uint32_t>(1);
   if (!ev || !h || !flag) return PS_ERR_ALLOC;
   PS_TRY(dev_memset(flag, 0, 4, st));
-  PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
+  PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, 0u, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
             (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
             (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, (const Fr*)w, ev);
   PS_LAUNCH(GateCheckK, st, n, n, (const Fr*)ev, flag);
@@ -963,6 +963,139 @@ int ps_g16_scalars_from_ab(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap
   PS_LAUNCH(FrFromMontK, st, nio + (n - 1) + n + 3, scC);
   PS_TRY(check_err_flag(ctx, d_err, PS_ERR_ENCODING));
   return check_err_flag(ctx, flag, PS_ERR_REMAINDER);
+}
+
+// ---- Groth16 over several GPUs: quotient split by subtree, MSMs overlapped with the division ---------------
+namespace {
+// out[i] = in[i] in standard form
+struct FrStdCopyK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t i, const Fr* in, Fr* out) { out[i] = in[i].from_mont(); }
+};
+// *status |= (enc ? 1 : 0) | (rem ? 2 : 0)      (device-side status word: no host round trip per call)
+struct StatusMergeK {
+  static constexpr int BLOCK = 32;
+  PS_DEV static void run(uint32_t i, const uint32_t* enc, const uint32_t* rem, uint32_t* status) {
+    if (i) return;
+    uint32_t v = ((enc && *enc) ? 1u : 0u) | ((rem && *rem) ? 2u : 0u);
+    if (v) ps_atomic_or(status, v);
+  }
+};
+int parse_fr(const uint8_t* src, Fr* out) {
+  Fr x;
+  for (int j = 0; j < 8; j++) {
+    const uint8_t* p = src + 4 * (7 - j);
+    x.v[j] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+  }
+  if (!limbs_lt_mod<FrParams>(x.v)) return PS_ERR_ENCODING;
+  *out = x.to_mont();
+  return PS_OK;
+}
+int log2_exact(size_t v) {
+  int l = 0;
+  while (((size_t)1 << l) < v) l++;
+  return ((size_t)1 << l) == v ? l : -1;
+}
+}  // namespace
+
+int ps_host_alloc(size_t bytes, void** out) {
+  if (!out) return PS_ERR_ARG;
+#if PS_GPU
+  PS_CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+#else
+  *out = malloc(bytes ? bytes : 1);
+  if (!*out) return PS_ERR_ALLOC;
+#endif
+  return PS_OK;
+}
+
+void ps_host_free(void* p) {
+  if (!p) return;
+#if PS_GPU
+  cudaFreeHost(p);
+#else
+  free(p);
+#endif
+}
+
+int ps_qap_interp_part(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_be, int which, size_t part, size_t parts,
+                       void* d_out_evals, void* d_w_nio_out, void* d_status) {
+  if (!ctx || !qap || !witness_be || !d_out_evals || !d_status || which < 0 || which > 1) return PS_ERR_ARG;
+  if (qap->dense) return PS_ERR_UNSUPPORTED;
+  const int lp = log2_exact(parts);
+  if (lp < 0 || parts > qap->n / 2 || part >= parts) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  const SparseQap* sq = (const SparseQap*)qap->sparse;
+  const uint32_t n = (uint32_t)qap->n, ns = (uint32_t)(qap->n / parts), lo = (uint32_t)part * ns;
+  ps_stream_t st = ctx->stream;
+  uint32_t *d_w = nullptr, *d_err = nullptr;
+  PS_TRY(stage_scalars(ctx, witness_be, qap->m, 1, &d_w, &d_err));
+  if (d_w_nio_out) PS_LAUNCH(FrStdCopyK, st, qap->n_io, (const Fr*)d_w + (qap->m - qap->n_io), (Fr*)d_w_nio_out);
+  Fr* ev = ctx->arena.take<Fr>((size_t)3 * ns);
+  Fr* E0 = ctx->arena.take<Fr>((size_t)2 * ns);
+  uint32_t* flag = ctx->arena.take<uint32_t>(1);
+  if (!ev || !E0 || !flag) return PS_ERR_ALLOC;
+  PS_TRY(dev_memset(flag, 0, 4, st));
+  PS_LAUNCH(SpmvK, st, (size_t)3 * ns, ns, lo, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
+            (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
+            (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, (const Fr*)d_w, ev);
+  PS_LAUNCH(GateCheckK, st, ns, ns, (const Fr*)ev, flag);   // this rank's gates; every gate is checked by some rank
+  PS_LAUNCH(InterpLeafK, st, ns, ns, (const Fr*)(ev + (size_t)which * ns), (const Fr*)(sq->inv_zprime + lo), E0);
+  // parts == 1: the whole tree, d_out_evals receives the n coefficients
+  PS_TRY(interpolate_levels(ctx, sq, n, qap->log_np, 1, lo, ns, 0, qap->log_np - lp, E0, lp ? (Fr*)d_out_evals : (Fr*)nullptr,
+                            lp ? (Fr*)nullptr : (Fr*)d_out_evals));
+  PS_LAUNCH(StatusMergeK, st, 1, (const uint32_t*)d_err, (const uint32_t*)flag, (uint32_t*)d_status);
+  return PS_OK;
+}
+
+int ps_qap_interp_finish(ps_ctx* ctx, const ps_qap* qap, size_t parts, const void* d_evals_all, void* d_out_coef) {
+  if (!ctx || !qap || !d_evals_all || !d_out_coef) return PS_ERR_ARG;
+  if (qap->dense) return PS_ERR_UNSUPPORTED;
+  const int lp = log2_exact(parts);
+  if (lp < 1 || parts > qap->n / 2) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  const SparseQap* sq = (const SparseQap*)qap->sparse;
+  const uint32_t n = (uint32_t)qap->n;
+  Fr* E0 = ctx->arena.take<Fr>((size_t)2 * n);
+  if (!E0) return PS_ERR_ALLOC;
+  PS_TRY(dev_d2d(E0, d_evals_all, (size_t)2 * n * sizeof(Fr), ctx->stream));
+  return interpolate_levels(ctx, sq, n, qap->log_np, 1, 0, n, qap->log_np - lp, qap->log_np, E0, (Fr*)nullptr, (Fr*)d_out_coef);
+}
+
+int ps_g16_h_from_ab(ps_ctx* ctx, const ps_qap* qap, const void* d_a, const void* d_b, void* d_h_out) {
+  if (!ctx || !qap || !d_a || !d_b || !d_h_out) return PS_ERR_ARG;
+  if (qap->dense) return PS_ERR_UNSUPPORTED;
+  PS_TRY(begin_call(ctx));
+  const SparseQap* sq = (const SparseQap*)qap->sparse;
+  const uint32_t n = (uint32_t)qap->n;
+  Fr* h = ctx->arena.take<Fr>(n);
+  if (!h) return PS_ERR_ALLOC;
+  PS_TRY(quotient_series(ctx, sq, n, qap->log_np, (const Fr*)d_a, (const Fr*)d_b, h, (Fr*)nullptr));
+  PS_LAUNCH(FrStdCopyK, ctx->stream, (size_t)n - 1, (const Fr*)h, (Fr*)d_h_out);
+  return PS_OK;
+}
+
+int ps_g16_scalars_ab(ps_ctx* ctx, const ps_g16_key* key, const uint8_t* r_be, const uint8_t* s_be, const void* d_a,
+                      const void* d_b, void* d_scA, void* d_scB, void* d_scC_tail) {
+  if (!ctx || !key || !r_be || !s_be || !d_a || !d_b || !d_scA || !d_scB || !d_scC_tail) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  ps_stream_t st = ctx->stream;
+  const size_t n = key->n;
+  Fr r, s;
+  PS_TRY(parse_fr(r_be, &r));
+  PS_TRY(parse_fr(s_be, &s));
+  const Fr rs = r * s;
+  const Fr* a = (const Fr*)d_a;
+  const Fr* b = (const Fr*)d_b;
+  Fr* scA = (Fr*)d_scA; Fr* scB = (Fr*)d_scB; Fr* tail = (Fr*)d_scC_tail;
+  PS_LAUNCH(FrStdCopyK, st, n, a, scA);
+  PS_LAUNCH(FrSet3K, st, 2, r.from_mont(), Fr::one().from_mont(), Fr::zero(), 2, scA + n);
+  PS_LAUNCH(FrStdCopyK, st, n, b, scB);
+  PS_LAUNCH(FrSet3K, st, 2, s.from_mont(), Fr::one().from_mont(), Fr::zero(), 2, scB + n);
+  PS_LAUNCH(FrAxpbyK, st, n, s, a, r, b, tail);
+  PS_LAUNCH(FrFromMontK, st, n, tail);
+  PS_LAUNCH(FrSet3K, st, 3, s.from_mont(), r.from_mont(), rs.from_mont(), 3, tail + n);
+  return PS_OK;
 }
 
 int ps_g16_scalars(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const uint8_t* witness_be, const uint8_t* r_be,

@@ -42,13 +42,13 @@ struct SparseQap {
   }
 };
 
-// ev[mat][j] = sum_k val[k] * w[col[k]] over row j          (thread = mat * n + j)
+// ev[mat][j] = sum_k val[k] * w[col[k]] over row row0 + j, j < n          (thread = mat * n + j)
 struct SpmvK {
   static constexpr int BLOCK = 128;
-  PS_DEV static void run(uint32_t tid, uint32_t n, const uint32_t* rp0, const uint32_t* c0, const Fr* v0, const uint32_t* rp1,
+  PS_DEV static void run(uint32_t tid, uint32_t n, uint32_t row0, const uint32_t* rp0, const uint32_t* c0, const Fr* v0, const uint32_t* rp1,
                          const uint32_t* c1, const Fr* v1, const uint32_t* rp2, const uint32_t* c2, const Fr* v2, const Fr* w,
                          Fr* ev) {
-    uint32_t m = tid / n, j = tid % n;
+    uint32_t m = tid / n, j = row0 + tid % n;
     const uint32_t* rp = m == 0 ? rp0 : (m == 1 ? rp1 : rp2);
     const uint32_t* col = m == 0 ? c0 : (m == 1 ? c1 : c2);
     const Fr* val = m == 0 ? v0 : (m == 1 ? v1 : v2);
@@ -195,34 +195,49 @@ struct FrScaleK {
   PS_DEV static void run(uint32_t i, Fr scale, Fr* a) { a[i] = a[i] * scale; }
 };
 
-// ev: P polynomials' evaluations on {1..n} (P*n) -> coef: their coefficients (P*n).
-inline int interpolate_ap(ps_ctx* ctx, const SparseQap* sq, uint32_t n, int k, int P, const Fr* ev, Fr* coef) {
+// Levels [l0, l1) of the interpolation tree over the leaves [lo, lo + ns) of the domain {1..n} (ns a power
+// of two that divides lo; the whole tree is lo = 0, ns = n, l0 = 0, l1 = k).  E0 holds the evaluations
+// entering level l0: P polynomials x ns/s nodes x 2s values (s = 2^l0); it is used as scratch.
+// l1 == k (only with ns == n): `coef` receives the P * n coefficients.  l1 < k: `Eout` receives the
+// evaluations entering level l1 (P * 2 ns values), e.g. to be gathered from several GPUs.
+inline int interpolate_levels(ps_ctx* ctx, const SparseQap* sq, uint32_t n, int k, int P, uint32_t lo, uint32_t ns, int l0,
+                              int l1, Fr* E0, Fr* Eout, Fr* coef) {
   ps_stream_t st = ctx->stream;
+  if (l0 < 0 || l1 > k || l0 > l1 || (l1 == k && (ns != n || !coef)) || (l1 < k && !Eout)) return PS_ERR_ARG;
   const NttTables* tabs = nullptr;
   PS_TRY(ctx_ntt_tables(ctx, k + 1, &tabs));
   const uint32_t n_tw = 2 * n;
-  Fr* E[2] = {ctx->arena.take<Fr>((size_t)P * 2 * n), ctx->arena.take<Fr>((size_t)P * 2 * n)};
-  Fr* Cbuf = ctx->arena.take<Fr>((size_t)P * n);
-  if (!E[0] || !E[1] || !Cbuf) return PS_ERR_ALLOC;
-  PS_LAUNCH(InterpLeafK, st, (size_t)P * n, n, ev, (const Fr*)sq->inv_zprime, E[0]);
+  Fr* E[2] = {E0, ctx->arena.take<Fr>((size_t)P * 2 * ns)};
+  Fr* Cbuf = ctx->arena.take<Fr>((size_t)P * ns);
+  if (!E[1] || !Cbuf) return PS_ERR_ALLOC;
   int cur = 0;
-  for (int l = 0; l < k; l++) {
+  for (int l = l0; l < l1; l++) {
     const uint32_t two_s = 2u << l;
     const bool last = (l + 1 == k);
     Fr inv2s = fr_inv(fr_host_from_u64(two_s));
     Fr* dst = last ? coef : Cbuf;
-    PS_LAUNCH(InterpCombine2K, st, (size_t)P * n, n, two_s, (const Fr*)E[cur], (const Fr*)sq->ztree[l], last ? (Fr*)nullptr : E[cur ^ 1], dst);
-    PS_TRY(ntt_inverse_blocks_unscaled(st, dst, (size_t)P * n, l + 1, tabs->tw_inv, n_tw));
+    const Fr* Zhat = sq->ztree[l] + 2 * (size_t)lo;  // node j of level l starts at j * 2s = 2 * (its first leaf)
+    PS_LAUNCH(InterpCombine2K, st, (size_t)P * ns, ns, two_s, (const Fr*)E[cur], Zhat, last ? (Fr*)nullptr : E[cur ^ 1], dst);
+    PS_TRY(ntt_inverse_blocks_unscaled(st, dst, (size_t)P * ns, l + 1, tabs->tw_inv, n_tw));
     if (last) {
-      PS_LAUNCH(FrScaleK, st, (size_t)P * n, inv2s, dst);
+      PS_LAUNCH(FrScaleK, st, (size_t)P * ns, inv2s, dst);
     } else {
-      PS_LAUNCH(InterpTwistK, st, (size_t)P * n, two_s, n_tw / (2 * two_s), inv2s, (const Fr*)tabs->tw, Cbuf);
-      PS_TRY(ntt_forward_blocks(st, Cbuf, (size_t)P * n, l + 1, tabs->tw, n_tw));
-      PS_LAUNCH(InterpOddK, st, (size_t)P * n, n, two_s, (const Fr*)Cbuf, E[cur ^ 1]);
+      PS_LAUNCH(InterpTwistK, st, (size_t)P * ns, two_s, n_tw / (2 * two_s), inv2s, (const Fr*)tabs->tw, Cbuf);
+      PS_TRY(ntt_forward_blocks(st, Cbuf, (size_t)P * ns, l + 1, tabs->tw, n_tw));
+      PS_LAUNCH(InterpOddK, st, (size_t)P * ns, ns, two_s, (const Fr*)Cbuf, E[cur ^ 1]);
       cur ^= 1;
     }
   }
+  if (l1 < k && E[cur] != Eout) PS_TRY(dev_d2d(Eout, E[cur], (size_t)P * 2 * ns * sizeof(Fr), st));
   return PS_OK;
+}
+
+// ev: P polynomials' evaluations on {1..n} (P*n) -> coef: their coefficients (P*n).
+inline int interpolate_ap(ps_ctx* ctx, const SparseQap* sq, uint32_t n, int k, int P, const Fr* ev, Fr* coef) {
+  Fr* E0 = ctx->arena.take<Fr>((size_t)P * 2 * n);
+  if (!E0) return PS_ERR_ALLOC;
+  PS_LAUNCH(InterpLeafK, ctx->stream, (size_t)P * n, n, ev, (const Fr*)sq->inv_zprime, E0);
+  return interpolate_levels(ctx, sq, n, k, P, 0, n, 0, k, E0, (Fr*)nullptr, coef);
 }
 
 // ---- division by z through the power-series inverse of rev(z) -----------------------------------------

@@ -61,51 +61,127 @@ class _KeyBases:
         self.handle, self.group = handle, group
 
 
-def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device="cpu", split_quotient: bool = True):
+def weighted_ranges(count: int, weights):
+    """contiguous slices of [0, count) with sizes proportional to `weights` (one per rank)"""
+    total = float(sum(weights))
+    cuts, acc = [0], 0.0
+    for w in weights:
+        acc += w
+        cuts.append(min(count, int(round(count * acc / total))))
+    cuts[-1] = count
+    return [(cuts[i], max(cuts[i], cuts[i + 1])) for i in range(len(weights))]
+
+
+def _raise_status(st: int):
+    if st & 2:
+        raise ArithmeticError("apocalypse")
+    if st & 1:
+        raise L.PlaysnarkError(L.PS_ERR_ENCODING, "bad scalar or point encoding")
+
+
+def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_share: float):
+    """world = 2 * parts ranks.  Ranks [0, parts) fold polynomial a, ranks [parts, 2 parts) polynomial b:
+    each one the subtree over its n/parts gates (ps_qap_interp_part); an all-gather hands the subtree
+    roots to the two leaders, which run the top levels (ps_qap_interp_finish) and broadcast a and b.
+    Every rank then derives the scalars of A, B and of C's tail locally and starts those MSM shards
+    while rank 0 divides (ps_g16_h_from_ab); h is broadcast into C's scalar vector and the remaining
+    shard [NioLP | XiT] follows.  One all-gather of the partial points (and of the device status words)
+    ends the proof; no host synchronisation in between."""
+    import torch
+    from .api import _fr_bytes
+    lib = be.lib
+    world, rank = dist.get_world_size(), dist.get_rank()
+    parts = world // 2
+    g, part = divmod(rank, parts)
+    kh, qh = tr._resident(be), q._resident(be)
+    n, nio = q.nbGates, q.nbIO
+    nA, nC, nB = (int(lib.ps_g16_scalar_count(kh, w)) for w in (0, 1, 2))
+    head = nio + n - 1                                   # [w_nio | h] ; tail = [s a + r b | s | r | r s]
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    new = lambda rows: torch.zeros((rows, 8), dtype=torch.int32, device=device)
+    bufA, bufC, bufB = new(nA), new(nC), new(nB)
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    wb, rb, sb = _fr_bytes(witness), _fr_bytes([r]), _fr_bytes([s])
+    e_rows = 2 * n // parts if parts > 1 else n
+    e_part = new(e_rows)
+    be._check(lib.ps_qap_interp_part(be.ctx, qh, wb, g, part, parts, ptr(e_part), ptr(bufC) if nio else None, ptr(status)))
+    if parts > 1:
+        e_all = [new(e_rows) for _ in range(world)]
+        dist.all_gather(e_all, e_part)
+        coef = [new(n), new(n)]
+        if part == 0:
+            mine = torch.cat(e_all[g * parts:(g + 1) * parts])
+            be._check(lib.ps_qap_interp_finish(be.ctx, qh, parts, ptr(mine), ptr(coef[g])))
+    else:
+        coef = [e_part if g == 0 else new(n), e_part if g == 1 else new(n)]
+    dist.broadcast(coef[0], src=0)
+    dist.broadcast(coef[1], src=parts)
+    be._check(lib.ps_g16_scalars_ab(be.ctx, kh, rb, sb, ptr(coef[0]), ptr(coef[1]), ptr(bufA), ptr(bufB), ptr(bufC[head:])))
+    hview = bufC[nio:head]
+    if rank == 0:
+        be._check(lib.ps_g16_h_from_ab(be.ctx, qh, ptr(coef[0]), ptr(coef[1]), ptr(hview)))
+    weights = [rank0_share] + [1.0] * (world - 1)       # rank 0 also divides: it takes a smaller MSM share
+    rA = weighted_ranges(nA, weights)[rank]
+    rB = weighted_ranges(nB, weights)[rank]
+    rT = weighted_ranges(nC - head, weights)[rank]
+    rH = weighted_ranges(head, weights)[rank]
+
+    def partials(spans):
+        # spans: (lo, hi) inside the base sets of A, C, B; scalar pointers offset to the span
+        out = torch.zeros(768, dtype=torch.uint8, device=device)
+        first = (C.c_size_t * 3)(*[lo for lo, _ in spans])
+        cnt = (C.c_size_t * 3)(*[hi - lo for lo, hi in spans])
+        views = [buf[lo:hi] if hi > lo else buf for buf, (lo, hi) in zip((bufA, bufC, bufB), spans)]
+        be._check(lib.ps_g16_msm_partials(be.ctx, kh, ptr(views[0]), ptr(views[1]), ptr(views[2]), first, cnt, ptr(out)))
+        return out
+
+    early = partials([rA, (head + rT[0], head + rT[1]), rB])
+    dist.broadcast(hview, src=0)
+    late = partials([(0, 0), rH, (0, 0)])
+    rec = torch.cat([early, late[192:384], status.view(torch.uint8)])   # A | C tail | B | C head | status
+    recs = [torch.zeros_like(rec) for _ in range(world)]
+    dist.all_gather(recs, rec)
+    allr = torch.stack(recs)
+    _raise_status(int(allr[:, 960:964].contiguous().view(torch.int32).max().item()) if world else 0)
+    if rank != 0:
+        return None
+    res = []
+    for grp, cols in ((L.PS_G1, [(0, 192)]), (L.PS_G2, [(384, 768)]), (L.PS_G1, [(192, 384), (768, 960)])):
+        allp = torch.cat([allr[:, lo:hi].reshape(-1) for lo, hi in cols]).contiguous()
+        out = C.create_string_buffer(48 if grp == L.PS_G1 else 96)
+        be._check(lib.ps_msm_combine(be.ctx, grp, C.c_void_p(allp.data_ptr()), world * len(cols), out))
+        res.append(out.raw)
+    return res[0], res[1], res[2]   # A, B, C
+
+
+def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device="cpu", split_quotient: bool = True,
+                          rank0_share: float = 0.5):
     """Groth16Prove (groth16.go:122-211) over the ranks of `dist`.  Every rank holds the proving key.
-    Quotient: rank 0 (and, with split_quotient and a sparse QAP, rank 1 for the second aggregate
-    polynomial) -- `q` and `witness` are only read there.  The three scalar vectors are broadcast, every
-    rank sums its index range of each MSM (G2 on its second stream), the 768-byte partials are
+    With a sparse QAP and an even, power-of-two-halved world the whole proof is pipelined across the
+    ranks (_groth16_pipelined: every rank holds the QAP and reads `witness`).  Otherwise the quotient
+    runs on rank 0 (`q` and `witness` are only read there), the three scalar vectors are broadcast,
+    every rank sums its index range of each MSM (G2 on its second stream), the 768-byte partials are
     all-gathered and rank 0 adds and encodes.  Returns (A, B, C) compressed on rank 0, None elsewhere."""
     import torch
     from .api import _fr_bytes
     lib = be.lib
     world = dist.get_world_size() if dist is not None else 1
     rank = dist.get_rank() if dist is not None else 0
+    parts = world // 2
+    if (split_quotient and world >= 2 and world % 2 == 0 and parts & (parts - 1) == 0 and type(q).__name__ == "SparseQAP"
+            and parts <= q.nbGates // 2):
+        return _groth16_pipelined(be, tr, q, witness, r, s, dist, device, rank0_share)
     kh = tr._resident(be)
     counts = [int(lib.ps_g16_scalar_count(kh, w)) for w in (0, 1, 2)]
     groups = [L.PS_G1, L.PS_G1, L.PS_G2]
     bufs = [torch.zeros((c, 8), dtype=torch.int32, device=device) for c in counts]
     status = torch.zeros(1, dtype=torch.int32, device=device)
-    split = bool(split_quotient and world > 1 and not getattr(q, "left", None) is None and type(q).__name__ == "SparseQAP")
     ptr = lambda t: C.c_void_p(t.data_ptr())
-    if split:
-        n = q.nbGates
-        wb = _fr_bytes(witness) if rank in (0, 1) else None
-        coef_b = torch.zeros((n, 8), dtype=torch.int32, device=device)
-        if rank == 1:
-            status[0] = lib.ps_qap_aggregate_one(be.ctx, q._resident(be), wb, 1, ptr(coef_b))
-            be.sync()
-        if rank == 0:
-            coef_a = torch.zeros((n, 8), dtype=torch.int32, device=device)
-            st0 = lib.ps_qap_aggregate_one(be.ctx, q._resident(be), wb, 0, ptr(coef_a))
-            be.sync()
-        dist.broadcast(coef_b, src=1)
-        if rank == 0:
-            st = st0 or lib.ps_g16_scalars_from_ab(be.ctx, kh, q._resident(be), wb, _fr_bytes([r]), _fr_bytes([s]), ptr(coef_a),
-                                                   ptr(coef_b), ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]))
-            status[0] = st
-        st1 = status.clone()
-        dist.broadcast(st1, src=1)
+    if rank == 0:
+        status[0] = lib.ps_g16_scalars(be.ctx, kh, q._resident(be), _fr_bytes(witness), _fr_bytes([r]), _fr_bytes([s]),
+                                       ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]))
+    if world > 1:
         dist.broadcast(status, src=0)
-        if int(status[0]) == 0 and int(st1[0]) != 0:
-            status = st1
-    else:
-        if rank == 0:
-            status[0] = lib.ps_g16_scalars(be.ctx, kh, q._resident(be), _fr_bytes(witness), _fr_bytes([r]), _fr_bytes([s]),
-                                           ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]))
-        if world > 1:
-            dist.broadcast(status, src=0)
     st = int(status[0])
     if st == L.PS_ERR_REMAINDER:
         raise ArithmeticError("apocalypse")
@@ -122,16 +198,16 @@ def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device=
     be._check(lib.ps_g16_msm_partials(be.ctx, kh, ptr(views[0]) if cnt[0] else ptr(bufs[0]), ptr(views[1]) if cnt[1] else ptr(bufs[1]),
                                       ptr(views[2]) if cnt[2] else ptr(bufs[2]), first, cnt, ptr(part)))
     if world > 1:
-        parts = [torch.zeros_like(part) for _ in range(world)]
-        dist.all_gather(parts, part)
+        parts_l = [torch.zeros_like(part) for _ in range(world)]
+        dist.all_gather(parts_l, part)
     else:
         be.sync()
-        parts = [part]
+        parts_l = [part]
     if rank != 0:
         return None
     res, off = [], 0
     for w in range(3):
-        allp = torch.cat([p[off:off + sizes[w]] for p in parts]).contiguous()
+        allp = torch.cat([p[off:off + sizes[w]] for p in parts_l]).contiguous()
         out = C.create_string_buffer(48 if groups[w] == L.PS_G1 else 96)
         be._check(lib.ps_msm_combine(be.ctx, groups[w], C.c_void_p(allp.data_ptr()), world, out))
         res.append(out.raw)

@@ -194,6 +194,12 @@ def readme_groth16(be):
     assert (pr.A.hex(), pr.B.hex(), pr.C.hex()) == (k["A"], k["B"], k["C"])
     assert pr.h == I(g["h"])
     assert pr.tp.R == int(k["r"], 16) and pr.tp.S == int(k["s"], 16)
+    # the same with the witness marshalled into page-locked host memory (ps_host_alloc)
+    hb = api.HostBuffer(be, g["witness"])
+    pr1 = api.Groth16Prove(tr, q, hb, int(k["r"], 16), int(k["s"], 16), backend=be)
+    assert (pr1.A.hex(), pr1.B.hex(), pr1.C.hex()) == (k["A"], k["B"], k["C"])
+    assert api.Quotient(q, hb, backend=be) == I(g["h"])
+    hb.close()
     # fresh randomness path (groth16.go:148,158): proof must still verify
     c = O.create_r1cs(); w = O.create_witness(c); oq = O.to_qap(c)
     otr = O.groth16_setup(oq, O.Sampler(0))

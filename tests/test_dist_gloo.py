@@ -73,12 +73,24 @@ dist.destroy_process_group()
 '''
 
 
-def test_sharded_msm_two_ranks(tmp_path):
+def _run(tmp_path, nproc, port):
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT})
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
-                         capture_output=True, text=True, timeout=900, env=env)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc,
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         capture_output=True, text=True, timeout=1200, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "SHARDED_OK" in res.stdout
+
+
+def test_sharded_msm_two_ranks(tmp_path):
+    """2 ranks: sharded MSM; Groth16 with a dense QAP (quotient on rank 0) and with a sparse QAP
+    (pipelined flow, one aggregate polynomial per rank)."""
+    _run(tmp_path, 2, 29533)
+
+
+def test_sharded_groth16_four_ranks(tmp_path):
+    """4 ranks: the interpolation of each aggregate polynomial is split over two subtrees
+    (ps_qap_interp_part / ps_qap_interp_finish), uneven MSM shares, h broadcast into C's scalars."""
+    _run(tmp_path, 4, 29534)

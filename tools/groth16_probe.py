@@ -26,6 +26,11 @@ for i in range(reps):
     t0 = time.time(); pr = ps.Groth16Prove(tr, sq, wb, r, s, backend=be); dt = time.time() - t0
     print("prove %d: %.2f ms wall (witness pre-marshalled), %d launches, device phases %s" % (
         i, dt * 1e3, be.launch_count() - l0, {k: round(v, 2) for k, v in be.prove_timing().items()}), flush=True)
+hb = ps.HostBuffer(be, wb)
+for i in range(reps):
+    t0 = time.time(); pr_p = ps.Groth16Prove(tr, sq, hb, r, s, backend=be); dt = time.time() - t0
+    print("prove (pinned witness) %d: %.2f ms wall, device phases %s" % (i, dt * 1e3, {k: round(v, 2) for k, v in be.prove_timing().items()}), flush=True)
+assert (pr_p.A, pr_p.B, pr_p.C) == (pr.A, pr.B, pr.C)
 print("last MSM inside prove (B, G2):", {k: round(v, 2) for k, v in be.msm_timing().items()})
 import random as _r
 from playsnark_b200 import _lib as _L
