@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--g2-log-n", type=int, default=20, help="also time a G2 MSM of 2^k points per GPU (0 = skip)")
+    ap.add_argument("--no-small-configs", action="store_true", help="skip the 2^10 dense / 2^16 sparse prove latencies")
     ap.add_argument("--groth16-log-n", type=int, default=20,
                     help="also time a full Groth16 prove on a sparse synthetic circuit of 2^k constraints (0 = skip)")
     args = ap.parse_args()
@@ -365,6 +366,12 @@ def main():
             line["groth16"] = groth16_section(be, args, dist if world > 1 else None, dev)
         except Exception as e:  # the headline metric must still be reported
             line["groth16"] = {"error": repr(e)}
+    if world == 1 and not args.no_small_configs:
+        try:
+            cb = line.get("cpu_baseline") or {}
+            line["small_configs"] = small_configs_section(be, cb.get("value"))
+        except Exception as e:
+            line["small_configs"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -392,7 +399,7 @@ def groth16_section(be, args, dist=None, dev="cuda"):
     wb = b"".join(v.to_bytes(32, "big") for v in wit)
     t0 = time.perf_counter()
     sq._resident(be)         # every rank folds a subtree of one aggregate polynomial
-    tr._resident(be); be.sync()
+    D.load_key_sharded(be, tr, world); be.sync()
     wb = ps.HostBuffer(be, wb)   # the caller marshals its witness into page-locked memory (ps_host_alloc)
     t_load = time.perf_counter() - t0
 
@@ -430,6 +437,42 @@ def groth16_section(be, args, dist=None, dev="cuda"):
                      if tuple(pr) == (A, B, Cc) else "MISMATCH")
     out["cpu_reference"] = ("does not finish at this size: ToQAP is O(m n^3) field multiplications and the dense QAP "
                             "would need 3*m*n*32 bytes (BASELINE.md section 2)")
+    return out
+
+
+def small_configs_section(be, cpu_points_per_s):
+    """BASELINE configs[1] and [2]: the 2^10 repeated-squaring circuit with its dense QAP (Groth16 and
+    PHGR13, checked against the oracle inside tests.parity_cases.config_c2) and a 2^16-constraint sparse
+    circuit (Groth16, checked in the exponent); end-to-end latency through the reference-facing calls.
+    The reference's own cost at 2^10 is an ESTIMATE from its operation counts (3*m*n scalar
+    multiplications in sumBlind, groth16.go:134-141) and the measured rate of the CPU port."""
+    import playsnark_b200 as ps
+    from oracle import ps_oracle as O
+    from tests import helpers as H, parity_cases as P
+    out = {}
+    t = {}
+    P.config_c2(be, 1 << 10, timings=t)
+    m, n = t["variables"], t["gates"]
+    t["parity"] = "h, A, B, C and the 8 PHGR13 elements equal the oracle's (tests.parity_cases.config_c2)"
+    if cpu_points_per_s:
+        t["reference_cpu_groth16_estimate_s"] = round((3 * m * n + 2 * n) / cpu_points_per_s, 1)
+        t["reference_cpu_estimate_how"] = ("(3*m*n + 2n) bit-serial scalar multiplications (sumBlind + BlindEval) / measured "
+                                          "CPU-port rate; Div2's n^3/2 field operations not included")
+    out["c2_dense_2p10"] = t
+    k = 16
+    nn = 1 << k
+    sq, wit = H.sparse_circuit(nn, 7, nn // 2)
+    tr, tw = H.sparse_groth16_setup(be, sq, 7)
+    smp = O.Sampler(99)
+    r, s = smp.fr(), smp.fr()
+    wb = ps.HostBuffer(be, b"".join(v.to_bytes(32, "big") for v in wit))
+    pr = ps.Groth16Prove(tr, sq, wb, r, s, backend=be)
+    best = 1e9
+    for _ in range(5):
+        t0 = time.perf_counter(); pr = ps.Groth16Prove(tr, sq, wb, r, s, backend=be); best = min(best, time.perf_counter() - t0)
+    A, B, Cc, _ = H.sparse_groth16_expected(sq, wit, tw, r, s)
+    out["c3_sparse_2p16"] = {"groth16_prove_ms": best * 1e3, "device_ms": be.prove_timing(),
+                             "parity": "A, B, C equal the exponent-level recomputation" if (pr.A, pr.B, pr.C) == (A, B, Cc) else "MISMATCH"}
     return out
 
 

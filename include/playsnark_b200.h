@@ -56,7 +56,9 @@ int ps_ctx_create(int device, ps_ctx** out);
 int ps_ctx_set_stream(ps_ctx* ctx, void* cuda_stream);
 /* tuning knobs: "msm_accumulate" = 0 (XYZZ accumulator chains, default) | 1 (batched affine tree rounds);
  * "msm_team" = 1 (latency-bound tail kernels of the MSM use a team of four lanes per group operation,
- * default) | 0 (one thread per operation) */
+ * default) | 0 (one thread per operation);
+ * "msm_shards" = N >= 1: base sets and keys loaded afterwards are meant to be summed in N index ranges
+ * (one per GPU, ps_msm_device / ps_g16_msm_partials), so their automatic window is sized for n / N points */
 int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value);
 int ps_ctx_sync(ps_ctx* ctx);
 void ps_ctx_destroy(ps_ctx* ctx);
@@ -181,6 +183,11 @@ int ps_qap_interp_finish(ps_ctx* ctx, const ps_qap* qap, size_t parts, const voi
 int ps_g16_scalars_ab(ps_ctx* ctx, const ps_g16_key* key, const uint8_t* r_be, const uint8_t* s_be, const void* d_a,
                       const void* d_b, void* d_scA, void* d_scB, void* d_scC_tail);
 int ps_g16_h_from_ab(ps_ctx* ctx, const ps_qap* qap, const void* d_a, const void* d_b, void* d_h_out);
+/* end of a sharded proof: `count` gathered records, `stride` bytes apart (a multiple of 16, >= 960), each
+ * [A 192 B | C tail 192 B | B 384 B | C head 192 B | ...] as written by two ps_g16_msm_partials calls;
+ * adds them up and emits the compressed proof elements (G2 on the second stream). */
+int ps_g16_combine(ps_ctx* ctx, const void* d_records, size_t count, size_t stride, uint8_t* outA, uint8_t* outB,
+                   uint8_t* outC);
 
 /* Page-locked host memory for call arguments (witness, scalars): host-to-device copies from it run at
  * link speed and asynchronously; plain pageable buffers are accepted everywhere as well.          */
@@ -211,8 +218,8 @@ int ps_bench_fieldmul(ps_ctx* ctx, int field, int iters, double* mul_per_s, doub
  * [0] digits+sort, [1] bucket-accumulate kernel, [2] partial merge, [3] bucket reduce, [4] total */
 int ps_last_msm_timing(ps_ctx* ctx, float out_ms[5]);
 /* device time in ms of the last ps_g16_prove: [0] quotient (aggregate / interpolation / NTT division),
- * [1] MSM A (G1), [2] MSM C (G1), [3] what remains of MSM B (G2, which runs concurrently on a second
- * stream) after C has finished, [4] normalise + encode, [5] total                                 */
+ * [1] MSM A (G1), [2] MSM C (G1), [3] normalise + encode A and C, [4] what then remains of MSM B and its
+ * encoding (G2, concurrently on a second stream), [5] total                                      */
 int ps_last_prove_timing(ps_ctx* ctx, float out_ms[6]);
 
 #ifdef __cplusplus

@@ -57,6 +57,7 @@ SYMBOLS = [
     ("ps_qap_interp_finish", _I, [_P, _P, _SZ, _P, _P]),
     ("ps_g16_scalars_ab", _I, [_P, _P, _B, _B, _P, _P, _P, _P, _P]),
     ("ps_g16_h_from_ab", _I, [_P, _P, _P, _P, _P]),
+    ("ps_g16_combine", _I, [_P, _P, _SZ, _SZ, _P, _P, _P]),
     ("ps_host_alloc", _I, [_SZ, C.POINTER(_P)]),
     ("ps_host_free", None, [_P]),
     ("ps_phgr13_key_load", _I, [_P, _SZ, _SZ, _I] + [_B] * 10 + [C.POINTER(_P)]),

@@ -163,7 +163,7 @@ class Backend:
     def prove_timing(self):
         t = (C.c_float * 6)()
         self._check(self.lib.ps_last_prove_timing(self.ctx, t))
-        return {"quotient_ms": t[0], "msm_a_ms": t[1], "msm_c_ms": t[2], "msm_b_g2_ms": t[3], "encode_ms": t[4], "total_ms": t[5]}
+        return {"quotient_ms": t[0], "msm_a_ms": t[1], "msm_c_ms": t[2], "encode_g1_ms": t[3], "wait_g2_ms": t[4], "total_ms": t[5]}
 
     def msm_timing(self):
         t = (C.c_float * 5)()

@@ -160,10 +160,13 @@ int bases_finish(ps_ctx* ctx, ps_bases* b) {
   return PS_OK;
 }
 
-int bases_alloc(int group, size_t n, int window_bits, int tables, ps_bases** out) {
+// `shards`: the base set will be summed in `shards` index ranges (one per GPU of a sharded proof); the
+// automatic window is sized for n / shards points per call so that each rank's bucket set (whose
+// merge and reduction are a fixed cost per call) matches its share
+int bases_alloc(int group, size_t n, int window_bits, int tables, int shards, ps_bases** out) {
   if (window_bits < 0 || window_bits > 24 || (window_bits > 0 && window_bits < 2)) return PS_ERR_ARG;
   if (tables < 0) {  // automatic: all windows precomputed when the tables fit comfortably in HBM
-    if (window_bits == 0) window_bits = msm_pick_window_full(n ? n : 1);
+    if (window_bits == 0) window_bits = msm_pick_window_full(n / (size_t)(shards > 0 ? shards : 1) + 1);
     tables = msm_windows(window_bits);
     size_t need = n * (size_t)tables * (group == PS_G1 ? sizeof(G1Affine) : sizeof(G2Affine));
     size_t free_b = need * 8, total_b = 0;
@@ -190,7 +193,7 @@ int bases_alloc(int group, size_t n, int window_bits, int tables, ps_bases** out
 template <class F, class DecodeK>
 int bases_load_t(ps_ctx* ctx, const uint8_t* points, size_t n, int format, int window_bits, int tables, ps_bases** out) {
   ps_bases* b = nullptr;
-  PS_TRY(bases_alloc(GroupOf<F>::ID, n, window_bits, tables, &b));
+  PS_TRY(bases_alloc(GroupOf<F>::ID, n, window_bits, tables, ctx->msm_shards, &b));
   ps_stream_t st = ctx->stream;
   size_t bytes = n * point_bytes(GroupOf<F>::ID, format);
   uint8_t* d_in = ctx->arena.take<uint8_t>(bytes);
@@ -258,6 +261,13 @@ int encode_points(ps_ctx* ctx, const XYZZ<F>* d_pts, size_t count, uint8_t* host
   PS_LAUNCH(XyzzEncodeK<F>, ctx->stream, count, d_pts, (int)PS_FMT_COMPRESSED, d_bytes);
   PS_TRY(dev_d2h(host_out, d_bytes, count * per, ctx->stream));
   return PS_OK;
+}
+
+// the same into the context's page-locked staging area (offset in bytes): does not block the host
+template <class F>
+int encode_points_staged(ps_ctx* ctx, const XYZZ<F>* d_pts, size_t count, size_t stage_off) {
+  if (stage_off + count * PointBytes<F>::COMP > ps_ctx::H_STAGE_BYTES) return PS_ERR_ARG;
+  return encode_points<F>(ctx, d_pts, count, ctx->h_stage + stage_off);
 }
 
 int check_err_flag(ps_ctx* ctx, const uint32_t* d_err, int code) {
@@ -399,6 +409,12 @@ int ps_ctx_create(int device, ps_ctx** out) {
 #endif
   ctx->arena.stream = ctx->stream;
   ctx->arena2.stream = ctx->stream2;
+  {
+    void* hp = nullptr;
+    int rc = ps_host_alloc(ps_ctx::H_STAGE_BYTES, &hp);
+    if (rc != PS_OK) { ps_ctx_destroy(ctx); return rc; }
+    ctx->h_stage = (uint8_t*)hp;
+  }
   *out = ctx;
   return PS_OK;
 }
@@ -424,6 +440,11 @@ int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value) {
     ctx->accum_mode = value;
     return PS_OK;
   }
+  if (!strcmp(name, "msm_shards")) {
+    if (value < 1 || value > 1024) return PS_ERR_ARG;
+    ctx->msm_shards = value;
+    return PS_OK;
+  }
   if (!strcmp(name, "msm_team")) {
     if (value != 0 && value != 1) return PS_ERR_ARG;
     ctx->msm_team = value;
@@ -443,6 +464,7 @@ void ps_ctx_destroy(ps_ctx* ctx) {
   for (auto& t : ctx->ntt_cache) t.release();
   dev_free(ctx->fixed_base[0]);
   dev_free(ctx->fixed_base[1]);
+  ps_host_free(ctx->h_stage);
 #if PS_GPU
   for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy((cudaEvent_t)ctx->ev[i]);
   for (int i = 0; i < 6; i++) if (ctx->evp[i]) cudaEventDestroy((cudaEvent_t)ctx->evp[i]);
@@ -484,7 +506,7 @@ int ps_bases_from_scalars(ps_ctx* ctx, int group, const uint8_t* scalars_be, siz
   if (!out || (n && !scalars_be) || (group != PS_G1 && group != PS_G2)) return PS_ERR_ARG;
   PS_TRY(begin_call(ctx));
   ps_bases* b = nullptr;
-  PS_TRY(bases_alloc(group, n, window_bits, precompute_tables, &b));
+  PS_TRY(bases_alloc(group, n, window_bits, precompute_tables, ctx->msm_shards, &b));
   uint32_t *d_sc = nullptr, *d_err = nullptr;
   int rc = stage_scalars(ctx, scalars_be, n, 0, &d_sc, &d_err);
   if (rc == PS_OK) {
@@ -844,23 +866,23 @@ int ps_g16_prove(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const ui
   {
     SecondaryScope scope(ctx);
     PS_TRY(msm_on_bases<Fp2>(ctx, key->B, 0, (const uint32_t*)sc.scB, sc.nB, 1, resG2));
+    PS_TRY(encode_points_staged<Fp2>(ctx, resG2, 1, 96));   // its inversion chain overlaps the G1 work too
   }
   PS_TRY(msm_on_bases<Fp>(ctx, key->A, 0, (const uint32_t*)sc.scA, sc.nA, 1, resG1));
   PS_TRY(ctx_prove_event(ctx, 2));
   PS_TRY(msm_on_bases<Fp>(ctx, key->C, 0, (const uint32_t*)sc.scC, sc.nC, 1, resG1 + 1));
   PS_TRY(ctx_prove_event(ctx, 3));
-  PS_TRY(ctx_join(ctx));
+  PS_TRY(encode_points_staged<Fp>(ctx, resG1, 2, 0));
   PS_TRY(ctx_prove_event(ctx, 4));
-  uint8_t ac[96];
-  PS_TRY(encode_points<Fp>(ctx, resG1, 2, ac));
-  PS_TRY(encode_points<Fp2>(ctx, resG2, 1, outB));
+  PS_TRY(ctx_join(ctx));
   PS_TRY(ctx_prove_event(ctx, 5));
   ctx->evp_valid = true;
   if (out_h) PS_TRY(export_fr(ctx, sc.qb.h, qap->n - 1, out_h));
   PS_TRY(check_err_flag(ctx, sc.qb.enc_err, PS_ERR_ENCODING));
-  PS_TRY(check_err_flag(ctx, sc.qb.flag, PS_ERR_REMAINDER));
-  memcpy(outA, ac, 48);
-  memcpy(outC, ac + 48, 48);
+  PS_TRY(check_err_flag(ctx, sc.qb.flag, PS_ERR_REMAINDER));   // synchronises the primary stream, which has joined the second
+  memcpy(outA, ctx->h_stage, 48);
+  memcpy(outC, ctx->h_stage + 48, 48);
+  memcpy(outB, ctx->h_stage + 96, 96);
   return PS_OK;
 }
 
@@ -1098,6 +1120,55 @@ int ps_g16_scalars_ab(ps_ctx* ctx, const ps_g16_key* key, const uint8_t* r_be, c
   return PS_OK;
 }
 
+extern "C++" {
+namespace {
+// Sums of the per-rank partial points of a sharded proof, read in place from the gathered records
+// (stride bytes apart): item i adds, over all records, the points at byte offsets off0[i] and (if
+// >= 0) off1[i].  One team of four lanes per item.
+template <class F>
+struct RecordSumK {
+  static constexpr int BLOCK = 32;
+  PS_DEV static void run(uint32_t tid, uint32_t count, const uint8_t* recs, uint32_t stride, int a0, int a1, int b0, int b1,
+                         XYZZ<F>* out) {
+    Coop<true> co(tid);
+    if (co.idle()) return;
+    const int o0 = tid == 0 ? a0 : b0, o1 = tid == 0 ? a1 : b1;
+    XYZZ<F> r = XYZZ<F>::inf();
+    for (uint32_t i = 0; i < count; i++) {
+      const uint8_t* rec = recs + (size_t)i * stride;
+      co.add(r, *(const XYZZ<F>*)(rec + o0));
+      if (o1 >= 0) co.add(r, *(const XYZZ<F>*)(rec + o1));
+    }
+    if (co.writer()) out[tid] = r;
+  }
+};
+}  // namespace
+}  // extern "C++"
+
+int ps_g16_combine(ps_ctx* ctx, const void* d_records, size_t count, size_t stride, uint8_t* outA, uint8_t* outB, uint8_t* outC) {
+  if (!ctx || !d_records || !count || !outA || !outB || !outC || stride < 960 || (stride & 15)) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  const uint8_t* recs = (const uint8_t*)d_records;
+  G1XYZZ* resG1 = ctx->arena.take<G1XYZZ>(2);
+  if (!resG1) return PS_ERR_ALLOC;
+  PS_TRY(ctx_fork(ctx));
+  {
+    SecondaryScope scope(ctx);
+    G2XYZZ* resG2 = ctx->arena.take<G2XYZZ>(1);
+    if (!resG2) return PS_ERR_ALLOC;
+    PS_LAUNCH(RecordSumK<Fp2>, ctx->stream, (size_t)TEAM, (uint32_t)count, recs, (uint32_t)stride, 384, -1, 384, -1, resG2);
+    PS_TRY(encode_points_staged<Fp2>(ctx, resG2, 1, 96));
+  }
+  PS_LAUNCH(RecordSumK<Fp>, ctx->stream, (size_t)2 * TEAM, (uint32_t)count, recs, (uint32_t)stride, 0, -1, 192, 768, resG1);
+  PS_TRY(encode_points_staged<Fp>(ctx, resG1, 2, 0));
+  PS_TRY(ctx_join(ctx));
+  PS_TRY(dev_sync(ctx->stream));
+  memcpy(outA, ctx->h_stage, 48);
+  memcpy(outC, ctx->h_stage + 48, 48);
+  memcpy(outB, ctx->h_stage + 96, 96);
+  return PS_OK;
+}
+
 int ps_g16_scalars(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const uint8_t* witness_be, const uint8_t* r_be,
                    const uint8_t* s_be, void* d_scA, void* d_scC, void* d_scB) {
   if (!key || !qap || !witness_be || !r_be || !s_be || !d_scA || !d_scC || !d_scB) return PS_ERR_ARG;
@@ -1165,16 +1236,24 @@ int ps_phgr13_prove(ps_ctx* ctx, const ps_phgr13_key* key, const ps_qap* qap, co
   if (!w3 || !resG1 || !resG2) return PS_ERR_ALLOC;
   const Fr* wmid = qb.w + diff;
   for (int t = 0; t < 3; t++) PS_LAUNCH(FrCopyK, st, nmid, wmid, w3 + t * nmid);
+  // wss (G2) is independent of the seven G1 sums: second stream, like Groth16's B
+  PS_TRY(ctx_fork(ctx));
+  {
+    SecondaryScope scope(ctx);
+    PS_TRY(msm_on_bases<Fp2>(ctx, key->ws, 0, (const uint32_t*)wmid, nmid, 1, resG2));               // wss
+    PS_TRY(encode_points_staged<Fp2>(ctx, resG2, 1, 7 * 48));
+  }
   PS_TRY(msm_on_bases<Fp>(ctx, key->g1[0], 0, (const uint32_t*)qb.h, n - 1, 1, resG1));            // hs
   for (int i = 1; i < 6; i++)                                                                         // vss yss vass wass yass
     PS_TRY(msm_on_bases<Fp>(ctx, key->g1[i], 0, (const uint32_t*)wmid, nmid, 1, resG1 + i));
   PS_TRY(msm_on_bases<Fp>(ctx, key->g1[6], 0, (const uint32_t*)w3, 3 * nmid, 1, resG1 + 6));         // gz
-  PS_TRY(msm_on_bases<Fp2>(ctx, key->ws, 0, (const uint32_t*)wmid, nmid, 1, resG2));                 // wss
-  PS_TRY(encode_points<Fp>(ctx, resG1, 7, out432));
-  PS_TRY(encode_points<Fp2>(ctx, resG2, 1, out432 + 7 * 48));
+  PS_TRY(encode_points_staged<Fp>(ctx, resG1, 7, 0));
+  PS_TRY(ctx_join(ctx));
   if (out_h) PS_TRY(export_fr(ctx, qb.h, n - 1, out_h));
   PS_TRY(check_err_flag(ctx, qb.enc_err, PS_ERR_ENCODING));
-  return check_err_flag(ctx, qb.flag, PS_ERR_REMAINDER);
+  PS_TRY(check_err_flag(ctx, qb.flag, PS_ERR_REMAINDER));
+  memcpy(out432, ctx->h_stage, 432);
+  return PS_OK;
 }
 
 // ---- measurement ----------------------------------------------------------------------------------------

@@ -28,6 +28,12 @@ struct ps_ctx {
   int accum_mode = 0;
   // latency-bound tail kernels of the MSM: 1 = a team of four lanes per group operation (team.cuh), 0 = one thread
   int msm_team = 1;
+  // base sets loaded from now on are meant to be summed in this many index ranges (sharded proofs)
+  int msm_shards = 1;
+  // small page-locked staging area for results: a device-to-host copy into pageable memory would block
+  // the host until the producing stream has drained, which serialises work meant for the other stream
+  uint8_t* h_stage = nullptr;
+  static constexpr size_t H_STAGE_BYTES = 4096;
 };
 
 namespace ps {

@@ -79,7 +79,7 @@ def _raise_status(st: int):
         raise L.PlaysnarkError(L.PS_ERR_ENCODING, "bad scalar or point encoding")
 
 
-def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_share: float):
+def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_share: float, trace=None):
     """world = 2 * parts ranks.  Ranks [0, parts) fold polynomial a, ranks [parts, 2 parts) polynomial b:
     each one the subtree over its n/parts gates (ps_qap_interp_part); an all-gather hands the subtree
     roots to the two leaders, which run the top levels (ps_qap_interp_finish) and broadcast a and b.
@@ -93,7 +93,15 @@ def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_s
     world, rank = dist.get_world_size(), dist.get_rank()
     parts = world // 2
     g, part = divmod(rank, parts)
-    kh, qh = tr._resident(be), q._resident(be)
+
+    def mark(name):
+        # optional stage timeline (CUDA events on the current stream), read by the caller after a sync
+        if trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            trace.append((name, ev))
+    mark("start")
+    kh, qh = load_key_sharded(be, tr, world), q._resident(be)
     n, nio = q.nbGates, q.nbIO
     nA, nC, nB = (int(lib.ps_g16_scalar_count(kh, w)) for w in (0, 1, 2))
     head = nio + n - 1                                   # [w_nio | h] ; tail = [s a + r b | s | r | r s]
@@ -105,21 +113,26 @@ def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_s
     e_rows = 2 * n // parts if parts > 1 else n
     e_part = new(e_rows)
     be._check(lib.ps_qap_interp_part(be.ctx, qh, wb, g, part, parts, ptr(e_part), ptr(bufC) if nio else None, ptr(status)))
+    mark("interp_part")
     if parts > 1:
         e_all = [new(e_rows) for _ in range(world)]
         dist.all_gather(e_all, e_part)
+        mark("gather_roots")
         coef = [new(n), new(n)]
         if part == 0:
             mine = torch.cat(e_all[g * parts:(g + 1) * parts])
             be._check(lib.ps_qap_interp_finish(be.ctx, qh, parts, ptr(mine), ptr(coef[g])))
     else:
         coef = [e_part if g == 0 else new(n), e_part if g == 1 else new(n)]
+    mark("interp_finish")
     dist.broadcast(coef[0], src=0)
     dist.broadcast(coef[1], src=parts)
+    mark("bcast_ab")
     be._check(lib.ps_g16_scalars_ab(be.ctx, kh, rb, sb, ptr(coef[0]), ptr(coef[1]), ptr(bufA), ptr(bufB), ptr(bufC[head:])))
     hview = bufC[nio:head]
     if rank == 0:
         be._check(lib.ps_g16_h_from_ab(be.ctx, qh, ptr(coef[0]), ptr(coef[1]), ptr(hview)))
+    mark("scalars_and_h")
     weights = [rank0_share] + [1.0] * (world - 1)       # rank 0 also divides: it takes a smaller MSM share
     rA = weighted_ranges(nA, weights)[rank]
     rB = weighted_ranges(nB, weights)[rank]
@@ -136,26 +149,35 @@ def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_s
         return out
 
     early = partials([rA, (head + rT[0], head + rT[1]), rB])
+    mark("msm_early")
     dist.broadcast(hview, src=0)
+    mark("bcast_h")
     late = partials([(0, 0), rH, (0, 0)])
-    rec = torch.cat([early, late[192:384], status.view(torch.uint8)])   # A | C tail | B | C head | status
-    recs = [torch.zeros_like(rec) for _ in range(world)]
-    dist.all_gather(recs, rec)
-    allr = torch.stack(recs)
-    _raise_status(int(allr[:, 960:964].contiguous().view(torch.int32).max().item()) if world else 0)
+    mark("msm_late")
+    pad = torch.zeros(12, dtype=torch.uint8, device=device)
+    rec = torch.cat([early, late[192:384], status.view(torch.uint8), pad])   # A | C tail | B | C head | status | pad
+    recs = torch.zeros((world, rec.numel()), dtype=torch.uint8, device=device)
+    dist.all_gather(list(recs.unbind(0)), rec)
+    mark("gather_partials")
+    _raise_status(int(recs[:, 960:964].contiguous().view(torch.int32).max().item()))
     if rank != 0:
         return None
-    res = []
-    for grp, cols in ((L.PS_G1, [(0, 192)]), (L.PS_G2, [(384, 768)]), (L.PS_G1, [(192, 384), (768, 960)])):
-        allp = torch.cat([allr[:, lo:hi].reshape(-1) for lo, hi in cols]).contiguous()
-        out = C.create_string_buffer(48 if grp == L.PS_G1 else 96)
-        be._check(lib.ps_msm_combine(be.ctx, grp, C.c_void_p(allp.data_ptr()), world * len(cols), out))
-        res.append(out.raw)
-    return res[0], res[1], res[2]   # A, B, C
+    oA, oB, oC = C.create_string_buffer(48), C.create_string_buffer(96), C.create_string_buffer(48)
+    be._check(lib.ps_g16_combine(be.ctx, ptr(recs), world, rec.numel(), oA, oB, oC))
+    return oA.raw, oB.raw, oC.raw
+
+
+def load_key_sharded(be, tr, world: int):
+    """proving key resident on this rank with MSM windows sized for a 1/world share of every base set"""
+    be.set_option("msm_shards", max(1, world))
+    try:
+        return tr._resident(be)
+    finally:
+        be.set_option("msm_shards", 1)
 
 
 def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device="cpu", split_quotient: bool = True,
-                          rank0_share: float = 0.5):
+                          rank0_share: float = 0.5, trace=None):
     """Groth16Prove (groth16.go:122-211) over the ranks of `dist`.  Every rank holds the proving key.
     With a sparse QAP and an even, power-of-two-halved world the whole proof is pipelined across the
     ranks (_groth16_pipelined: every rank holds the QAP and reads `witness`).  Otherwise the quotient
@@ -170,8 +192,8 @@ def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device=
     parts = world // 2
     if (split_quotient and world >= 2 and world % 2 == 0 and parts & (parts - 1) == 0 and type(q).__name__ == "SparseQAP"
             and parts <= q.nbGates // 2):
-        return _groth16_pipelined(be, tr, q, witness, r, s, dist, device, rank0_share)
-    kh = tr._resident(be)
+        return _groth16_pipelined(be, tr, q, witness, r, s, dist, device, rank0_share, trace)
+    kh = load_key_sharded(be, tr, world)
     counts = [int(lib.ps_g16_scalar_count(kh, w)) for w in (0, 1, 2)]
     groups = [L.PS_G1, L.PS_G1, L.PS_G2]
     bufs = [torch.zeros((c, 8), dtype=torch.int32, device=device) for c in counts]

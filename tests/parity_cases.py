@@ -312,7 +312,7 @@ def groth16_sparse_exponent_check(be, log_n, seed):
         api.Groth16Prove(tr, sq, bad, r, s, backend=be)
 
 
-def config_c2(be, n=1 << 10):
+def config_c2(be, n=1 << 10, timings=None):
     """BASELINE configs[1]: repeated-squaring R1CS with 2^10 multiplication gates (dense QAP of
     3*1026*1024 coefficients), Groth16 and PHGR13 prove; int witness x0 = -1 (the only chain that fits
     the reference's Value int) -- a full-width negative scalar r-1 repeated."""
@@ -358,6 +358,18 @@ def config_c2(be, n=1 << 10):
     gz = O.g1_add(O.msm_naive(O.F1, fe, st["EK"]["vbs"]), O.g1_add(O.msm_naive(O.F1, fe, st["EK"]["wbs"]),
                                                                     O.msm_naive(O.F1, fe, st["EK"]["ybs"])))
     assert pp.gz == O.g1_compress(gz)
+    if timings is not None:   # bench.py: end-to-end latency of the two provers on this config (host bytes in / out)
+        import time
+        ek = H.mirror_phgr13_ek(st["EK"])
+        wb = b"".join(v.to_bytes(32, "big") for v in w)
+        for name, fn in (("groth16_prove_ms", lambda: api.Groth16Prove(tr, q, wb, rr, ss, backend=be)),
+                         ("phgr13_prove_ms", lambda: api.PHGR13Prove(ek, q, wb, backend=be))):
+            fn()
+            best = 1e9
+            for _ in range(5):
+                t0 = time.perf_counter(); fn(); best = min(best, time.perf_counter() - t0)
+            timings[name] = best * 1e3
+        timings.update(gates=n, variables=oq.nb_vars, mid=oq.nb_io)
 
 
 def readme_flow_through_api(be):

@@ -31,7 +31,7 @@ tr, tw = H.sparse_groth16_setup(be, sq, 7)
 smp = O.Sampler(99)
 r, s = smp.fr(), smp.fr()
 wb = ps.HostBuffer(be, b"".join(v.to_bytes(32, "big") for v in wit))
-sq._resident(be); tr._resident(be); be.sync()
+sq._resident(be); D.load_key_sharded(be, tr, world); be.sync()
 want = H.sparse_groth16_expected(sq, wit, tw, r, s)[:3] if rank == 0 else None
 for share in shares:
     for _ in range(2):
@@ -45,4 +45,13 @@ for share in shares:
     ms = (time.perf_counter() - t0) / reps * 1e3
     if rank == 0:
         print("world %d 2^%d rank0_share %.2f: %.2f ms per proof, parity %s" % (world, log_n, share, ms, tuple(pr) == tuple(want)), flush=True)
+# stage timeline of one proof per rank (CUDA events; ms since the start of the call)
+trace = []
+pr = D.groth16_prove_sharded(be, tr, sq, wb, r, s, dist, dev, rank0_share=shares[0], trace=trace)
+torch.cuda.synchronize()
+line = "rank %d: " % rank + ", ".join("%s %.2f" % (nm, trace[0][1].elapsed_time(ev)) for nm, ev in trace[1:])
+for rk in range(world):
+    dist.barrier()
+    if rk == rank:
+        print(line, flush=True)
 dist.destroy_process_group()
