@@ -100,6 +100,7 @@ inline int ps_launch(ps_stream_t, size_t n, Args... args) {
 }
 #endif
 #define PS_LAUNCH(K, st, n, ...) PS_TRY((ps_launch<K>(st, n, __VA_ARGS__)))
+#define PS_COMMA ,
 
 // ---- device memory ----------------------------------------------------------------------------
 inline int dev_alloc(void** p, size_t bytes) {

@@ -736,6 +736,7 @@ int ps_qap_load_r1cs(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, co
   if (rc == PS_OK && !d_z) rc = PS_ERR_ALLOC;
   if (rc == PS_OK) rc = inv_zprime_build(ctx, sq, (uint32_t)n_gates);
   if (rc == PS_OK) rc = ztree_build(ctx, sq, (uint32_t)n_gates, k, d_z);
+  if (rc == PS_OK) rc = twist_tables_build(ctx, sq, (uint32_t)n_gates, k);
   if (rc == PS_OK) rc = series_tables_build(ctx, sq, (uint32_t)n_gates, k, d_z);
   q->log_np = k;
   if (rc == PS_OK) rc = check_err_flag(ctx, d_err, PS_ERR_ENCODING);

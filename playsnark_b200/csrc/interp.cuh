@@ -32,11 +32,12 @@ struct SparseQap {
   CsrDev mat[3];                 // left, right, out
   Fr* inv_zprime = nullptr;      // 1 / z'(j), j = 1..n
   std::vector<Fr*> ztree;        // level l: NTT_{2s} of every node's Z (s = 2^l), n/s nodes x 2s
+  Fr* twist = nullptr;           // level l at offset 2s - 2 (s = 2^l): (1/2s) * omega_{4s}^t, t < 2s; l < k - 1
   Fr* s_hat = nullptr;           // NTT_{2n} of the series inverse of rev(z) mod x^(n-1)   (bit-reversed)
   Fr* z_hat = nullptr;           // NTT_{2n} of z                                          (bit-reversed)
   void release() {
     for (auto& m : mat) { dev_free(m.row_ptr); dev_free(m.col); dev_free(m.val); }
-    dev_free(inv_zprime); dev_free(s_hat); dev_free(z_hat);
+    dev_free(inv_zprime); dev_free(s_hat); dev_free(z_hat); dev_free(twist);
     for (auto* p : ztree) dev_free(p);
     ztree.clear();
   }
@@ -149,6 +150,26 @@ inline int inv_zprime_build(ps_ctx* ctx, SparseQap* sq, uint32_t n) {
   return dev_sync(ctx->stream);
 }
 
+// T[t] = scale * tw[t * step]                                                          (thread over 2s)
+struct TwistTableK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t t, uint32_t step, Fr scale, const Fr* tw, Fr* T) { T[t] = scale * fe_ld(tw + (size_t)t * step); }
+};
+// per-level twist factors of the interpolation tree: turning the coefficients of a node polynomial
+// (degree < 2s) into its values on the odd 4s-th roots of unity, with the 1/2s of the inverse transform
+inline int twist_tables_build(ps_ctx* ctx, SparseQap* sq, uint32_t n, int k) {
+  const NttTables* tabs = nullptr;
+  PS_TRY(ctx_ntt_tables(ctx, k + 1, &tabs));
+  const uint32_t n_tw = 2 * n;
+  PS_TRY(dev_alloc((void**)&sq->twist, (size_t)(n > 2 ? n : 2) * sizeof(Fr)));
+  for (int l = 0; l + 1 < k; l++) {
+    const uint32_t two_s = 2u << l;
+    PS_LAUNCH(TwistTableK, ctx->stream, two_s, n_tw / (2 * two_s), fr_inv(fr_host_from_u64(two_s)), (const Fr*)tabs->tw,
+              sq->twist + (two_s - 2));
+  }
+  return PS_OK;
+}
+
 // E0[poly][j][0..2) = [w_j, w_j]: the size-2 transform of the constant polynomial w_j   (thread over P*n)
 struct InterpLeafK {
   static constexpr int BLOCK = 256;
@@ -214,17 +235,25 @@ inline int interpolate_levels(ps_ctx* ctx, const SparseQap* sq, uint32_t n, int 
   for (int l = l0; l < l1; l++) {
     const uint32_t two_s = 2u << l;
     const bool last = (l + 1 == k);
-    Fr inv2s = fr_inv(fr_host_from_u64(two_s));
     Fr* dst = last ? coef : Cbuf;
+    // The combine O = E_L Zhat_R + E_R Zhat_L is its own (perfectly coalesced) pass: fused into the
+    // loads of the inverse transform's first pass it was measured slower (2^20: quotient 21.1 vs 17.6 ms;
+    // that pass reads thread-contiguous runs of 8 elements, and the combine multiplies the badly
+    // coalesced streams by five).  The other element-wise steps ride on the transforms' last passes
+    // (NttIO), whose accesses are coalesced:
+    //   twist    coefficient t times (1/2s) omega_{4s}^t while the inverse transform stores its output,
+    //   the forward transform stores straight into the odd half of the parent's block.
+    NttIO io;
+    io.ns = ns;
+    io.two_s = two_s;
+    io.twist = sq->twist + (two_s - 2);
+    io.odd_dst = E[cur ^ 1];
+    io.scale = fr_inv(fr_host_from_u64(two_s));
     const Fr* Zhat = sq->ztree[l] + 2 * (size_t)lo;  // node j of level l starts at j * 2s = 2 * (its first leaf)
     PS_LAUNCH(InterpCombine2K, st, (size_t)P * ns, ns, two_s, (const Fr*)E[cur], Zhat, last ? (Fr*)nullptr : E[cur ^ 1], dst);
-    PS_TRY(ntt_inverse_blocks_unscaled(st, dst, (size_t)P * ns, l + 1, tabs->tw_inv, n_tw));
-    if (last) {
-      PS_LAUNCH(FrScaleK, st, (size_t)P * ns, inv2s, dst);
-    } else {
-      PS_LAUNCH(InterpTwistK, st, (size_t)P * ns, two_s, n_tw / (2 * two_s), inv2s, (const Fr*)tabs->tw, Cbuf);
-      PS_TRY(ntt_forward_blocks(st, Cbuf, (size_t)P * ns, l + 1, tabs->tw, n_tw));
-      PS_LAUNCH(InterpOddK, st, (size_t)P * ns, ns, two_s, (const Fr*)Cbuf, E[cur ^ 1]);
+    PS_TRY(ntt_inverse_blocks_unscaled(st, dst, (size_t)P * ns, l + 1, tabs->tw_inv, n_tw, last ? NTT_ST_SCALE : NTT_ST_TWIST, &io));
+    if (!last) {
+      PS_TRY(ntt_forward_blocks(st, Cbuf, (size_t)P * ns, l + 1, tabs->tw, n_tw, NTT_ST_ODD, &io));
       cur ^= 1;
     }
   }

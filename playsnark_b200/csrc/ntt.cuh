@@ -40,18 +40,48 @@ struct FrMulTableK {
 #ifndef PS_NTT_MINB
 #define PS_NTT_MINB 4
 #endif
-template <int R>
+
+// How the LAST pass of a batched transform writes its outputs (compile-time mode, so that every variant
+// stays as lean as the plain kernel).  The interpolation tree (interp.cuh) fuses its element-wise steps
+// into these stores:
+//   NTT_ST_PLAIN  a[idx] = v
+//   NTT_ST_TWIST  a[idx] = v * io.twist[idx mod two_s]
+//   NTT_ST_SCALE  a[idx] = v * io.scale
+//   NTT_ST_ODD    v goes to the odd half of its parent block in io.odd_dst (not to a)
+enum { NTT_ST_PLAIN = 0, NTT_ST_TWIST = 1, NTT_ST_SCALE = 2, NTT_ST_ODD = 3 };
+struct NttIO {
+  const Fr* twist = nullptr;
+  Fr* odd_dst = nullptr;
+  uint32_t ns = 0, two_s = 0;
+  Fr scale;
+};
+template <int MODE>
+PS_DEV void ntt_io_store(const NttIO& io, Fr* a, size_t idx, const Fr& v) {
+  if (MODE == NTT_ST_ODD) {
+    const uint32_t poly = (uint32_t)(idx / io.ns), r = (uint32_t)(idx % io.ns);
+    const uint32_t p = r / io.two_s, e = r % io.two_s;
+    io.odd_dst[(size_t)poly * 2 * io.ns + (size_t)p * 2 * io.two_s + io.two_s + e] = v;
+  } else if (MODE == NTT_ST_TWIST) {
+    a[idx] = v * fe_ld(io.twist + ((uint32_t)idx & (io.two_s - 1)));
+  } else if (MODE == NTT_ST_SCALE) {
+    a[idx] = v * io.scale;
+  } else {
+    a[idx] = v;
+  }
+}
+
+template <int R, int MODE = NTT_ST_PLAIN>
 struct NttDifK {
   static constexpr int BLOCK = PS_NTT_BLOCK;
   static constexpr int MIN_BLOCKS = PS_NTT_MINB;   // 8 field elements per thread: cap registers for 4 warps / scheduler
   // one launch = R stages on sub-transforms of size B (B >= 2^R); n/2^R threads
-  PS_DEV static void run(uint32_t tid, Fr* a, uint32_t n, uint32_t B, const Fr* tw) {
+  PS_DEV static void run(uint32_t tid, Fr* a, uint32_t n, uint32_t B, const Fr* tw, NttIO io) {
     const uint32_t q = B >> R;
     const uint32_t blk = tid / q, j = tid % q;
-    Fr* base = a + (size_t)blk * B + j;
+    const size_t base = (size_t)blk * B + j;
     Fr x[1 << R];
 #pragma unroll
-    for (int k = 0; k < (1 << R); k++) x[k] = base[(size_t)k * q];
+    for (int k = 0; k < (1 << R); k++) x[k] = a[base + (size_t)k * q];
 #pragma unroll
     for (int t = 0; t < R; t++) {
       const int hl = 1 << (R - 1 - t);           // half size in units of k
@@ -69,21 +99,21 @@ struct NttDifK {
       }
     }
 #pragma unroll
-    for (int k = 0; k < (1 << R); k++) base[(size_t)k * q] = x[k];
+    for (int k = 0; k < (1 << R); k++) ntt_io_store<MODE>(io, a, base + (size_t)k * q, x[k]);
   }
 };
 
-template <int R>
+template <int R, int MODE = NTT_ST_PLAIN>
 struct NttDitK {
   static constexpr int BLOCK = PS_NTT_BLOCK;
   static constexpr int MIN_BLOCKS = PS_NTT_MINB;
   // one launch = R stages that grow finished sub-transforms of size B0 to B0 * 2^R
-  PS_DEV static void run(uint32_t tid, Fr* a, uint32_t n, uint32_t B0, const Fr* tw_inv) {
+  PS_DEV static void run(uint32_t tid, Fr* a, uint32_t n, uint32_t B0, const Fr* tw_inv, NttIO io) {
     const uint32_t blk = tid / B0, j = tid % B0;
-    Fr* base = a + ((size_t)blk * B0 << R) + j;
+    const size_t base = ((size_t)blk * B0 << R) + j;
     Fr x[1 << R];
 #pragma unroll
-    for (int k = 0; k < (1 << R); k++) x[k] = base[(size_t)k * B0];
+    for (int k = 0; k < (1 << R); k++) x[k] = a[base + (size_t)k * B0];
 #pragma unroll
     for (int t = 0; t < R; t++) {
       const int hl = 1 << t;
@@ -101,7 +131,7 @@ struct NttDitK {
       }
     }
 #pragma unroll
-    for (int k = 0; k < (1 << R); k++) base[(size_t)k * B0] = x[k];
+    for (int k = 0; k < (1 << R); k++) ntt_io_store<MODE>(io, a, base + (size_t)k * B0, x[k]);
   }
 };
 
@@ -137,27 +167,46 @@ inline Fr fr_root_of_unity(int log_n) {
 #ifndef PS_NTT_MAXR
 #define PS_NTT_MAXR 3
 #endif
-inline int ntt_forward_blocks(ps_stream_t st, Fr* a, size_t len, int log_block, const Fr* tw, uint32_t n_tw) {
+template <template <int, int> class K, int MODE>
+inline int ntt_launch_pass(ps_stream_t st, int r, size_t len, Fr* a, uint32_t n_tw, uint32_t B, const Fr* tw, const NttIO& io) {
+  if (r == 3) PS_LAUNCH(K<3 PS_COMMA MODE>, st, len >> 3, a, n_tw, B, tw, io);
+  else if (r == 2) PS_LAUNCH(K<2 PS_COMMA MODE>, st, len >> 2, a, n_tw, B, tw, io);
+  else PS_LAUNCH(K<1 PS_COMMA MODE>, st, len >> 1, a, n_tw, B, tw, io);
+  return PS_OK;
+}
+template <template <int, int> class K>
+inline int ntt_launch_pass_mode(ps_stream_t st, int mode, int r, size_t len, Fr* a, uint32_t n_tw, uint32_t B, const Fr* tw, const NttIO& io) {
+  switch (mode) {
+    case NTT_ST_TWIST: return ntt_launch_pass<K, NTT_ST_TWIST>(st, r, len, a, n_tw, B, tw, io);
+    case NTT_ST_SCALE: return ntt_launch_pass<K, NTT_ST_SCALE>(st, r, len, a, n_tw, B, tw, io);
+    case NTT_ST_ODD: return ntt_launch_pass<K, NTT_ST_ODD>(st, r, len, a, n_tw, B, tw, io);
+    default: return ntt_launch_pass<K, NTT_ST_PLAIN>(st, r, len, a, n_tw, B, tw, io);
+  }
+}
+// `store_mode` / `io`: output handling of the LAST pass (the earlier passes store in place).
+inline int ntt_forward_blocks(ps_stream_t st, Fr* a, size_t len, int log_block, const Fr* tw, uint32_t n_tw,
+                              int store_mode = NTT_ST_PLAIN, const NttIO* io = nullptr) {
   int done = 0;
+  NttIO none;
   while (done < log_block) {
     int r = log_block - done >= PS_NTT_MAXR ? PS_NTT_MAXR : log_block - done;
     uint32_t B = 1u << (log_block - done);
-    if (r == 3) PS_LAUNCH(NttDifK<3>, st, len >> 3, a, n_tw, B, tw);
-    else if (r == 2) PS_LAUNCH(NttDifK<2>, st, len >> 2, a, n_tw, B, tw);
-    else PS_LAUNCH(NttDifK<1>, st, len >> 1, a, n_tw, B, tw);
+    const bool lastp = done + r == log_block;
+    PS_TRY(ntt_launch_pass_mode<NttDifK>(st, lastp ? store_mode : NTT_ST_PLAIN, r, len, a, n_tw, B, tw, (lastp && io) ? *io : none));
     done += r;
   }
   return PS_OK;
 }
 // Batched inverse DIT (bit-reversed -> natural inside each block), WITHOUT the 1/2^log_block factor.
-inline int ntt_inverse_blocks_unscaled(ps_stream_t st, Fr* a, size_t len, int log_block, const Fr* tw_inv, uint32_t n_tw) {
+inline int ntt_inverse_blocks_unscaled(ps_stream_t st, Fr* a, size_t len, int log_block, const Fr* tw_inv, uint32_t n_tw,
+                                       int store_mode = NTT_ST_PLAIN, const NttIO* io = nullptr) {
   int done = 0;
+  NttIO none;
   while (done < log_block) {
     int r = log_block - done >= PS_NTT_MAXR ? PS_NTT_MAXR : log_block - done;
     uint32_t B0 = 1u << done;
-    if (r == 3) PS_LAUNCH(NttDitK<3>, st, len >> 3, a, n_tw, B0, tw_inv);
-    else if (r == 2) PS_LAUNCH(NttDitK<2>, st, len >> 2, a, n_tw, B0, tw_inv);
-    else PS_LAUNCH(NttDitK<1>, st, len >> 1, a, n_tw, B0, tw_inv);
+    const bool lastp = done + r == log_block;
+    PS_TRY(ntt_launch_pass_mode<NttDitK>(st, lastp ? store_mode : NTT_ST_PLAIN, r, len, a, n_tw, B0, tw_inv, (lastp && io) ? *io : none));
     done += r;
   }
   return PS_OK;

@@ -312,6 +312,93 @@ def groth16_sparse_exponent_check(be, log_n, seed):
         api.Groth16Prove(tr, sq, bad, r, s, backend=be)
 
 
+def sharded_steps_recombine(be, log_n, parts, fake_world, seed, device="cpu"):
+    """The entry points of the multi-GPU Groth16 flow (dist.py), driven from ONE process: the subtrees
+    of ps_qap_interp_part + ps_qap_interp_finish must reproduce ps_qap_aggregate_one's coefficients,
+    ps_g16_scalars_ab / ps_g16_h_from_ab the scalar vectors of ps_g16_scalars, and the partial MSMs of
+    `fake_world` uneven shards, added by ps_g16_combine, the proof of ps_g16_prove -- all bit for bit."""
+    import ctypes as C
+    import torch
+    from playsnark_b200 import dist as D
+    lib = be.lib
+    n = 1 << log_n
+    sq, wit = H.sparse_circuit(n, seed, n // 2)
+    tr, tw = H.sparse_groth16_setup(be, sq, seed)
+    smp = O.Sampler(seed + 77)
+    r, s = smp.fr(), smp.fr()
+    pr = api.Groth16Prove(tr, sq, wit, r, s, backend=be)
+    kh, qh = tr._resident(be), sq._resident(be)
+    wb, rb, sb = api._fr_bytes(wit), api._fr_bytes([r]), api._fr_bytes([s])
+    new = lambda rows: torch.zeros((rows, 8), dtype=torch.int32, device=device)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    nio = sq.nbIO
+    nA, nC, nB = (int(lib.ps_g16_scalar_count(kh, w)) for w in (0, 1, 2))
+    head = nio + n - 1
+    # reference scalar vectors and coefficients from the single-GPU entry points
+    refA, refC, refB = new(nA), new(nC), new(nB)
+    be._check(lib.ps_g16_scalars(be.ctx, kh, qh, wb, rb, sb, ptr(refA), ptr(refC), ptr(refB)))
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    bufA, bufC, bufB = new(nA), new(nC), new(nB)
+    coef = []
+    for which in (0, 1):
+        want = new(n)
+        be._check(lib.ps_qap_aggregate_one(be.ctx, qh, wb, which, ptr(want)))
+        if parts == 1:
+            got = new(n)
+            be._check(lib.ps_qap_interp_part(be.ctx, qh, wb, which, 0, 1, ptr(got), ptr(bufC), ptr(status)))
+        else:
+            rows = 2 * n // parts
+            e_all = new(parts * rows)
+            for part in range(parts):
+                be._check(lib.ps_qap_interp_part(be.ctx, qh, wb, which, part, parts, ptr(e_all[part * rows:(part + 1) * rows]),
+                                                 ptr(bufC), ptr(status)))
+            got = new(n)
+            be._check(lib.ps_qap_interp_finish(be.ctx, qh, parts, ptr(e_all), ptr(got)))
+        be.sync()
+        assert torch.equal(got, want), ("coefficients", which)
+        coef.append(got)
+    be._check(lib.ps_g16_scalars_ab(be.ctx, kh, rb, sb, ptr(coef[0]), ptr(coef[1]), ptr(bufA), ptr(bufB), ptr(bufC[head:])))
+    be._check(lib.ps_g16_h_from_ab(be.ctx, qh, ptr(coef[0]), ptr(coef[1]), ptr(bufC[nio:head])))
+    be.sync()
+    assert int(status[0]) == 0
+    assert torch.equal(bufA, refA) and torch.equal(bufB, refB) and torch.equal(bufC, refC)
+    # uneven shards of the four MSM pieces, one 976-byte record per fake rank
+    weights = [0.4] + [1.0] * (fake_world - 1)
+    recs = torch.zeros((fake_world, 976), dtype=torch.uint8, device=device)
+    spans = lambda cnt: D.weighted_ranges(cnt, weights)
+    rA, rB, rT, rH = spans(nA), spans(nB), spans(nC - head), spans(head)
+
+    def partials(sp):
+        out = torch.zeros(768, dtype=torch.uint8, device=device)
+        first = (C.c_size_t * 3)(*[lo for lo, _ in sp])
+        cnt = (C.c_size_t * 3)(*[hi - lo for lo, hi in sp])
+        views = [buf[lo:hi] if hi > lo else buf for buf, (lo, hi) in zip((bufA, bufC, bufB), sp)]
+        be._check(lib.ps_g16_msm_partials(be.ctx, kh, ptr(views[0]), ptr(views[1]), ptr(views[2]), first, cnt, ptr(out)))
+        be.sync()
+        return out
+
+    for k in range(fake_world):
+        early = partials([rA[k], (head + rT[k][0], head + rT[k][1]), rB[k]])
+        late = partials([(0, 0), rH[k], (0, 0)])
+        recs[k, :768] = early
+        recs[k, 768:960] = late[192:384]
+    assert sum(hi - lo for lo, hi in rA) == nA and rA[0][0] == 0 and rA[-1][1] == nA
+    oA, oB, oC = C.create_string_buffer(48), C.create_string_buffer(96), C.create_string_buffer(48)
+    be._check(lib.ps_g16_combine(be.ctx, ptr(recs), fake_world, 976, oA, oB, oC))
+    assert (oA.raw, oB.raw, oC.raw) == (pr.A, pr.B, pr.C)
+    # a broken witness sets the remainder bit of the device status word on the rank that owns the gate
+    bad = list(wit); bad[-1] = (bad[-1] + 1) % O.R
+    st2 = torch.zeros(1, dtype=torch.int32, device=device)
+    hit = 0
+    for part in range(parts):
+        st2.zero_()
+        rows = 2 * n // parts if parts > 1 else n
+        be._check(lib.ps_qap_interp_part(be.ctx, qh, api._fr_bytes(bad), 0, part, parts, ptr(new(rows)), None, ptr(st2)))
+        be.sync()
+        hit += int(st2[0]) & 2
+    assert hit >= 2
+
+
 def config_c2(be, n=1 << 10, timings=None):
     """BASELINE configs[1]: repeated-squaring R1CS with 2^10 multiplication gates (dense QAP of
     3*1026*1024 coefficients), Groth16 and PHGR13 prove; int witness x0 = -1 (the only chain that fits

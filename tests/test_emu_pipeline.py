@@ -92,3 +92,7 @@ def test_msm_batched_affine_option(be):
 
 
 def test_sparse_phgr13_exponent_check(be): P.phgr13_sparse_exponent_check(be, 4, seed=11)
+
+
+@pytest.mark.parametrize("parts,world", [(1, 2), (2, 3), (4, 5)])
+def test_sharded_steps_recombine(be, parts, world): P.sharded_steps_recombine(be, 4, parts, world, seed=21 + parts)

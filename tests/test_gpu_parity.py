@@ -136,6 +136,12 @@ def test_msm_batched_affine_option(be):
         be.set_option("msm_accumulate", 0)
 
 
+@pytest.mark.parametrize("log_n,parts,world", [(6, 1, 2), (10, 4, 8), (14, 2, 3)])
+def test_sharded_steps_recombine(be, log_n, parts, world):
+    # every entry point of the multi-GPU Groth16 flow, recombined on one GPU against ps_g16_prove
+    P.sharded_steps_recombine(be, log_n, parts, world, seed=log_n, device="cuda")
+
+
 def test_no_device_is_loud():
     lib = L.load()
     import ctypes as C
