@@ -58,7 +58,9 @@ int ps_ctx_set_stream(ps_ctx* ctx, void* cuda_stream);
  * "msm_team" = 1 (latency-bound tail kernels of the MSM use a team of four lanes per group operation,
  * default) | 0 (one thread per operation);
  * "msm_shards" = N >= 1: base sets and keys loaded afterwards are meant to be summed in N index ranges
- * (one per GPU, ps_msm_device / ps_g16_msm_partials), so their automatic window is sized for n / N points */
+ * (one per GPU, ps_msm_device / ps_g16_msm_partials), so their automatic window is sized for n / N points;
+ * "msm_bucket_cost" = cost of one bucket (merge + reduction) in the automatic window choice, in field
+ * products with a mixed addition counting 10 (default 70, fitted on B200) */
 int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value);
 int ps_ctx_sync(ps_ctx* ctx);
 void ps_ctx_destroy(ps_ctx* ctx);

@@ -163,10 +163,10 @@ int bases_finish(ps_ctx* ctx, ps_bases* b) {
 // `shards`: the base set will be summed in `shards` index ranges (one per GPU of a sharded proof); the
 // automatic window is sized for n / shards points per call so that each rank's bucket set (whose
 // merge and reduction are a fixed cost per call) matches its share
-int bases_alloc(int group, size_t n, int window_bits, int tables, int shards, ps_bases** out) {
+int bases_alloc(int group, size_t n, int window_bits, int tables, int shards, int bucket_cost, ps_bases** out) {
   if (window_bits < 0 || window_bits > 24 || (window_bits > 0 && window_bits < 2)) return PS_ERR_ARG;
   if (tables < 0) {  // automatic: all windows precomputed when the tables fit comfortably in HBM
-    if (window_bits == 0) window_bits = msm_pick_window_full(n / (size_t)(shards > 0 ? shards : 1) + 1);
+    if (window_bits == 0) window_bits = msm_pick_window_full(n / (size_t)(shards > 0 ? shards : 1) + 1, (double)bucket_cost);
     tables = msm_windows(window_bits);
     size_t need = n * (size_t)tables * (group == PS_G1 ? sizeof(G1Affine) : sizeof(G2Affine));
     size_t free_b = need * 8, total_b = 0;
@@ -193,7 +193,7 @@ int bases_alloc(int group, size_t n, int window_bits, int tables, int shards, ps
 template <class F, class DecodeK>
 int bases_load_t(ps_ctx* ctx, const uint8_t* points, size_t n, int format, int window_bits, int tables, ps_bases** out) {
   ps_bases* b = nullptr;
-  PS_TRY(bases_alloc(GroupOf<F>::ID, n, window_bits, tables, ctx->msm_shards, &b));
+  PS_TRY(bases_alloc(GroupOf<F>::ID, n, window_bits, tables, ctx->msm_shards, ctx->msm_bucket_cost, &b));
   ps_stream_t st = ctx->stream;
   size_t bytes = n * point_bytes(GroupOf<F>::ID, format);
   uint8_t* d_in = ctx->arena.take<uint8_t>(bytes);
@@ -445,6 +445,11 @@ int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value) {
     ctx->msm_shards = value;
     return PS_OK;
   }
+  if (!strcmp(name, "msm_bucket_cost")) {
+    if (value < 1 || value > 100000) return PS_ERR_ARG;
+    ctx->msm_bucket_cost = value;
+    return PS_OK;
+  }
   if (!strcmp(name, "msm_team")) {
     if (value != 0 && value != 1) return PS_ERR_ARG;
     ctx->msm_team = value;
@@ -506,7 +511,7 @@ int ps_bases_from_scalars(ps_ctx* ctx, int group, const uint8_t* scalars_be, siz
   if (!out || (n && !scalars_be) || (group != PS_G1 && group != PS_G2)) return PS_ERR_ARG;
   PS_TRY(begin_call(ctx));
   ps_bases* b = nullptr;
-  PS_TRY(bases_alloc(group, n, window_bits, precompute_tables, ctx->msm_shards, &b));
+  PS_TRY(bases_alloc(group, n, window_bits, precompute_tables, ctx->msm_shards, ctx->msm_bucket_cost, &b));
   uint32_t *d_sc = nullptr, *d_err = nullptr;
   int rc = stage_scalars(ctx, scalars_be, n, 0, &d_sc, &d_err);
   if (rc == PS_OK) {

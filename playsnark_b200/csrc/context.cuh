@@ -4,6 +4,10 @@
 #include "ntt.cuh"
 #include <utility>
 
+#ifndef PS_BUCKET_COST
+#define PS_BUCKET_COST 70   // see msm_pick_window_full (msm.cuh)
+#endif
+
 struct ps_ctx {
   int device = 0;
   ps::ps_stream_t stream = nullptr;
@@ -30,6 +34,8 @@ struct ps_ctx {
   int msm_team = 1;
   // base sets loaded from now on are meant to be summed in this many index ranges (sharded proofs)
   int msm_shards = 1;
+  // window model: time of one bucket (merge + reduction) in field products, a mixed addition being 10
+  int msm_bucket_cost = PS_BUCKET_COST;
   // small page-locked staging area for results: a device-to-host copy into pageable memory would block
   // the host until the producing stream has drained, which serialises work meant for the other stream
   uint8_t* h_stage = nullptr;

@@ -174,6 +174,8 @@ struct MsmAccumK {
         while (off[b + 1] <= cur) b++;
         bend = off[b + 1];
       }
+      // (an L2 prefetch of the next entry's base was measured slightly slower: 79.8 vs 78.8 ms at 2^24 --
+      // the other resident warps already cover the gather latency)
       xyzz_madd(acc, msm_load_point(tab, ent[cur]));
     }
     flush(b, acc, head_open, bend <= end, head, tail, buckets, slot_pt, slot_bid, slot_fl);
@@ -527,13 +529,19 @@ inline int msm_pick_window(size_t n) {
   return best;
 }
 
-// window for bases that carry all W tables (one shared bucket set): fewer, larger windows pay off
-inline int msm_pick_window_full(size_t n) {
+// window for bases that carry all W tables (one shared bucket set): fewer, larger windows pay off.
+// Cost in field products: 10 per mixed addition; `bucket_cost` per bucket for everything that scales
+// with the bucket count (boundary-partial merge + reduction).  By operation count a bucket costs 38
+// (2 full additions + share of the merge), but those kernels run at a lower fraction of the multiplier
+// peak than the accumulate kernel: measured on B200 at 2^20 points, c = 20, a bucket costs about as
+// much time as 10 mixed additions in G1 and in G2 alike; a sweep of the window over 2^16..2^24 points
+// (profiles/r01s2_window_model.md) is matched best by PS_BUCKET_COST = 70 (context.cuh).
+inline int msm_pick_window_full(size_t n, double bucket_cost = PS_BUCKET_COST) {
   int best = 4; double best_cost = 1e300;
   for (int c = 4; c <= 24; c++) {
     double W = msm_windows(c);
     if ((double)n * W >= 2.0e9) continue;  // entry indices are 31 bits
-    double cost = (double)n * W * 10.0 + (double)(1u << (c - 1)) * (2.0 * 14.0 + 10.0);
+    double cost = (double)n * W * 10.0 + (double)(1u << (c - 1)) * bucket_cost;
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
@@ -580,15 +588,23 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   const size_t max_ent = (size_t)g.n * g.W;
   if (max_ent >= 0xFFFFFFFFull) return PS_ERR_UNSUPPORTED;
 
-  // entries per accumulate thread: keep >= ~8 waves of threads when the problem is large enough
-  // entries per accumulate thread: about one average bucket or more, so that a bucket spans at most
-  // two or three threads (few boundary partials, short merge runs); twice that when the input is
-  // large enough to keep > 400K threads; never so long that fewer than ~24K threads remain.
+  // entries per accumulate thread.  Target L0: about one average bucket or more, so that a bucket spans
+  // at most two or three threads (few boundary partials, short merge runs); twice that when the input
+  // is large enough to keep > 400K threads.  Then whole WAVES: the kernel keeps R = SMs x blocks/SM x 128
+  // threads resident and every thread runs the same L iterations, so a grid of 1.1 R threads costs as
+  // much as one of 2 R (measured: 2^20 points at c = 17 took 9.3 ms in 61K threads of 256 entries,
+  // 1.08 waves).  w = number of waves at about L0 entries per thread; L is then set so that the grid
+  // fills exactly w waves.
   const size_t avg_bucket = max_ent / nb + 1;
-  uint32_t L = 8;
-  while (L < 512 && L < avg_bucket) L <<= 1;
-  if (L < 512 && max_ent / (2 * (size_t)L) >= 400000) L <<= 1;
-  while (L > 8 && max_ent / L < 24576) L >>= 1;
+  uint32_t L0 = 8;
+  while (L0 < 512 && L0 < avg_bucket) L0 <<= 1;
+  if (L0 < 512 && max_ent / (2 * (size_t)L0) >= 400000) L0 <<= 1;
+  const size_t R = (size_t)ctx->sm_count * MsmAccumK<F>::MIN_BLOCKS * MsmAccumK<F>::BLOCK;
+  const size_t waves = (max_ent + R * L0 - 1) / (R * L0);
+  // with many waves the last, partly filled one costs little and L0 itself is kept (more, shorter chunks
+  // only add boundary partials: measured +0.2 ms of merge at 2^20, c = 20, for no gain in the accumulation)
+  uint32_t L = waves >= 6 ? L0 : (uint32_t)((max_ent + waves * R - 1) / (waves * R));
+  if (L < 8) L = 8;
   const size_t T1 = (max_ent + L - 1) / L;
   const uint32_t CF = 64;  // slots merged per combine thread (most are empty after the pair merge)
   const bool team = ctx->msm_team != 0;

@@ -14,7 +14,7 @@ n = 1 << k
 be = ps.Backend(0)
 sq, wit = H.sparse_circuit(n, 7, n // 2)
 tr, tw = H.sparse_groth16_setup(be, sq, 7)
-wb = b"".join(v.to_bytes(32, "big") for v in wit)
+wb = ps.HostBuffer(be, b"".join(v.to_bytes(32, "big") for v in wit))
 smp = O.Sampler(99)
 r, s = smp.fr(), smp.fr()
 sq._resident(be); tr._resident(be); be.sync()
