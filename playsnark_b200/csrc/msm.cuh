@@ -143,9 +143,12 @@ PS_DEV Affine<F> msm_load_point(const Affine<F>* tab, uint32_t e) {
 #ifndef PS_G2_MINB
 #define PS_G2_MINB 2
 #endif
+#ifndef PS_ACC_BLOCK
+#define PS_ACC_BLOCK 128
+#endif
 template <class F>
 struct MsmAccumK {
-  static constexpr int BLOCK = 128;
+  static constexpr int BLOCK = PS_ACC_BLOCK;
   // registers: G1 fits 3 resident blocks per SM without spilling; G2 (Fp2) is register-bound
   static constexpr int MIN_BLOCKS = sizeof(F) == sizeof(Fp) ? PS_G1_MINB : PS_G2_MINB;
   using Self = MsmAccumK<F>;
