@@ -50,6 +50,25 @@ def test_fp_ops(host_check):
         host_check.hc_fp_sqrt(limbs(sq, 12), out); assert unl(out) in (a, (O.P - a) % O.P)
 
 
+def test_dedicated_squaring(host_check):
+    """Fe::sqr (symmetric products once + separate Montgomery reduction) against a*a mod p, on edge values
+    (carry-heavy limbs) and random ones, through the domain conversion and on raw limbs."""
+    rng = random.Random(7)
+    out12, out8 = (U32 * 12)(), (U32 * 8)()
+    heavy_p = [O.P - 1, O.P - 2, (1 << 380) - 1, (1 << 381) - 1 - ((1 << 381) - 1 >= O.P) * (1 << 380), int("f" * 95, 16) % O.P,
+               sum(0xFFFFFFFF << (64 * k) for k in range(6)) % O.P, sum(0xFFFFFFFF << (64 * k + 32) for k in range(6)) % O.P]
+    rinv = pow(1 << 384, -1, O.P)
+    for a in fp_vals(rng, 300) + heavy_p:
+        host_check.hc_fp_sqr(limbs(a, 12), out12); assert unl(out12) == a * a % O.P, hex(a)
+        host_check.hc_fp_montsqr_raw(limbs(a, 12), out12); assert unl(out12) == a * a * rinv % O.P, hex(a)
+    heavy_r = [O.R - 1, O.R - 2, (1 << 254) - 1, (1 << 255) - 1 - O.R if (1 << 255) - 1 >= O.R else (1 << 255) - 1 - (1 << 254),
+               sum(0xFFFFFFFF << (64 * k) for k in range(4)) % O.R, sum(0xFFFFFFFF << (64 * k + 32) for k in range(4)) % O.R]
+    rinv = pow(1 << 256, -1, O.R)
+    for a in fr_vals(rng, 300) + heavy_r:
+        host_check.hc_fr_sqr(limbs(a, 8), out8); assert unl(out8) == a * a % O.R, hex(a)
+        host_check.hc_fr_montsqr_raw(limbs(a, 8), out8); assert unl(out8) == a * a * rinv % O.R, hex(a)
+
+
 def test_fr_ops(host_check):
     rng = random.Random(2)
     vals = fr_vals(rng, 40)
