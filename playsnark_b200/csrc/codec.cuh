@@ -231,7 +231,7 @@ template <class F>
 struct XyzzEncodeK {
   static constexpr int BLOCK = 32;
   PS_DEV static void run(uint32_t i, const XYZZ<F>* in, int format, uint8_t* out) {
-    Affine<F> a = xyzz_to_affine_c(in[i]);
+    Affine<F> a = xyzz_to_affine_serial(in[i]);
     point_encode(a, format, out + (size_t)i * (format == PS_FMT_COMPRESSED ? PointBytes<F>::COMP : PointBytes<F>::AFF));
   }
 };

@@ -50,11 +50,24 @@ PS_DEV Fp2 fp2_inv(const Fp2& a) {
   return Fp2{fe_mul_call(a.c0, d), fe_mul_call(a.c1, d).neg()};
 }
 
+// the same with the binary-algorithm base-field inversion (one-thread tails, field.cuh)
+PS_DEV Fp2 fp2_inv_serial(const Fp2& a) {
+  Fp d = fp_inv_serial(fe_mul_call(a.c0, a.c0) + fe_mul_call(a.c1, a.c1));
+  return Fp2{fe_mul_call(a.c0, d), fe_mul_call(a.c1, d).neg()};
+}
+
 template <class F> struct FieldInv;
-template <> struct FieldInv<Fp> { PS_DEV static Fp inv(const Fp& a) { return fp_inv(a); } };
-template <> struct FieldInv<Fp2> { PS_DEV static Fp2 inv(const Fp2& a) { return fp2_inv(a); } };
+template <> struct FieldInv<Fp> {
+  PS_DEV static Fp inv(const Fp& a) { return fp_inv(a); }
+  PS_DEV static Fp inv_serial(const Fp& a) { return fp_inv_serial(a); }
+};
+template <> struct FieldInv<Fp2> {
+  PS_DEV static Fp2 inv(const Fp2& a) { return fp2_inv(a); }
+  PS_DEV static Fp2 inv_serial(const Fp2& a) { return fp2_inv_serial(a); }
+};
 template <> struct FieldInv<Fp2I> {
   PS_DEV static Fp2I inv(const Fp2I& a) { Fp2 r = fp2_inv(Fp2{a.c0, a.c1}); return Fp2I{r.c0, r.c1}; }
+  PS_DEV static Fp2I inv_serial(const Fp2I& a) { Fp2 r = fp2_inv_serial(Fp2{a.c0, a.c1}); return Fp2I{r.c0, r.c1}; }
 };
 
 // ---- points --------------------------------------------------------------------------------------
@@ -196,6 +209,15 @@ PS_DEV XYZZ<F> xyzz_scalar_mul(const XYZZ<F>& p, const uint32_t* k, int nlimbs) 
 }
 
 template <class F> PS_NOINLINE Affine<F> xyzz_to_affine_c(const XYZZ<F>& p) { return xyzz_to_affine(p); }
+// for the handful of result points a call ends with (one thread each): binary-algorithm inversion
+template <class F>
+PS_NOINLINE Affine<F> xyzz_to_affine_serial(const XYZZ<F>& p) {
+  if (p.is_inf()) return Affine<F>::inf();
+  F zzz_inv = FieldInv<F>::inv_serial(p.zzz);
+  F t = zzz_inv * p.zz;
+  F zz_inv = t.sqr();
+  return Affine<F>{p.x * zz_inv, p.y * zzz_inv};
+}
 
 using G1Affine = Affine<Fp>;
 using G2Affine = Affine<Fp2>;

@@ -18,6 +18,14 @@ void hc_fp_mul(const uint32_t* a, const uint32_t* b, uint32_t* o) { store_std(o,
 void hc_fp_add(const uint32_t* a, const uint32_t* b, uint32_t* o) { store_std(o, load_std<Fp>(a) + load_std<Fp>(b)); }
 void hc_fp_sub(const uint32_t* a, const uint32_t* b, uint32_t* o) { store_std(o, load_std<Fp>(a) - load_std<Fp>(b)); }
 void hc_fp_inv(const uint32_t* a, uint32_t* o) { store_std(o, fp_inv(load_std<Fp>(a))); }
+void hc_fp_inv_serial(const uint32_t* a, uint32_t* o) { store_std(o, fp_inv_serial(load_std<Fp>(a))); }
+void hc_fr_inv_serial(const uint32_t* a, uint32_t* o) { store_std(o, fr_inv_serial(load_std<Fr>(a))); }
+void hc_g2_to_affine_serial(const uint32_t* p, int pre, uint32_t* o) {
+  G2XYZZ a = G2XYZZ::from_affine(load_g2(p));
+  for (int i = 0; i < pre; i++) a = xyzz_dbl(a);
+  G2Affine s = xyzz_to_affine_serial(a), f = xyzz_to_affine(a);
+  store_g2(o, s); store_g2(o + 48, f);
+}
 void hc_fp_sqrt(const uint32_t* a, uint32_t* o) { store_std(o, fp_sqrt_candidate(load_std<Fp>(a))); }
 void hc_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* o) { store_std(o, load_std<Fr>(a) * load_std<Fr>(b)); }
 void hc_fr_add(const uint32_t* a, const uint32_t* b, uint32_t* o) { store_std(o, load_std<Fr>(a) + load_std<Fr>(b)); }

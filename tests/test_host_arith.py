@@ -50,6 +50,36 @@ def test_fp_ops(host_check):
         host_check.hc_fp_sqrt(limbs(sq, 12), out); assert unl(out) in (a, (O.P - a) % O.P)
 
 
+def test_inversion_binary_gcd_vs_fermat(host_check):
+    """fp_inv_serial / fr_inv_serial (binary extended Euclid) against a^-1 mod p and against the Fermat route, edge values
+    included (1, p-1, powers of two, values whose Montgomery form is small)."""
+    rng = random.Random(9)
+    out, out2 = (U32 * 12)(), (U32 * 12)()
+    rinv = pow(1 << 384, -1, O.P)
+    vals = fp_vals(rng, 120) + [rinv, 2 * rinv % O.P, (O.P - rinv) % O.P, 1 << 200, (1 << 381) % O.P, O.P - 1]
+    for a in vals:
+        host_check.hc_fp_inv_serial(limbs(a, 12), out)
+        host_check.hc_fp_inv(limbs(a, 12), out2)
+        assert unl(out) == unl(out2) == (pow(a, -1, O.P) if a else 0), hex(a)
+    out, out2 = (U32 * 8)(), (U32 * 8)()
+    rinv = pow(1 << 256, -1, O.R)
+    vals = fr_vals(rng, 120) + [rinv, 2 * rinv % O.R, (O.R - rinv) % O.R, 1 << 200, O.R - 1]
+    for a in vals:
+        host_check.hc_fr_inv_serial(limbs(a, 8), out)
+        host_check.hc_fr_inv(limbs(a, 8), out2)
+        assert unl(out) == unl(out2) == (pow(a, -1, O.R) if a else 0), hex(a)
+
+
+def test_to_affine_serial_matches(host_check):
+    rng = random.Random(4)
+    out = (U32 * 96)()
+    for pre in (0, 1, 3):
+        p = O.pt_mul(O.F2, rng.randrange(1, O.R), O.G2_GEN)
+        arr = (U32 * 48)(*(list(limbs(p[0][0], 12)) + list(limbs(p[0][1], 12)) + list(limbs(p[1][0], 12)) + list(limbs(p[1][1], 12))))
+        host_check.hc_g2_to_affine_serial(arr, pre, out)
+        assert list(out[:48]) == list(out[48:])
+
+
 def test_dedicated_squaring(host_check):
     """Fe::sqr (symmetric products once + separate Montgomery reduction) against a*a mod p, on edge values
     (carry-heavy limbs) and random ones, through the domain conversion and on raw limbs."""
