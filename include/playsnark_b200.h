@@ -181,6 +181,13 @@ int ps_g16_scalars_from_ab(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap
  *  - ps_g16_h_from_ab: h = floor(a b / z), n - 1 standard-form values (to be broadcast into C's vector). */
 int ps_qap_interp_part(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_be, int which, size_t part,
                        size_t parts, void* d_out_evals, void* d_w_nio_out, void* d_status);
+/* the same with the witness already on the device (n_vars Montgomery values), e.g. after every rank has
+ * uploaded one slice with ps_fr_upload (host wire format -> Montgomery limbs in device memory, encoding
+ * errors into the status word) and the slices have been all-gathered over NVLink: one upload of the
+ * witness per node instead of one per GPU */
+int ps_qap_interp_part_dev(ps_ctx* ctx, const ps_qap* qap, const void* d_witness_mont, int which, size_t part,
+                           size_t parts, void* d_out_evals, void* d_w_nio_out, void* d_status);
+int ps_fr_upload(ps_ctx* ctx, const uint8_t* values_be, size_t count, void* d_out_mont, void* d_status);
 int ps_qap_interp_finish(ps_ctx* ctx, const ps_qap* qap, size_t parts, const void* d_evals_all, void* d_out_coef);
 int ps_g16_scalars_ab(ps_ctx* ctx, const ps_g16_key* key, const uint8_t* r_be, const uint8_t* s_be, const void* d_a,
                       const void* d_b, void* d_scA, void* d_scB, void* d_scC_tail);

@@ -54,6 +54,8 @@ SYMBOLS = [
     ("ps_qap_aggregate_one", _I, [_P, _P, _P, _I, _P]),
     ("ps_g16_scalars_from_ab", _I, [_P, _P, _P, _P, _B, _B, _P, _P, _P, _P, _P]),
     ("ps_qap_interp_part", _I, [_P, _P, _P, _I, _SZ, _SZ, _P, _P, _P]),
+    ("ps_qap_interp_part_dev", _I, [_P, _P, _P, _I, _SZ, _SZ, _P, _P, _P]),
+    ("ps_fr_upload", _I, [_P, _P, _SZ, _P, _P]),
     ("ps_qap_interp_finish", _I, [_P, _P, _SZ, _P, _P]),
     ("ps_g16_scalars_ab", _I, [_P, _P, _B, _B, _P, _P, _P, _P, _P]),
     ("ps_g16_h_from_ab", _I, [_P, _P, _P, _P, _P]),

@@ -1046,19 +1046,14 @@ void ps_host_free(void* p) {
 #endif
 }
 
-int ps_qap_interp_part(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_be, int which, size_t part, size_t parts,
-                       void* d_out_evals, void* d_w_nio_out, void* d_status) {
-  if (!ctx || !qap || !witness_be || !d_out_evals || !d_status || which < 0 || which > 1) return PS_ERR_ARG;
-  if (qap->dense) return PS_ERR_UNSUPPORTED;
-  const int lp = log2_exact(parts);
-  if (lp < 0 || parts > qap->n / 2 || part >= parts) return PS_ERR_ARG;
-  PS_TRY(begin_call(ctx));
+namespace {
+// body of ps_qap_interp_part once the witness is on the device (Montgomery form); d_err may be null
+int interp_part_run(ps_ctx* ctx, const ps_qap* qap, const Fr* d_w, const uint32_t* d_err, int which, size_t part, size_t parts,
+                    int lp, void* d_out_evals, void* d_w_nio_out, void* d_status) {
   const SparseQap* sq = (const SparseQap*)qap->sparse;
   const uint32_t n = (uint32_t)qap->n, ns = (uint32_t)(qap->n / parts), lo = (uint32_t)part * ns;
   ps_stream_t st = ctx->stream;
-  uint32_t *d_w = nullptr, *d_err = nullptr;
-  PS_TRY(stage_scalars(ctx, witness_be, qap->m, 1, &d_w, &d_err));
-  if (d_w_nio_out) PS_LAUNCH(FrStdCopyK, st, qap->n_io, (const Fr*)d_w + (qap->m - qap->n_io), (Fr*)d_w_nio_out);
+  if (d_w_nio_out) PS_LAUNCH(FrStdCopyK, st, qap->n_io, d_w + (qap->m - qap->n_io), (Fr*)d_w_nio_out);
   Fr* ev = ctx->arena.take<Fr>((size_t)3 * ns);
   Fr* E0 = ctx->arena.take<Fr>((size_t)2 * ns);
   uint32_t* flag = ctx->arena.take<uint32_t>(1);
@@ -1066,13 +1061,50 @@ int ps_qap_interp_part(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_be
   PS_TRY(dev_memset(flag, 0, 4, st));
   PS_LAUNCH(SpmvK, st, (size_t)3 * ns, ns, lo, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
             (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
-            (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, (const Fr*)d_w, ev);
+            (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, d_w, ev);
   PS_LAUNCH(GateCheckK, st, ns, ns, (const Fr*)ev, flag);   // this rank's gates; every gate is checked by some rank
   PS_LAUNCH(InterpLeafK, st, ns, ns, (const Fr*)(ev + (size_t)which * ns), (const Fr*)(sq->inv_zprime + lo), E0);
   // parts == 1: the whole tree, d_out_evals receives the n coefficients
   PS_TRY(interpolate_levels(ctx, sq, n, qap->log_np, 1, lo, ns, 0, qap->log_np - lp, E0, lp ? (Fr*)d_out_evals : (Fr*)nullptr,
                             lp ? (Fr*)nullptr : (Fr*)d_out_evals));
-  PS_LAUNCH(StatusMergeK, st, 1, (const uint32_t*)d_err, (const uint32_t*)flag, (uint32_t*)d_status);
+  PS_LAUNCH(StatusMergeK, st, 1, d_err, (const uint32_t*)flag, (uint32_t*)d_status);
+  return PS_OK;
+}
+}  // namespace
+
+int ps_qap_interp_part(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_be, int which, size_t part, size_t parts,
+                       void* d_out_evals, void* d_w_nio_out, void* d_status) {
+  if (!ctx || !qap || !witness_be || !d_out_evals || !d_status || which < 0 || which > 1) return PS_ERR_ARG;
+  if (qap->dense) return PS_ERR_UNSUPPORTED;
+  const int lp = log2_exact(parts);
+  if (lp < 0 || parts > qap->n / 2 || part >= parts) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  uint32_t *d_w = nullptr, *d_err = nullptr;
+  PS_TRY(stage_scalars(ctx, witness_be, qap->m, 1, &d_w, &d_err));
+  return interp_part_run(ctx, qap, (const Fr*)d_w, d_err, which, part, parts, lp, d_out_evals, d_w_nio_out, d_status);
+}
+
+int ps_qap_interp_part_dev(ps_ctx* ctx, const ps_qap* qap, const void* d_witness_mont, int which, size_t part, size_t parts,
+                           void* d_out_evals, void* d_w_nio_out, void* d_status) {
+  if (!ctx || !qap || !d_witness_mont || !d_out_evals || !d_status || which < 0 || which > 1) return PS_ERR_ARG;
+  if (qap->dense) return PS_ERR_UNSUPPORTED;
+  const int lp = log2_exact(parts);
+  if (lp < 0 || parts > qap->n / 2 || part >= parts) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  return interp_part_run(ctx, qap, (const Fr*)d_witness_mont, (const uint32_t*)nullptr, which, part, parts, lp, d_out_evals,
+                         d_w_nio_out, d_status);
+}
+
+int ps_fr_upload(ps_ctx* ctx, const uint8_t* values_be, size_t count, void* d_out_mont, void* d_status) {
+  if (!ctx || (count && (!values_be || !d_out_mont)) || !d_status) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  uint8_t* d_in = ctx->arena.take<uint8_t>(count * 32);
+  uint32_t* d_err = ctx->arena.take<uint32_t>(1);
+  if (!d_in || !d_err) return PS_ERR_ALLOC;
+  PS_TRY(dev_memset(d_err, 0, 4, ctx->stream));
+  if (count) PS_TRY(dev_h2d(d_in, values_be, count * 32, ctx->stream));
+  PS_LAUNCH(FrFromBytesK, ctx->stream, count, (const uint8_t*)d_in, (uint32_t*)d_out_mont, 1, d_err);
+  PS_LAUNCH(StatusMergeK, ctx->stream, 1, (const uint32_t*)d_err, (const uint32_t*)nullptr, (uint32_t*)d_status);
   return PS_OK;
 }
 

@@ -79,7 +79,8 @@ def _raise_status(st: int):
         raise L.PlaysnarkError(L.PS_ERR_ENCODING, "bad scalar or point encoding")
 
 
-def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_share: float, trace=None):
+def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_share: float, trace=None,
+                       gather_witness: bool = True):
     """world = 2 * parts ranks.  Ranks [0, parts) fold polynomial a, ranks [parts, 2 parts) polynomial b:
     each one the subtree over its n/parts gates (ps_qap_interp_part); an all-gather hands the subtree
     roots to the two leaders, which run the top levels (ps_qap_interp_finish) and broadcast a and b.
@@ -88,7 +89,7 @@ def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_s
     shard [NioLP | XiT] follows.  One all-gather of the partial points (and of the device status words)
     ends the proof; no host synchronisation in between."""
     import torch
-    from .api import _fr_bytes
+    from .api import _fr_bytes, HostBuffer
     lib = be.lib
     world, rank = dist.get_world_size(), dist.get_rank()
     parts = world // 2
@@ -109,10 +110,28 @@ def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_s
     new = lambda rows: torch.zeros((rows, 8), dtype=torch.int32, device=device)
     bufA, bufC, bufB = new(nA), new(nC), new(nB)
     status = torch.zeros(1, dtype=torch.int32, device=device)
-    wb, rb, sb = _fr_bytes(witness), _fr_bytes([r]), _fr_bytes([s])
+    rb, sb = _fr_bytes([r]), _fr_bytes([s])
     e_rows = 2 * n // parts if parts > 1 else n
     e_part = new(e_rows)
-    be._check(lib.ps_qap_interp_part(be.ctx, qh, wb, g, part, parts, ptr(e_part), ptr(bufC) if nio else None, ptr(status)))
+    m = q.nbVars
+    if gather_witness:
+        # every rank uploads 1/world of the witness; the slices travel over NVLink (one upload per node)
+        chunk = (m + world - 1) // world
+        wfull = new(world * chunk)
+        lo, hi = min(m, rank * chunk), min(m, (rank + 1) * chunk)
+        if isinstance(witness, HostBuffer):
+            src = C.c_void_p(witness.ptr.value + 32 * lo)
+        else:
+            src = _fr_bytes(witness)[32 * lo:32 * hi]
+        mine = wfull[rank * chunk:(rank + 1) * chunk]
+        be._check(lib.ps_fr_upload(be.ctx, src, hi - lo, ptr(mine), ptr(status)))
+        dist.all_gather(list(wfull.view(world, chunk, 8).unbind(0)), mine.clone())
+        mark("witness")
+        be._check(lib.ps_qap_interp_part_dev(be.ctx, qh, ptr(wfull), g, part, parts, ptr(e_part), ptr(bufC) if nio else None,
+                                             ptr(status)))
+    else:
+        be._check(lib.ps_qap_interp_part(be.ctx, qh, _fr_bytes(witness), g, part, parts, ptr(e_part), ptr(bufC) if nio else None,
+                                         ptr(status)))
     mark("interp_part")
     if parts > 1:
         e_all = [new(e_rows) for _ in range(world)]
@@ -177,7 +196,7 @@ def load_key_sharded(be, tr, world: int):
 
 
 def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device="cpu", split_quotient: bool = True,
-                          rank0_share: float = 0.5, trace=None):
+                          rank0_share: float = 0.5, trace=None, gather_witness: bool = True):
     """Groth16Prove (groth16.go:122-211) over the ranks of `dist`.  Every rank holds the proving key.
     With a sparse QAP and an even, power-of-two-halved world the whole proof is pipelined across the
     ranks (_groth16_pipelined: every rank holds the QAP and reads `witness`).  Otherwise the quotient
@@ -192,7 +211,7 @@ def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device=
     parts = world // 2
     if (split_quotient and world >= 2 and world % 2 == 0 and parts & (parts - 1) == 0 and type(q).__name__ == "SparseQAP"
             and parts <= q.nbGates // 2):
-        return _groth16_pipelined(be, tr, q, witness, r, s, dist, device, rank0_share, trace)
+        return _groth16_pipelined(be, tr, q, witness, r, s, dist, device, rank0_share, trace, gather_witness)
     kh = load_key_sharded(be, tr, world)
     counts = [int(lib.ps_g16_scalar_count(kh, w)) for w in (0, 1, 2)]
     groups = [L.PS_G1, L.PS_G1, L.PS_G2]

@@ -357,6 +357,18 @@ def sharded_steps_recombine(be, log_n, parts, fake_world, seed, device="cpu"):
         be.sync()
         assert torch.equal(got, want), ("coefficients", which)
         coef.append(got)
+    # witness uploaded in two slices (ps_fr_upload) and used from device memory: same subtree root
+    m = sq.nbVars
+    wdev = new(m)
+    half = m // 2
+    be._check(lib.ps_fr_upload(be.ctx, wb[:32 * half], half, ptr(wdev), ptr(status)))
+    be._check(lib.ps_fr_upload(be.ctx, wb[32 * half:], m - half, ptr(wdev[half:]), ptr(status)))
+    rows = 2 * n // parts if parts > 1 else n
+    via_host, via_dev, nio_dev = new(rows), new(rows), new(max(1, nio))
+    be._check(lib.ps_qap_interp_part(be.ctx, qh, wb, 1, parts - 1, parts, ptr(via_host), None, ptr(status)))
+    be._check(lib.ps_qap_interp_part_dev(be.ctx, qh, ptr(wdev), 1, parts - 1, parts, ptr(via_dev), ptr(nio_dev), ptr(status)))
+    be.sync()
+    assert torch.equal(via_host, via_dev) and torch.equal(nio_dev[:nio], bufC[:nio])
     be._check(lib.ps_g16_scalars_ab(be.ctx, kh, rb, sb, ptr(coef[0]), ptr(coef[1]), ptr(bufA), ptr(bufB), ptr(bufC[head:])))
     be._check(lib.ps_g16_h_from_ab(be.ctx, qh, ptr(coef[0]), ptr(coef[1]), ptr(bufC[nio:head])))
     be.sync()
@@ -393,10 +405,16 @@ def sharded_steps_recombine(be, log_n, parts, fake_world, seed, device="cpu"):
     for part in range(parts):
         st2.zero_()
         rows = 2 * n // parts if parts > 1 else n
-        be._check(lib.ps_qap_interp_part(be.ctx, qh, api._fr_bytes(bad), 0, part, parts, ptr(new(rows)), None, ptr(st2)))
+        sink = new(rows)                                       # kept alive across the call
+        be._check(lib.ps_qap_interp_part(be.ctx, qh, api._fr_bytes(bad), 0, part, parts, ptr(sink), None, ptr(st2)))
         be.sync()
         hit += int(st2[0]) & 2
     assert hit >= 2
+    st3 = torch.zeros(1, dtype=torch.int32, device=device)     # a non-canonical scalar sets the encoding bit
+    sink = new(1)
+    be._check(lib.ps_fr_upload(be.ctx, b"\xff" * 32, 1, ptr(sink), ptr(st3)))
+    be.sync()
+    assert int(st3[0]) & 1
 
 
 def config_c2(be, n=1 << 10, timings=None):
