@@ -196,7 +196,7 @@ def load_key_sharded(be, tr, world: int):
 
 
 def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device="cpu", split_quotient: bool = True,
-                          rank0_share: float = 0.5, trace=None, gather_witness: bool = True):
+                          rank0_share: float = 0.4, trace=None, gather_witness: bool = True):
     """Groth16Prove (groth16.go:122-211) over the ranks of `dist`.  Every rank holds the proving key.
     With a sparse QAP and an even, power-of-two-halved world the whole proof is pipelined across the
     ranks (_groth16_pipelined: every rank holds the QAP and reads `witness`).  Otherwise the quotient
