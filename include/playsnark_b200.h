@@ -60,7 +60,9 @@ int ps_ctx_set_stream(ps_ctx* ctx, void* cuda_stream);
  * "msm_shards" = N >= 1: base sets and keys loaded afterwards are meant to be summed in N index ranges
  * (one per GPU, ps_msm_device / ps_g16_msm_partials), so their automatic window is sized for n / N points;
  * "msm_bucket_cost" = cost of one bucket (merge + reduction) in the automatic window choice, in field
- * products with a mixed addition counting 10 (default 70, fitted on B200) */
+ * products with a mixed addition counting 10 (default 70, fitted on B200);
+ * "msm_scatter" = 0 (one-pass scatter of the counting sort) | 1 (two passes through a partitioned staging
+ * array when the entry array exceeds L2) | 2 (two passes whenever the window count allows; tests) */
 int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value);
 int ps_ctx_sync(ps_ctx* ctx);
 void ps_ctx_destroy(ps_ctx* ctx);

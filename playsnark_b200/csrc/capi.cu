@@ -450,6 +450,11 @@ int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value) {
     ctx->msm_bucket_cost = value;
     return PS_OK;
   }
+  if (!strcmp(name, "msm_scatter")) {
+    if (value < 0 || value > 2) return PS_ERR_ARG;
+    ctx->msm_scatter = value;
+    return PS_OK;
+  }
   if (!strcmp(name, "msm_team")) {
     if (value != 0 && value != 1) return PS_ERR_ARG;
     ctx->msm_team = value;

@@ -8,6 +8,10 @@
 #define PS_BUCKET_COST 70   // see msm_pick_window_full (msm.cuh)
 #endif
 
+#ifndef PS_SCATTER_DEFAULT
+#define PS_SCATTER_DEFAULT 1
+#endif
+
 struct ps_ctx {
   int device = 0;
   ps::ps_stream_t stream = nullptr;
@@ -34,6 +38,9 @@ struct ps_ctx {
   int msm_team = 1;
   // base sets loaded from now on are meant to be summed in this many index ranges (sharded proofs)
   int msm_shards = 1;
+  // counting-sort scatter: 0 = one pass, 1 = two passes through a partitioned staging array when the
+  // entry array exceeds L2 (msm.cuh), 2 = two passes whenever possible (tests)
+  int msm_scatter = PS_SCATTER_DEFAULT;
   // window model: time of one bucket (merge + reduction) in field products, a mixed addition being 10
   int msm_bucket_cost = PS_BUCKET_COST;
   // small page-locked staging area for results: a device-to-host copy into pageable memory would block

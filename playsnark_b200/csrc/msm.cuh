@@ -517,6 +517,105 @@ inline int exclusive_scan_u32(ps_stream_t st, const uint32_t* in, uint32_t* out,
   return PS_OK;
 }
 
+// ---- two-pass scatter for large inputs -----------------------------------------------------------------
+// The counting sort's scatter writes n*W 4-byte entries to positions that are uniformly random over an
+// array far larger than L2 (805 MB at 2^24 points): every store costs a DRAM read-modify-write of its
+// sector (6.5 of the 93 ms of that MSM).  Two passes instead:
+//   1. k_scatter_stage (block-cooperative): a block of 512 scalars computes its (position, entry) pairs,
+//      bins them by the high bits of the POSITION (partitions of 2^shift consecutive positions, 4 MB of
+//      the final array) with a shared-memory histogram, reserves one contiguous run per partition in the
+//      staging array with one global atomic per (block, partition), and writes its pairs there: runs of
+//      ~32 pairs (256 B) instead of single words.  Partition p of the staging array is exactly as large as
+//      the partition itself (positions are a permutation), so no counting pass is needed.
+//   2. MsmStageScatterK: reads the staging array in order (coalesced) and stores each entry at its final
+//      position -- random, but inside the 4 MB window the neighbouring threads are working on, i.e. in L2.
+struct MsmStageScatterK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t j, int shift, const uint32_t* part_count, const uint32_t* staging, uint32_t* ent) {
+    const uint32_t part = j >> shift, k = j & ((1u << shift) - 1);
+    if (k >= part_count[part]) return;
+    const uint32_t pos = staging[2 * (size_t)j], val = staging[2 * (size_t)j + 1];
+    ent[pos] = val;
+  }
+};
+constexpr int SCATTER2_WMAX = 16;
+#ifndef PS_SCATTER2_BLOCK
+#define PS_SCATTER2_BLOCK 512
+#endif
+constexpr int SCATTER2_BLOCK = PS_SCATTER2_BLOCK;  // scalars per block: longer runs per partition, fewer global atomics
+#if PS_GPU
+static __global__ void __launch_bounds__(SCATTER2_BLOCK) k_scatter_stage(MsmGeom g, const uint32_t* scalars, int mont, const uint32_t* off,
+                                                             const uint32_t* ranks, uint32_t* part_count, uint32_t* staging,
+                                                             int shift, uint32_t nparts) {
+  extern __shared__ uint32_t sh_scatter[];
+  uint32_t* hist = sh_scatter;
+  uint32_t* base = sh_scatter + nparts;
+  for (uint32_t p = threadIdx.x; p < nparts; p += blockDim.x) hist[p] = 0;
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t pos[SCATTER2_WMAX], val[SCATTER2_WMAX], lr[SCATTER2_WMAX];
+#pragma unroll
+  for (int w = 0; w < SCATTER2_WMAX; w++) pos[w] = 0xFFFFFFFFu;
+  if (i < g.n) {
+    uint32_t k[8]; bool neg;
+    msm_load_scalar(scalars, i, mont, k, neg);
+    uint32_t carry = 0;
+#pragma unroll
+    for (int w = 0; w < SCATTER2_WMAX; w++) {
+      if (w < g.W) {
+        uint32_t mag; bool dneg;
+        if (msm_next_digit(k, g.c, carry, mag, dneg)) {
+          const uint32_t b = (uint32_t)(w / g.T) * g.D + (mag - 1);
+          pos[w] = off[b] + ranks[(size_t)w * g.n + i];
+          val[w] = ((uint32_t)(w % g.T) * g.nbase + g.first + i) | ((neg != dneg) ? 0x80000000u : 0u);
+          lr[w] = atomicAdd(&hist[pos[w] >> shift], 1u);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t p = threadIdx.x; p < nparts; p += blockDim.x)
+    if (hist[p]) base[p] = atomicAdd(&part_count[p], hist[p]);
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < SCATTER2_WMAX; w++) {
+    if (pos[w] != 0xFFFFFFFFu) {
+      const uint32_t part = pos[w] >> shift;
+      const size_t slot = ((size_t)part << shift) + base[part] + lr[w];
+      reinterpret_cast<uint2*>(staging)[slot] = make_uint2(pos[w], val[w]);
+    }
+  }
+}
+#endif
+// pass 1 on the stream; part_count (nparts words) must be zero; staging holds 2 words per position
+inline int scatter_stage(ps_stream_t st, MsmGeom g, const uint32_t* scalars, int mont, const uint32_t* off, const uint32_t* ranks,
+                         uint32_t* part_count, uint32_t* staging, int shift, uint32_t nparts) {
+#if PS_GPU
+  const uint32_t blocks = (g.n + SCATTER2_BLOCK - 1) / SCATTER2_BLOCK;
+  k_scatter_stage<<<blocks, SCATTER2_BLOCK, 2 * nparts * sizeof(uint32_t), st>>>(g, scalars, mont, off, ranks, part_count, staging, shift, nparts);
+  PS_CUDA_TRY(cudaGetLastError());
+  launch_counter()++;
+#else
+  (void)st; (void)nparts;
+  for (uint32_t i = 0; i < g.n; i++) {
+    uint32_t k[8]; bool neg;
+    msm_load_scalar(scalars, i, mont, k, neg);
+    uint32_t carry = 0;
+    for (int w = 0; w < g.W; w++) {
+      uint32_t mag; bool dneg;
+      if (!msm_next_digit(k, g.c, carry, mag, dneg)) continue;
+      const uint32_t b = (uint32_t)(w / g.T) * g.D + (mag - 1);
+      const uint32_t pos = off[b] + ranks[(size_t)w * g.n + i];
+      const uint32_t part = pos >> shift;
+      const size_t slot = ((size_t)part << shift) + part_count[part]++;
+      staging[2 * slot] = pos;
+      staging[2 * slot + 1] = ((uint32_t)(w % g.T) * g.nbase + g.first + i) | ((neg != dneg) ? 0x80000000u : 0u);
+    }
+  }
+#endif
+  return PS_OK;
+}
+
 // ---- planning ------------------------------------------------------------------------------------------
 inline int msm_windows(int c) { return (255 + c - 1) / c; }
 
@@ -626,7 +725,22 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   PS_TRY(dev_memset(buckets, 0, (size_t)nb * sizeof(XYZZ<F>), st));
   PS_LAUNCH(MsmCountK, st, g.n, g, d_scalars, mont, count, ranks);
   PS_TRY(exclusive_scan_u32(st, count, off, tile_sums, nb + 1));
-  PS_LAUNCH(MsmScatterK, st, g.n, g, d_scalars, mont, (const uint32_t*)off, (const uint32_t*)ranks, ent);
+  // scatter: one pass while the entry array fits in L2, two passes through a partitioned staging array above
+  // (option msm_scatter: 0 = always one pass, 1 = automatic, 2 = two passes whenever W <= 16)
+  const bool two_pass = g.W <= SCATTER2_WMAX && (ctx->msm_scatter == 2 || (ctx->msm_scatter == 1 && max_ent >= ((size_t)1 << 27)));
+  if (two_pass) {
+    int shift = 20;
+    while ((max_ent >> shift) >= 1024) shift++;
+    const uint32_t nparts = (uint32_t)((max_ent + ((size_t)1 << shift) - 1) >> shift);
+    uint32_t* part_count = ar.take<uint32_t>(nparts);
+    uint32_t* staging = ar.take<uint32_t>(2 * ((size_t)nparts << shift));
+    if (!part_count || !staging) return PS_ERR_ALLOC;
+    PS_TRY(dev_memset(part_count, 0, (size_t)nparts * 4, st));
+    PS_TRY(scatter_stage(st, g, d_scalars, mont, off, ranks, part_count, staging, shift, nparts));
+    PS_LAUNCH(MsmStageScatterK, st, (size_t)nparts << shift, shift, (const uint32_t*)part_count, (const uint32_t*)staging, ent);
+  } else {
+    PS_LAUNCH(MsmScatterK, st, g.n, g, d_scalars, mont, (const uint32_t*)off, (const uint32_t*)ranks, ent);
+  }
   PS_TRY(ctx_event(ctx, 1));
   if (ctx->accum_mode == 1) {
     PS_TRY(msm_accumulate_affine<F>(ctx, nb, max_ent, tab, ent, off, buckets));

@@ -96,3 +96,14 @@ def test_sparse_phgr13_exponent_check(be): P.phgr13_sparse_exponent_check(be, 4,
 
 @pytest.mark.parametrize("parts,world", [(1, 2), (2, 3), (4, 5)])
 def test_sharded_steps_recombine(be, parts, world): P.sharded_steps_recombine(be, 4, parts, world, seed=21 + parts)
+
+
+@pytest.mark.parametrize("wb,tables,kind", [(16, 16, "rand"), (16, 1, "edge"), (20, -1, "rand"), (17, 3, "ones")])
+def test_msm_two_pass_scatter(be, wb, tables, kind):
+    """the partitioned two-pass scatter of the counting sort (forced on: option msm_scatter = 2)"""
+    be.set_option("msm_scatter", 2)
+    try:
+        P.msm_exponent_check(be, L.PS_G1, 300, kind, wb, tables)
+        P.msm_exponent_check(be, L.PS_G2, 40, kind, wb, tables)
+    finally:
+        be.set_option("msm_scatter", 1)

@@ -142,6 +142,17 @@ def test_sharded_steps_recombine(be, log_n, parts, world):
     P.sharded_steps_recombine(be, log_n, parts, world, seed=log_n, device="cuda")
 
 
+@pytest.mark.parametrize("n,wb,tables,kind", [(5000, 16, 16, "rand"), (1 << 16, 0, -1, "rand"), (1 << 18, 20, -1, "small"),
+                                              (3000, 17, 3, "ones"), (1 << 21, 0, -1, "rand")])
+def test_msm_two_pass_scatter(be, n, wb, tables, kind):
+    # block-cooperative staging pass + L2-resident fine scatter, forced on; same bytes as the one-pass sort
+    be.set_option("msm_scatter", 2)
+    try:
+        P.msm_exponent_check(be, L.PS_G1, n, kind, wb, tables)
+    finally:
+        be.set_option("msm_scatter", 1)
+
+
 def test_no_device_is_loud():
     lib = L.load()
     import ctypes as C
