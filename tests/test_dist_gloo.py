@@ -94,3 +94,17 @@ def test_sharded_groth16_four_ranks(tmp_path):
     """4 ranks: the interpolation of each aggregate polynomial is split over two subtrees
     (ps_qap_interp_part / ps_qap_interp_finish), uneven MSM shares, h broadcast into C's scalars."""
     _run(tmp_path, 4, 29534)
+
+
+def test_weighted_ranges_cover_exactly():
+    """MSM shares of the pipelined prover: contiguous, exhaustive, proportional, robust to tiny counts."""
+    from playsnark_b200 import dist as D
+    for count in (0, 1, 5, 1000, (1 << 20) + 2):
+        for world in (2, 4, 8):
+            w = [max(0.2, 1.0 - 0.075 * world)] + [1.0] * (world - 1)
+            r = D.weighted_ranges(count, w)
+            assert r[0][0] == 0 and r[-1][1] == count and len(r) == world
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:])) and all(lo <= hi for lo, hi in r)
+            if count >= 1000:
+                sizes = [hi - lo for lo, hi in r]
+                assert abs(sizes[0] / count - w[0] / sum(w)) < 0.01 and max(sizes[1:]) - min(sizes[1:]) <= 1
