@@ -107,7 +107,8 @@ def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_s
     nA, nC, nB = (int(lib.ps_g16_scalar_count(kh, w)) for w in (0, 1, 2))
     head = nio + n - 1                                   # [w_nio | h] ; tail = [s a + r b | s | r | r s]
     ptr = lambda t: C.c_void_p(t.data_ptr())
-    new = lambda rows: torch.zeros((rows, 8), dtype=torch.int32, device=device)
+    # every buffer below is completely written before it is read (no zero fill: ~0.4 GB of memsets per proof)
+    new = lambda rows: torch.empty((rows, 8), dtype=torch.int32, device=device)
     bufA, bufC, bufB = new(nA), new(nC), new(nB)
     status = torch.zeros(1, dtype=torch.int32, device=device)
     rb, sb = _fr_bytes([r]), _fr_bytes([s])
@@ -160,7 +161,7 @@ def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_s
 
     def partials(spans):
         # spans: (lo, hi) inside the base sets of A, C, B; scalar pointers offset to the span
-        out = torch.zeros(768, dtype=torch.uint8, device=device)
+        out = torch.empty(768, dtype=torch.uint8, device=device)
         first = (C.c_size_t * 3)(*[lo for lo, _ in spans])
         cnt = (C.c_size_t * 3)(*[hi - lo for lo, hi in spans])
         views = [buf[lo:hi] if hi > lo else buf for buf, (lo, hi) in zip((bufA, bufC, bufB), spans)]
@@ -175,7 +176,7 @@ def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_s
     mark("msm_late")
     pad = torch.zeros(12, dtype=torch.uint8, device=device)
     rec = torch.cat([early, late[192:384], status.view(torch.uint8), pad])   # A | C tail | B | C head | status | pad
-    recs = torch.zeros((world, rec.numel()), dtype=torch.uint8, device=device)
+    recs = torch.empty((world, rec.numel()), dtype=torch.uint8, device=device)
     dist.all_gather(list(recs.unbind(0)), rec)
     mark("gather_partials")
     _raise_status(int(recs[:, 960:964].contiguous().view(torch.int32).max().item()))
