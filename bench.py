@@ -60,6 +60,17 @@ def be_to_le_limbs(a):
     return np.ascontiguousarray(a[:, ::-1]).view("<u4").reshape(-1, 8).copy()
 
 
+def expected_exponent(ks_be, sc_be) -> int:
+    """sum_i k_i s_i mod r for the bases k_i*G and scalars s_i (oracle's C dot product; checker, untimed)"""
+    from oracle import c_oracle as CO
+    return CO.fr_dot(ks_be, sc_be)
+
+
+def expected_point(group: int, e: int) -> bytes:
+    from oracle import ps_oracle as O
+    return O.g1_compress(O.g1_mul(e)) if group == 1 else O.g2_compress(O.g2_mul(e))
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -186,7 +197,6 @@ def main():
     bases = be.bases_from_scalars(L.PS_G1, ks.tobytes(), args.window_bits, args.tables)
     be.sync()
     t_bases = time.time() - t0
-    del ks
     d_scalars = torch.from_numpy(be_to_le_limbs(sc_be).view(np.int32)).to(dev)
     h_scalars = torch.from_numpy(sc_be).pin_memory()            # e2e input: pinned host, wire format
     d_part = torch.zeros(192, dtype=torch.uint8, device=dev)
@@ -216,10 +226,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # correctness gate before timing: the device result must equal the exponent-level expectation on
-    # a small prefix (same kernels, same bases); full parity lives in tests/.
     for _ in range(args.warmup):
         step_resident()
+    barrier()
+    # Correctness gate on the exact configuration that is timed (same bases, scalars, window, scatter path): the
+    # rank's partial must equal (sum_i k_i s_i mod r) * G, the exponent-level check of groth16_test.go:32-107.
+    # The expectation comes from the oracle (checker only, untimed): a C dot product over Fr and one scalar-mul.
+    exp_e = expected_exponent(ks, sc_be)
+    del ks
+    be._check(lib.ps_msm_combine(be.ctx, L.PS_G1, C.c_void_p(d_part.data_ptr()), 1, out))
+    parity = {"g1_2p%d_resident" % args.log_n: out.raw == expected_point(L.PS_G1, exp_e)}
     barrier()
 
     # integer-multiply peak measured on this device (MEASURED_PEAKS.json has no integer figure)
@@ -258,18 +274,30 @@ def main():
         res = step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
+    if world == 1:
+        parity["g1_2p%d_e2e" % args.log_n] = res == expected_point(L.PS_G1, exp_e)
+    else:
+        exps = [None] * world
+        dist.all_gather_object(exps, exp_e)
+        if rank == 0:
+            parity["g1_2p%d_x%d_e2e" % (args.log_n, world)] = res == expected_point(L.PS_G1, sum(exps) % R)
 
     # secondary figure: G2 MSM (same pipeline over Fp2), resident scalars, every rank its own range
     g2 = None
     if args.g2_log_n:
         n2 = 1 << args.g2_log_n
         bases2 = be.bases_from_scalars(L.PS_G2, random_scalars_be(n2, 3000 + rank).tobytes(), args.window_bits, args.tables)
-        d_sc2 = torch.from_numpy(be_to_le_limbs(random_scalars_be(n2, 4000 + rank)).view(np.int32)).to(dev)
+        ks2, sc2 = random_scalars_be(n2, 3000 + rank), random_scalars_be(n2, 4000 + rank)
+        d_sc2 = torch.from_numpy(be_to_le_limbs(sc2).view(np.int32)).to(dev)
         d_part2 = torch.zeros(384, dtype=torch.uint8, device=dev)
         step2 = lambda: be._check(lib.ps_msm_device(be.ctx, bases2.handle, 0, C.c_void_p(d_sc2.data_ptr()), n2, C.c_void_p(d_part2.data_ptr())))
         for _ in range(3):
             step2()
         barrier()
+        out2 = C.create_string_buffer(96)
+        be._check(lib.ps_msm_combine(be.ctx, L.PS_G2, C.c_void_p(d_part2.data_ptr()), 1, out2))
+        parity["g2_2p%d_resident" % args.g2_log_n] = out2.raw == expected_point(L.PS_G2, expected_exponent(ks2, sc2))
+        del ks2, sc2
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
         for _ in range(args.steps):
@@ -283,9 +311,12 @@ def main():
         del d_sc2
 
     t = torch.tensor([ms_total, e2e_s * 1e3, g2["ms"] if g2 else 0.0], dtype=torch.float64, device=dev)
+    ok = torch.tensor([1.0 if all(parity.values()) else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     ms_total, e2e_ms = float(t[0]), float(t[1])
+    parity["all_ranks_ok"] = bool(ok.item() > 0.5)
     if g2:
         g2["ms"] = float(t[2])
     if rank != 0:
@@ -332,6 +363,8 @@ def main():
                    "parallelism": "point-range shard x%d, all-gather of 192 B partials" % world if world > 1 else "single GPU",
                    "bases_build_s": round(t_bases, 2)},
         "clocks": clocks,
+        "parity": dict(parity, how="every timed configuration checked against (sum k_i s_i mod r)*G from the oracle "
+                                   "(C dot product over Fr + one scalar multiplication), untimed"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 48,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
@@ -375,6 +408,9 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not parity["all_ranks_ok"]:
+        print("bench.py: PARITY MISMATCH %r -- the numbers above are invalid" % parity, file=sys.stderr)
+        sys.exit(3)
 
 
 def groth16_section(be, args, dist=None, dev="cuda"):

@@ -16,6 +16,8 @@ def lib():
         _lib.oc_quotient.restype = C.c_int
         _lib.oc_quotient.argtypes = [C.c_char_p] * 4 + [C.c_long, C.c_int, C.c_char_p]
         _lib.oc_aggregate.argtypes = [C.c_char_p, C.c_char_p, C.c_long, C.c_long, C.c_char_p]
+        _lib.oc_fr_dot.restype = None
+        _lib.oc_fr_dot.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_char_p]
     return _lib
 
 
@@ -72,3 +74,16 @@ def quotient(a, b, c, z, faithful=False):
     if rc:
         raise ArithmeticError("apocalypse")
     return [int.from_bytes(out.raw[32 * i:32 * i + 32], "big") for i in range(n - 1)]
+
+
+def fr_dot(a_be, b_be) -> int:
+    """sum_i a[i]*b[i] mod r; a_be, b_be: bytes or C-contiguous numpy uint8 arrays of n x 32 big-endian bytes"""
+    def ptr(x):
+        if isinstance(x, (bytes, bytearray)):
+            return C.cast(C.c_char_p(bytes(x)), C.c_void_p), len(x)
+        return C.c_void_p(x.ctypes.data), x.nbytes
+    (pa, la), (pb, lb) = ptr(a_be), ptr(b_be)
+    assert la == lb and la % 32 == 0
+    out = C.create_string_buffer(32)
+    lib().oc_fr_dot(pa, pb, la // 32, out)
+    return int.from_bytes(out.raw, "big")

@@ -270,3 +270,19 @@ int oc_quotient(const uint8_t* a_be, const uint8_t* b_be, const uint8_t* c_be, c
   free(a); free(b); free(c); free(z); free(r); free(q);
   return nonzero;
 }
+
+/* sum_i a[i] * b[i] mod r over n pairs of 32-byte big-endian scalars (values may be >= r: they are
+ * reduced).  Checker for the exponent-level MSM test at the benchmark's sizes
+ * (groth16_test.go:32-107 style: the MSM over bases k_i*G must equal (sum k_i s_i)*G). */
+void oc_fr_dot(const uint8_t* a_be, const uint8_t* b_be, long n, uint8_t* out32) {
+  ensure_init();
+  fr acc, x, y, t;
+  memset(&acc, 0, sizeof acc);
+  for (long i = 0; i < n; i++) {
+    fr_from_be(&x, a_be + 32 * i);
+    fr_from_be(&y, b_be + 32 * i);
+    fr_mul(&t, &x, &y);
+    fr_add(&acc, &acc, &t);
+  }
+  fr_to_be(out32, &acc);
+}

@@ -55,6 +55,45 @@ def msm_exponent_check(be, group, n, kind="rand", window_bits=0, tables=1, seed=
     bases.close()
 
 
+def msm_exponent_check_big(be, group, log_n, window_bits=0, tables=-1, seed=0, resident=True):
+    """the same check at the benchmark's sizes (2^24 G1 / 2^20 G2): inputs generated with numpy as
+    bench.py does, the expectation from the oracle's C dot product over Fr; with `tables` = -1 the
+    bases carry all window tables and the library picks the window (c = 22 and the two-pass scatter
+    at 2^24).  Both the host-scalar call (ps_msm) and the device-resident one (ps_msm_device +
+    ps_msm_combine) are checked."""
+    import ctypes as C
+    import numpy as np
+    from oracle import c_oracle as CO
+    F, gen, comp, _ = _grp(group)
+    n = 1 << log_n
+    rng = np.random.default_rng(seed * 1000 + log_n * 4 + group)
+
+    def scalars():
+        a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        a[:, 0] &= 0x3F
+        return a
+    ks, sc = scalars(), scalars()
+    bases = be.bases_from_scalars(group, ks.tobytes(), window_bits, tables)
+    want = comp(O.pt_mul(F, CO.fr_dot(ks, sc), gen))
+    del ks
+    out = C.create_string_buffer(48 if group == L.PS_G1 else 96)
+    st = be.lib.ps_msm(be.ctx, bases.handle, C.c_void_p(sc.ctypes.data), n, out)
+    be._check(st)
+    assert out.raw == want, (group, log_n, "ps_msm")
+    if resident:
+        import torch
+        limbs = np.ascontiguousarray(sc[:, ::-1]).view("<u4").reshape(-1, 8)
+        d_sc = torch.from_numpy(limbs.view(np.int32)).cuda()
+        d_part = torch.zeros(192 if group == L.PS_G1 else 384, dtype=torch.uint8, device="cuda")
+        be._check(be.lib.ps_msm_device(be.ctx, bases.handle, 0, C.c_void_p(d_sc.data_ptr()), n, C.c_void_p(d_part.data_ptr())))
+        be._check(be.lib.ps_msm_combine(be.ctx, group, C.c_void_p(d_part.data_ptr()), 1, out))
+        assert out.raw == want, (group, log_n, "ps_msm_device")
+    info = (C.c_int * 4)()
+    be._check(be.lib.ps_bases_info(bases.handle, info))
+    bases.close()
+    return info[0], info[1], info[2]
+
+
 def msm_vs_naive(be, group, n, seed=1):
     """against the reference's own algorithm (BlindEval: one scalar-mul per term)."""
     F, gen, comp, _ = _grp(group)

@@ -65,6 +65,22 @@ def test_msm_large_g2(be):
     P.msm_exponent_check(be, L.PS_G2, 1 << 17, "rand")
 
 
+def test_msm_g1_2p24_bench_configuration(be):
+    # BASELINE configs[3] at the headline size, exactly as bench.py runs it: all window tables, automatic
+    # window (c = 22), automatic two-pass scatter (entry array > L2)
+    c, W, T = P.msm_exponent_check_big(be, L.PS_G1, 24)
+    assert W == T and c >= 20
+
+
+def test_msm_g2_2p20_bench_configuration(be):
+    c, W, T = P.msm_exponent_check_big(be, L.PS_G2, 20)
+    assert W == T
+
+
+def test_msm_g2_2p22(be):
+    P.msm_exponent_check_big(be, L.PS_G2, 22, resident=False)
+
+
 def test_msm_linearity(be):
     """MSM(s+t) = MSM(s) + MSM(t), MSM(k*s) = k*MSM(s) on a fixed base set."""
     rng = random.Random(42)
@@ -105,13 +121,13 @@ def test_phgr13_mixed(be): P.phgr13_circuit(be, 20, seed=6)
 def test_sparse_quotient(be, n): P.sparse_quotient_vs_dense(be, n, seed=n)
 
 
-@pytest.mark.parametrize("log_n", [8, 12, 16])
+@pytest.mark.parametrize("log_n", [8, 12, 16, 20])
 def test_sparse_groth16_exponent_check(be, log_n):
     # config C3: 2^16 constraints, full prove (interpolation + NTT quotient + 3 MSMs), exponent-level parity
     P.groth16_sparse_exponent_check(be, log_n, seed=log_n)
 
 
-@pytest.mark.parametrize("log_n", [6, 12])
+@pytest.mark.parametrize("log_n", [6, 12, 16])
 def test_sparse_phgr13_exponent_check(be, log_n): P.phgr13_sparse_exponent_check(be, log_n, seed=log_n)
 
 
