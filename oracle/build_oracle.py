@@ -6,15 +6,16 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "ps_oracle.c")
+SRC = os.path.join(HERE, "ps_prover.c")      # includes ps_oracle.c: one translation unit
+DEPS = [SRC, os.path.join(HERE, "ps_oracle.c")]
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libps_oracle.so")
 
 
 def build() -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
-    if not os.path.exists(LIB) or os.path.getmtime(SRC) > os.path.getmtime(LIB):
-        subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-shared", "-fPIC", "-o", LIB, SRC])
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+        subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-fopenmp", "-shared", "-fPIC", "-o", LIB, SRC])
     return LIB
 
 

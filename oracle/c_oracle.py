@@ -87,3 +87,83 @@ def fr_dot(a_be, b_be) -> int:
     out = C.create_string_buffer(32)
     lib().oc_fr_dot(pa, pb, la // 32, out)
     return int.from_bytes(out.raw, "big")
+
+
+# ---- the reference's whole proving flow restated in C (oracle/ps_prover.c) ---------------------------
+_gen_set = False
+
+
+def _prover_lib():
+    global _gen_set
+    L = lib()
+    if not _gen_set:
+        L.op_set_generators(O.g1_affine_bytes(O.G1_GEN), O.g2_affine_bytes(O.G2_GEN))
+        L.op_groth16_flow.restype = C.c_int
+        L.op_phgr13_flow.restype = C.c_int
+        L.op_blind_eval_g1_mt.restype = C.c_long
+        L.op_blind_eval_g1_mt.argtypes = [C.c_char_p, C.c_char_p, C.c_long, C.c_int, C.c_char_p]
+        _gen_set = True
+    return L
+
+
+def max_threads() -> int:
+    return int(lib().op_max_threads())
+
+
+def _matrix(rows, n, m):
+    flat = (C.c_long * (n * m))()
+    for j, row in enumerate(rows):
+        for i, v in enumerate(row):
+            if v:
+                flat[j * m + i] = v
+    return flat
+
+
+def groth16_flow(r1cs, witness_fr, toxic, r: int, s: int, threads: int = 1, fast_qap: bool = False):
+    """ToQAP -> NewGroth16TrustedSetup -> Groth16Prove in C on `r1cs` (oracle R1CS with dense Go-int rows).
+    toxic = (alpha, beta, delta, x).  Returns (A, B, C oracle points, h, seconds dict)."""
+    L = _prover_lib()
+    n, m = len(r1cs.left), len(r1cs.vars)
+    out = C.create_string_buffer(384)
+    hb = C.create_string_buffer(32 * max(1, n - 1))
+    sec = (C.c_double * 3)()
+    rc = L.op_groth16_flow(_matrix(r1cs.left, n, m), _matrix(r1cs.right, n, m), _matrix(r1cs.out, n, m), C.c_long(n), C.c_long(m),
+                           C.c_long(r1cs.nb_io()), _poly_bytes(witness_fr), b"".join(O.fr_to_bytes(t) for t in toxic),
+                           O.fr_to_bytes(r), O.fr_to_bytes(s), C.c_int(threads), C.c_int(1 if fast_qap else 0), out, hb, sec)
+    if rc == 1:
+        raise ArithmeticError("apocalypse")
+    assert rc == 0
+    raw = out.raw
+    h = [int.from_bytes(hb.raw[32 * i:32 * i + 32], "big") for i in range(n - 1)]
+    return (O.g1_from_affine_bytes(raw[:96]), O.g2_from_affine_bytes(raw[96:288]), O.g1_from_affine_bytes(raw[288:]), h,
+            {"to_qap_s": sec[0], "setup_s": sec[1], "prove_s": sec[2]})
+
+
+def phgr13_flow(r1cs, witness_fr, toxic, threads: int = 1, fast_qap: bool = False):
+    """ToQAP -> NewPHGR13TrustedSetup (evaluation key) -> PHGR13Prove in C.
+    toxic = (s, av, aw, ay, rv, rw, beta).  Returns (dict of the eight proof points, h, seconds dict)."""
+    L = _prover_lib()
+    n, m = len(r1cs.left), len(r1cs.vars)
+    out = C.create_string_buffer(864)
+    hb = C.create_string_buffer(32 * max(1, n - 1))
+    sec = (C.c_double * 3)()
+    rc = L.op_phgr13_flow(_matrix(r1cs.left, n, m), _matrix(r1cs.right, n, m), _matrix(r1cs.out, n, m), C.c_long(n), C.c_long(m),
+                          C.c_long(r1cs.nb_io()), _poly_bytes(witness_fr), b"".join(O.fr_to_bytes(t) for t in toxic),
+                          C.c_int(threads), C.c_int(1 if fast_qap else 0), out, hb, sec)
+    if rc == 1:
+        raise ArithmeticError("apocalypse")
+    assert rc == 0
+    raw = out.raw
+    names = ("hs", "vss", "yss", "vass", "wass", "yass", "gz")
+    proof = {nm: O.g1_from_affine_bytes(raw[96 * i:96 * i + 96]) for i, nm in enumerate(names)}
+    proof["wss"] = O.g2_from_affine_bytes(raw[672:864])
+    h = [int.from_bytes(hb.raw[32 * i:32 * i + 32], "big") for i in range(n - 1)]
+    return proof, h, {"to_qap_s": sec[0], "setup_s": sec[1], "prove_s": sec[2]}
+
+
+def blind_eval_g1_mt(points_affine_bytes: bytes, scalars_be: bytes, threads: int):
+    n = len(scalars_be) // 32
+    assert len(points_affine_bytes) == 96 * n
+    out = C.create_string_buffer(96)
+    _prover_lib().op_blind_eval_g1_mt(points_affine_bytes, scalars_be, n, threads, out)
+    return O.g1_from_affine_bytes(out.raw)
