@@ -54,7 +54,8 @@ const char* ps_version(void);
 int ps_ctx_create(int device, ps_ctx** out);
 /* run on a caller-provided CUDA stream (cudaStream_t passed as void*), e.g. torch's current one */
 int ps_ctx_set_stream(ps_ctx* ctx, void* cuda_stream);
-/* tuning knobs: "msm_accumulate" = 0 (XYZZ accumulator chains, default) | 1 (batched affine tree rounds);
+/* options: "subgroup_check" = 1 (points decoded by the loaders must lie in the prime-order subgroup, as kilic's
+ * FromCompressed demands of the reference's keys; default) | 0 (skip the r-multiplication for vouched keys);
  * "msm_team" = 1 (latency-bound tail kernels of the MSM use a team of four lanes per group operation,
  * default) | 0 (one thread per operation);
  * "msm_shards" = N >= 1: base sets and keys loaded afterwards are meant to be summed in N index ranges

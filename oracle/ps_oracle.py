@@ -186,6 +186,20 @@ def pt_mul(F, k: int, a):
     return to_affine(F, acc)
 
 
+def in_subgroup(F, a) -> bool:
+    """r * a == O with the scalar NOT reduced (kilic's FromCompressed / FromBytes reject points of the
+    curve that lie outside the prime-order subgroup; kyber's UnmarshalBinary goes through them)."""
+    if a is None:
+        return True
+    acc = (F.one, F.one, F.zero)
+    base = to_jac(F, a)
+    for bit in bin(R)[2:]:
+        acc = jac_dbl(F, acc)
+        if bit == "1":
+            acc = jac_add(F, acc, base)
+    return to_affine(F, acc) is None
+
+
 def pt_sum(F, pts):
     acc = (F.one, F.one, F.zero)
     for p in pts:
@@ -282,6 +296,8 @@ def g1_decompress(b: bytes):
         raise ValueError("bad G1 encoding")
     if _fp_larger(y) != bool(b[0] & 0x20):
         y = P - y
+    if not in_subgroup(F1, (x, y)):
+        raise ValueError("G1 point outside the prime-order subgroup")
     return (x, y)
 
 
@@ -330,6 +346,8 @@ def g2_decompress(b: bytes):
         raise ValueError("bad G2 encoding")
     if _fp2_larger(y) != bool(b[0] & 0x20):
         y = F2.neg(y)
+    if not in_subgroup(F2, (x, y)):
+        raise ValueError("G2 point outside the prime-order subgroup")
     return (x, y)
 
 

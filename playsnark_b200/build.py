@@ -1,22 +1,44 @@
-"""Builds libplaysnark_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Builds libplaysnark_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+One object file per translation unit, compiled in parallel and only when one of the files it includes
+(transitively) has changed; then one link.  Objects live in playsnark_b200/_build/ (not shipped)."""
 from __future__ import annotations
 
 import glob
 import os
+import re
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libplaysnark_b200.so")
 
-CU_SOURCES = [os.path.join(CSRC, "capi.cu"), os.path.join(CSRC, "accum_g2.cu")]
+CU_SOURCES = [os.path.join(CSRC, f) for f in ("capi.cu", "capi_poly.cu", "capi_multi.cu", "group_g1.cu", "group_g2.cu", "accum_g2.cu")
+              if os.path.exists(os.path.join(CSRC, f))]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
-    "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
+    "-lineinfo", "-Xcompiler", "-fPIC",
 ]
+
+_INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+
+def _deps(path: str, seen=None):
+    """the file and every project header it includes, transitively"""
+    seen = set() if seen is None else seen
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    with open(path) as f:
+        for inc in _INC.findall(f.read()):
+            _deps(os.path.join(os.path.dirname(path), inc), seen)
+    return seen
 
 
 def _sources():
@@ -31,24 +53,57 @@ def stale(target: str, sources) -> bool:
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build_cuda(force: bool = False, verbose: bool = False) -> str:
-    srcs = _sources()
-    if not force and not stale(LIB, srcs):
-        return LIB
+def build_cuda(force: bool = False, verbose: bool = False, out: str = LIB, extra_flags=()) -> str:
+    if not force and not extra_flags and not stale(out, _sources()):
+        return out
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["--threads", "2", "-o", LIB] + CU_SOURCES
+    obj_dir = OBJ if out == LIB else out + ".obj"
+    os.makedirs(obj_dir, exist_ok=True)
+    jobs = []
+    for src in CU_SOURCES:
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        if force or extra_flags or stale(obj, _deps(src)):
+            jobs.append((src, obj))
+    threads = max(1, (os.cpu_count() or 2) // max(1, len(jobs)))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-split-compile", str(threads), "-c", "-o", obj, src]
+        print("[playsnark_b200] " + " ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd, cwd=ROOT)
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            list(ex.map(compile_one, jobs))
+    objs = [os.path.join(obj_dir, os.path.basename(s)[:-3] + ".o") for s in CU_SOURCES]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs
     print("[playsnark_b200] " + " ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd, cwd=ROOT)
-    return LIB
+    return out
 
 
 def build_host_emulation(out_dir: str) -> str:
     """TEST-ONLY: the same sources with -DPS_HOST_EMU (kernel bodies driven by serial loops)."""
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libps_hostemu.so")
-    if stale(so, _sources()):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-DPS_HOST_EMU", "-shared", "-fPIC", "-o", so] + CU_SOURCES,
-                              cwd=ROOT)
+    if not stale(so, _sources()):
+        return so
+    jobs = []
+    for src in CU_SOURCES:
+        obj = os.path.join(out_dir, "emu_" + os.path.basename(src)[:-3] + ".o")
+        if stale(obj, _deps(src)):
+            jobs.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-DPS_HOST_EMU", "-fPIC", "-c", "-o", obj, src], cwd=ROOT)
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            list(ex.map(compile_one, jobs))
+    objs = [os.path.join(out_dir, "emu_" + os.path.basename(s)[:-3] + ".o") for s in CU_SOURCES]
+    subprocess.check_call(["g++", "-shared", "-o", so] + objs + ["-lpthread"], cwd=ROOT)
     return so
 
 

@@ -6,8 +6,7 @@
 // Bulk keys may also come zcash-uncompressed (96 B / 192 B).  All conversion, including the square
 // roots of decompression, runs on the device.
 #pragma once
-#include "backend.cuh"
-#include "curve.cuh"
+#include "group_ops.cuh"
 
 namespace ps {
 
@@ -81,7 +80,7 @@ PS_DEV bool fp_sqrt(const Fp& a, Fp& out) {
   out = fp_sqrt_candidate(a);
   return out.sqr() == a;
 }
-PS_NOINLINE Fp2 fp2_pow(const Fp2& a, const uint32_t* e, int nlimbs) {
+inline PS_NOINLINE Fp2 fp2_pow(const Fp2& a, const uint32_t* e, int nlimbs) {
   Fp2 acc = Fp2::one();
   bool started = false;
   for (int i = nlimbs - 1; i >= 0; i--) {
@@ -125,13 +124,30 @@ PS_DEV bool read_fp(const uint8_t* b, bool mask, Fp& out) {
   return ok;
 }
 
+// r * P == O ?  (kilic's FromCompressed / FromBytes reject points outside the prime-order subgroup; the
+// MSM relies on it when it folds k > r/2 to r - k with the point negated)
+template <class F>
+PS_NOINLINE bool in_subgroup(const Affine<F>& p) {
+  uint32_t k[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) k[j] = FrParams::MOD(j);
+  return xyzz_scalar_mul(XYZZ<F>::from_affine(p), k, 8).is_inf();
+}
+// the infinity encoding must be canonical: flag bits 0xC0 (compressed) / 0x40 (uncompressed), all else zero
+PS_DEV bool inf_is_canonical(const uint8_t* b, int len, bool compressed) {
+  uint32_t o = (uint32_t)(b[0] ^ (compressed ? 0xC0 : 0x40));
+  for (int k = 1; k < len; k++) o |= b[k];
+  return o == 0;
+}
+
 struct G1DecodeK {
   static constexpr int BLOCK = 128;
-  PS_DEV static void run(uint32_t i, const uint8_t* in, int format, G1Affine* out, uint32_t* err) {
+  PS_DEV static void run(uint32_t i, const uint8_t* in, int format, G1Affine* out, uint32_t* err, int subgroup) {
     const uint8_t* b = in + (size_t)i * (format == PS_FMT_COMPRESSED ? 48 : 96);
     uint8_t flags = b[0];
     bool ok = true;
     G1Affine p = G1Affine::inf();
+    if (flags & 0x40) ok = inf_is_canonical(b, format == PS_FMT_COMPRESSED ? 48 : 96, format == PS_FMT_COMPRESSED);
     if (format == PS_FMT_COMPRESSED) {
       if (!(flags & 0x80)) ok = false;
       if (!(flags & 0x40)) {
@@ -153,17 +169,19 @@ struct G1DecodeK {
       }
     }
     if (!ok) { ps_atomic_or(err, 2u); p = G1Affine::inf(); }
+    else if (subgroup && !p.is_inf() && !in_subgroup(p)) { ps_atomic_or(err, 4u); p = G1Affine::inf(); }
     out[i] = p;
   }
 };
 
 struct G2DecodeK {
   static constexpr int BLOCK = 64;
-  PS_DEV static void run(uint32_t i, const uint8_t* in, int format, G2Affine* out, uint32_t* err) {
+  PS_DEV static void run(uint32_t i, const uint8_t* in, int format, G2Affine* out, uint32_t* err, int subgroup) {
     const uint8_t* b = in + (size_t)i * (format == PS_FMT_COMPRESSED ? 96 : 192);
     uint8_t flags = b[0];
     bool ok = true;
     G2Affine p = G2Affine::inf();
+    if (flags & 0x40) ok = inf_is_canonical(b, format == PS_FMT_COMPRESSED ? 96 : 192, format == PS_FMT_COMPRESSED);
     if (format == PS_FMT_COMPRESSED) {
       if (!(flags & 0x80)) ok = false;
       if (!(flags & 0x40)) {
@@ -188,6 +206,7 @@ struct G2DecodeK {
       }
     }
     if (!ok) { ps_atomic_or(err, 2u); p = G2Affine::inf(); }
+    else if (subgroup && !p.is_inf() && !in_subgroup(p)) { ps_atomic_or(err, 4u); p = G2Affine::inf(); }
     out[i] = p;
   }
 };
@@ -221,10 +240,10 @@ PS_DEV void g2_encode(const G2Affine& p, int format, uint8_t* b) {
 }
 PS_DEV void point_encode(const G1Affine& p, int format, uint8_t* b) { g1_encode(p, format, b); }
 PS_DEV void point_encode(const G2Affine& p, int format, uint8_t* b) { g2_encode(p, format, b); }
+template <class F> struct DecodeKernel;
+template <> struct DecodeKernel<Fp> { using K = G1DecodeK; };
+template <> struct DecodeKernel<Fp2> { using K = G2DecodeK; };
 
-template <class F> struct PointBytes;
-template <> struct PointBytes<Fp> { static constexpr int COMP = 48, AFF = 96; };
-template <> struct PointBytes<Fp2> { static constexpr int COMP = 96, AFF = 192; };
 
 // XYZZ (device) -> affine -> bytes; one thread per point
 template <class F>

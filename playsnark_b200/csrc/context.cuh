@@ -1,12 +1,21 @@
 // The per-GPU context behind the C ABI's opaque ps_ctx handle.
 #pragma once
 #include "backend.cuh"
-#include "ntt.cuh"
 #include <utility>
 
 #ifndef PS_BUCKET_COST
-#define PS_BUCKET_COST 70   // see msm_pick_window_full (msm.cuh)
+#define PS_BUCKET_COST 70   // see msm_pick_window_full (group_ops.cuh)
 #endif
+
+namespace ps {
+// Twiddle tables for one transform size, resident on the device (built by ntt_tables_build, ntt.cuh).
+struct NttTables {
+  int log_n = -1;
+  Fr* tw = nullptr;      // omega^i, i < max(n/2, 1)
+  Fr* tw_inv = nullptr;  // omega^-i
+  void release() { dev_free(tw); dev_free(tw_inv); tw = tw_inv = nullptr; log_n = -1; }
+};
+}  // namespace ps
 
 #ifndef PS_SCATTER_DEFAULT
 #define PS_SCATTER_DEFAULT 1
@@ -32,8 +41,9 @@ struct ps_ctx {
   // phase events of the last Groth16 prove: start, quotient done, MSM A, MSM C, MSM B, encoded
   void* evp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool evp_valid = false;
-  // bucket accumulation: 0 = XYZZ chains (MsmAccumK), 1 = batched affine tree rounds (msm_affine.cuh)
-  int accum_mode = 0;
+  // point decoding rejects points outside the prime-order subgroup (kilic's FromCompressed does); 0 skips the
+  // r-multiplication for key material the caller vouches for
+  int subgroup_check = 1;
   // latency-bound tail kernels of the MSM: 1 = a team of four lanes per group operation (team.cuh), 0 = one thread
   int msm_team = 1;
   // base sets loaded from now on are meant to be summed in this many index ranges (sharded proofs)
@@ -50,13 +60,8 @@ struct ps_ctx {
 };
 
 namespace ps {
-inline int ctx_ntt_tables(ps_ctx* ctx, int log_n, const NttTables** out) {
-  if (log_n < 0 || log_n > 30) return PS_ERR_ARG;
-  NttTables& t = ctx->ntt_cache[log_n];
-  if (t.log_n != log_n) PS_TRY(ntt_tables_build(ctx->stream, log_n, &t));
-  *out = &t;
-  return PS_OK;
-}
+// twiddle tables by size, built on first use (defined in capi_poly.cu, the translation unit of the Fr kernels)
+int ctx_ntt_tables(ps_ctx* ctx, int log_n, const NttTables** out);
 inline int ctx_event(ps_ctx* ctx, int i) {
   if (!ctx->timing_events) return PS_OK;
 #if PS_GPU

@@ -23,22 +23,16 @@
 //   7. MsmFinalK      Horner over the bucket sets (c*T doublings between sets)
 // With T precomputed tables (2^(c t) * P_i, t < T) the windows w = s*T + t share bucket set s.
 #pragma once
-#include "context.cuh"
-#include "curve.cuh"
+#include "group_ops.cuh"
 #include "team.cuh"
 
 namespace ps {
 
-struct MsmGeom {
-  uint32_t n;      // scalars / points in this call
-  uint32_t nbase;  // points per table (table stride)
-  uint32_t first;  // first point of the range inside each table
-  int c;           // window bits
-  int W;           // windows = ceil(255 / c)
-  int T;           // precomputed tables
-  int S;           // bucket sets = ceil(W / T)
-  uint32_t D;      // buckets per set = 2^(c-1)
-};
+PS_DEV int msm_seg_of(const MsmPlan& p, uint32_t i) {
+  int k = 0;
+  while (k + 1 < p.nseg && i >= p.seg[k + 1].start) k++;
+  return k;
+}
 
 // Loads scalar i (8 LE limbs), optionally leaves Montgomery form, folds k > (r-1)/2 to r-k.
 PS_DEV void msm_load_scalar(const uint32_t* scalars, uint32_t i, int mont, uint32_t k[8], bool& neg) {
@@ -84,35 +78,38 @@ PS_DEV bool msm_next_digit(uint32_t k[8], int c, uint32_t& carry, uint32_t& mag,
 
 struct MsmCountK {
   static constexpr int BLOCK = 256;
-  PS_DEV static void run(uint32_t i, MsmGeom g, const uint32_t* scalars, int mont, uint32_t* count, uint32_t* ranks) {
+  PS_DEV static void run(uint32_t i, MsmPlan p, uint32_t* count, uint32_t* ranks) {
+    const MsmSeg sg = p.seg[msm_seg_of(p, i)];
     uint32_t k[8]; bool neg;
-    msm_load_scalar(scalars, i, mont, k, neg);
+    msm_load_scalar(sg.scalars, i - sg.start, (int)sg.mont, k, neg);
     uint32_t carry = 0;
-    for (int w = 0; w < g.W; w++) {
+    const uint32_t b0 = sg.set * (uint32_t)p.S * p.D;
+    for (int w = 0; w < p.W; w++) {
       uint32_t mag; bool dneg;
       uint32_t rank = 0xFFFFFFFFu;
-      if (msm_next_digit(k, g.c, carry, mag, dneg)) {
-        uint32_t b = (uint32_t)(w / g.T) * g.D + (mag - 1);
+      if (msm_next_digit(k, p.c, carry, mag, dneg)) {
+        uint32_t b = b0 + (uint32_t)(w / p.T) * p.D + (mag - 1);
         rank = ps_atomic_add(count + b, 1u);
       }
-      ranks[(size_t)w * g.n + i] = rank;
+      ranks[(size_t)w * p.total + i] = rank;
     }
   }
 };
 
 struct MsmScatterK {
   static constexpr int BLOCK = 256;
-  PS_DEV static void run(uint32_t i, MsmGeom g, const uint32_t* scalars, int mont, const uint32_t* off,
-                         const uint32_t* ranks, uint32_t* ent) {
+  PS_DEV static void run(uint32_t i, MsmPlan p, const uint32_t* off, const uint32_t* ranks, uint32_t* ent) {
+    const MsmSeg sg = p.seg[msm_seg_of(p, i)];
     uint32_t k[8]; bool neg;
-    msm_load_scalar(scalars, i, mont, k, neg);
+    msm_load_scalar(sg.scalars, i - sg.start, (int)sg.mont, k, neg);
     uint32_t carry = 0;
-    for (int w = 0; w < g.W; w++) {
+    const uint32_t b0 = sg.set * (uint32_t)p.S * p.D, nbase = p.nbase[sg.set], pt = sg.first + (i - sg.start);
+    for (int w = 0; w < p.W; w++) {
       uint32_t mag; bool dneg;
-      if (msm_next_digit(k, g.c, carry, mag, dneg)) {
-        uint32_t b = (uint32_t)(w / g.T) * g.D + (mag - 1);
-        uint32_t pos = off[b] + ranks[(size_t)w * g.n + i];
-        uint32_t idx = (uint32_t)(w % g.T) * g.nbase + g.first + i;
+      if (msm_next_digit(k, p.c, carry, mag, dneg)) {
+        uint32_t b = b0 + (uint32_t)(w / p.T) * p.D + (mag - 1);
+        uint32_t pos = off[b] + ranks[(size_t)w * p.total + i];
+        uint32_t idx = (uint32_t)(w % p.T) * nbase + pt;
         ent[pos] = idx | ((neg != dneg) ? 0x80000000u : 0u);
       }
     }
@@ -152,7 +149,10 @@ struct MsmAccumK {
   // registers: G1 fits 3 resident blocks per SM without spilling; G2 (Fp2) is register-bound
   static constexpr int MIN_BLOCKS = sizeof(F) == sizeof(Fp) ? PS_G1_MINB : PS_G2_MINB;
   using Self = MsmAccumK<F>;
-  PS_DEV static void run(uint32_t tid, uint32_t nb, uint32_t L, const Affine<F>* tab, const uint32_t* ent,
+  PS_DEV static const Affine<F>* table_of(const MsmTabs& tabs, uint32_t b) {
+    return (const Affine<F>*)tabs.tab[(b >> tabs.log_d) / (uint32_t)tabs.S];
+  }
+  PS_DEV static void run(uint32_t tid, uint32_t nb, uint32_t L, MsmTabs tabs, const uint32_t* ent,
                          const uint32_t* off, XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid,
                          uint8_t* slot_fl) {
     const uint32_t M = off[nb];
@@ -165,6 +165,7 @@ struct MsmAccumK {
     uint32_t b = msm_find_bucket(off, nb, cur);
     bool head_open = off[b] < cur;
     uint32_t bend = off[b + 1];
+    const Affine<F>* tab = table_of(tabs, b);
     XYZZ<F> acc = XYZZ<F>::inf();
     // One flat loop of (at most) L iterations: every lane of the warp reaches the madd together; the
     // bucket hand-over is a short predicated block in front of it.
@@ -176,6 +177,7 @@ struct MsmAccumK {
         b++;
         while (off[b + 1] <= cur) b++;
         bend = off[b + 1];
+        tab = table_of(tabs, b);
       }
       // (an L2 prefetch of the next entry's base was measured slightly slower: 79.8 vs 78.8 ms at 2^24 --
       // the other resident warps already cover the gather latency)
@@ -401,20 +403,19 @@ struct MsmBitFinalK {
   }
 };
 
-// Horner over the bucket sets: R = sum_s 2^(shift*s) * set[s]   (one work item)
+// Horner over the bucket sets of output k: out[k] = sum_s 2^(shift*s) * sets[k*S + s]   (one work item per output)
 template <class F, bool T>
 struct MsmFinalK {
   static constexpr int BLOCK = 32;
   PS_DEV static void run(uint32_t tid, int S, int shift, const XYZZ<F>* sets, XYZZ<F>* out) {
     Coop<T> co(tid);
     if (co.idle()) return;
-    if (tid != 0) return;
     XYZZ<F> r = XYZZ<F>::inf();
     for (int s = S - 1; s >= 0; s--) {
       for (int d = 0; d < shift; d++) co.dbl(r);
-      co.add(r, sets[s]);
+      co.add(r, sets[(size_t)tid * S + s]);
     }
-    if (co.writer()) *out = r;
+    if (co.writer()) out[tid] = r;
   }
 };
 
@@ -544,38 +545,39 @@ constexpr int SCATTER2_WMAX = 16;
 #endif
 constexpr int SCATTER2_BLOCK = PS_SCATTER2_BLOCK;  // scalars per block: longer runs per partition, fewer global atomics
 #if PS_GPU
-static __global__ void __launch_bounds__(SCATTER2_BLOCK) k_scatter_stage(MsmGeom g, const uint32_t* scalars, int mont, const uint32_t* off,
-                                                             const uint32_t* ranks, uint32_t* part_count, uint32_t* staging,
-                                                             int shift, uint32_t nparts) {
+static __global__ void __launch_bounds__(SCATTER2_BLOCK) k_scatter_stage(MsmPlan p, const uint32_t* off, const uint32_t* ranks,
+                                                             uint32_t* part_count, uint32_t* staging, int shift, uint32_t nparts) {
   extern __shared__ uint32_t sh_scatter[];
   uint32_t* hist = sh_scatter;
   uint32_t* base = sh_scatter + nparts;
-  for (uint32_t p = threadIdx.x; p < nparts; p += blockDim.x) hist[p] = 0;
+  for (uint32_t q = threadIdx.x; q < nparts; q += blockDim.x) hist[q] = 0;
   __syncthreads();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t pos[SCATTER2_WMAX], val[SCATTER2_WMAX], lr[SCATTER2_WMAX];
 #pragma unroll
   for (int w = 0; w < SCATTER2_WMAX; w++) pos[w] = 0xFFFFFFFFu;
-  if (i < g.n) {
+  if (i < p.total) {
+    const MsmSeg sg = p.seg[msm_seg_of(p, i)];
     uint32_t k[8]; bool neg;
-    msm_load_scalar(scalars, i, mont, k, neg);
+    msm_load_scalar(sg.scalars, i - sg.start, (int)sg.mont, k, neg);
     uint32_t carry = 0;
+    const uint32_t b0 = sg.set * (uint32_t)p.S * p.D, nbase = p.nbase[sg.set], pt = sg.first + (i - sg.start);
 #pragma unroll
     for (int w = 0; w < SCATTER2_WMAX; w++) {
-      if (w < g.W) {
+      if (w < p.W) {
         uint32_t mag; bool dneg;
-        if (msm_next_digit(k, g.c, carry, mag, dneg)) {
-          const uint32_t b = (uint32_t)(w / g.T) * g.D + (mag - 1);
-          pos[w] = off[b] + ranks[(size_t)w * g.n + i];
-          val[w] = ((uint32_t)(w % g.T) * g.nbase + g.first + i) | ((neg != dneg) ? 0x80000000u : 0u);
+        if (msm_next_digit(k, p.c, carry, mag, dneg)) {
+          const uint32_t b = b0 + (uint32_t)(w / p.T) * p.D + (mag - 1);
+          pos[w] = off[b] + ranks[(size_t)w * p.total + i];
+          val[w] = ((uint32_t)(w % p.T) * nbase + pt) | ((neg != dneg) ? 0x80000000u : 0u);
           lr[w] = atomicAdd(&hist[pos[w] >> shift], 1u);
         }
       }
     }
   }
   __syncthreads();
-  for (uint32_t p = threadIdx.x; p < nparts; p += blockDim.x)
-    if (hist[p]) base[p] = atomicAdd(&part_count[p], hist[p]);
+  for (uint32_t q = threadIdx.x; q < nparts; q += blockDim.x)
+    if (hist[q]) base[q] = atomicAdd(&part_count[q], hist[q]);
   __syncthreads();
 #pragma unroll
   for (int w = 0; w < SCATTER2_WMAX; w++) {
@@ -588,86 +590,50 @@ static __global__ void __launch_bounds__(SCATTER2_BLOCK) k_scatter_stage(MsmGeom
 }
 #endif
 // pass 1 on the stream; part_count (nparts words) must be zero; staging holds 2 words per position
-inline int scatter_stage(ps_stream_t st, MsmGeom g, const uint32_t* scalars, int mont, const uint32_t* off, const uint32_t* ranks,
-                         uint32_t* part_count, uint32_t* staging, int shift, uint32_t nparts) {
+inline int scatter_stage(ps_stream_t st, const MsmPlan& p, const uint32_t* off, const uint32_t* ranks, uint32_t* part_count,
+                         uint32_t* staging, int shift, uint32_t nparts) {
 #if PS_GPU
-  const uint32_t blocks = (g.n + SCATTER2_BLOCK - 1) / SCATTER2_BLOCK;
-  k_scatter_stage<<<blocks, SCATTER2_BLOCK, 2 * nparts * sizeof(uint32_t), st>>>(g, scalars, mont, off, ranks, part_count, staging, shift, nparts);
+  const uint32_t blocks = (p.total + SCATTER2_BLOCK - 1) / SCATTER2_BLOCK;
+  k_scatter_stage<<<blocks, SCATTER2_BLOCK, 2 * nparts * sizeof(uint32_t), st>>>(p, off, ranks, part_count, staging, shift, nparts);
   PS_CUDA_TRY(cudaGetLastError());
   launch_counter()++;
 #else
   (void)st; (void)nparts;
-  for (uint32_t i = 0; i < g.n; i++) {
+  for (uint32_t i = 0; i < p.total; i++) {
+    const MsmSeg sg = p.seg[msm_seg_of(p, i)];
     uint32_t k[8]; bool neg;
-    msm_load_scalar(scalars, i, mont, k, neg);
+    msm_load_scalar(sg.scalars, i - sg.start, (int)sg.mont, k, neg);
     uint32_t carry = 0;
-    for (int w = 0; w < g.W; w++) {
+    const uint32_t b0 = sg.set * (uint32_t)p.S * p.D, nbase = p.nbase[sg.set], pt = sg.first + (i - sg.start);
+    for (int w = 0; w < p.W; w++) {
       uint32_t mag; bool dneg;
-      if (!msm_next_digit(k, g.c, carry, mag, dneg)) continue;
-      const uint32_t b = (uint32_t)(w / g.T) * g.D + (mag - 1);
-      const uint32_t pos = off[b] + ranks[(size_t)w * g.n + i];
+      if (!msm_next_digit(k, p.c, carry, mag, dneg)) continue;
+      const uint32_t b = b0 + (uint32_t)(w / p.T) * p.D + (mag - 1);
+      const uint32_t pos = off[b] + ranks[(size_t)w * p.total + i];
       const uint32_t part = pos >> shift;
       const size_t slot = ((size_t)part << shift) + part_count[part]++;
       staging[2 * slot] = pos;
-      staging[2 * slot + 1] = ((uint32_t)(w % g.T) * g.nbase + g.first + i) | ((neg != dneg) ? 0x80000000u : 0u);
+      staging[2 * slot + 1] = ((uint32_t)(w % p.T) * nbase + pt) | ((neg != dneg) ? 0x80000000u : 0u);
     }
   }
 #endif
   return PS_OK;
 }
 
-// ---- planning ------------------------------------------------------------------------------------------
-inline int msm_windows(int c) { return (255 + c - 1) / c; }
-
-// cost model (field multiplications) used to pick c when the bases carry no precomputed tables
-inline int msm_pick_window(size_t n) {
-  int best = 4; double best_cost = 1e300;
-  for (int c = 4; c <= 22; c++) {
-    double W = msm_windows(c);
-    double buckets = W * (double)(1u << (c - 1));
-    double cost = (double)n * W * 10.0 + buckets * (2.0 * 14.0 + 10.0);
-    if (cost < best_cost) { best_cost = cost; best = c; }
-  }
-  return best;
-}
-
-// window for bases that carry all W tables (one shared bucket set): fewer, larger windows pay off.
-// Cost in field products: 10 per mixed addition; `bucket_cost` per bucket for everything that scales
-// with the bucket count (boundary-partial merge + reduction).  By operation count a bucket costs 38
-// (2 full additions + share of the merge), but those kernels run at a lower fraction of the multiplier
-// peak than the accumulate kernel: measured on B200 at 2^20 points, c = 20, a bucket costs about as
-// much time as 10 mixed additions in G1 and in G2 alike; a sweep of the window over 2^16..2^24 points
-// (profiles/r01s2_window_model.md) is matched best by PS_BUCKET_COST = 70 (context.cuh).
-inline int msm_pick_window_full(size_t n, double bucket_cost = PS_BUCKET_COST) {
-  int best = 4; double best_cost = 1e300;
-  for (int c = 4; c <= 24; c++) {
-    double W = msm_windows(c);
-    if ((double)n * W >= 2.0e9) continue;  // entry indices are 31 bits
-    double cost = (double)n * W * 10.0 + (double)(1u << (c - 1)) * bucket_cost;
-    if (cost < best_cost) { best_cost = cost; best = c; }
-  }
-  return best;
-}
-
-// Runs the pipeline; result (XYZZ) written to d_out (device).  `tab` holds g.T tables of g.nbase points.
-template <class F>
-int msm_accumulate_affine(ps_ctx* ctx, uint32_t nb, size_t max_ent, const Affine<F>* tab, const uint32_t* ent, const uint32_t* off0,
-                          XYZZ<F>* buckets);
-
 // the hot kernel: G1 as is; G2 through the layout-identical Fp2I (inlined base-field products)
 template <class F>
-inline int launch_accum(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const Affine<F>* tab, const uint32_t* ent, const uint32_t* off,
+inline int launch_accum(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const MsmTabs& tabs, const uint32_t* ent, const uint32_t* off,
                         XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid, uint8_t* slot_fl) {
-  PS_LAUNCH(MsmAccumK<F>, st, T1, nb, L, tab, ent, off, buckets, slot_pt, slot_bid, slot_fl);
+  PS_LAUNCH(MsmAccumK<F>, st, T1, nb, L, tabs, ent, off, buckets, slot_pt, slot_bid, slot_fl);
   return PS_OK;
 }
 // defined in accum_g2.cu (its own translation unit: the fully inlined kernel dominates compile time)
-int launch_accum_g2(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const Affine<Fp2>* tab, const uint32_t* ent, const uint32_t* off,
+int launch_accum_g2(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const MsmTabs& tabs, const uint32_t* ent, const uint32_t* off,
                     XYZZ<Fp2>* buckets, XYZZ<Fp2>* slot_pt, int32_t* slot_bid, uint8_t* slot_fl);
 template <>
-inline int launch_accum<Fp2>(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const Affine<Fp2>* tab, const uint32_t* ent,
+inline int launch_accum<Fp2>(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const MsmTabs& tabs, const uint32_t* ent,
                              const uint32_t* off, XYZZ<Fp2>* buckets, XYZZ<Fp2>* slot_pt, int32_t* slot_bid, uint8_t* slot_fl) {
-  return launch_accum_g2(st, T1, nb, L, tab, ent, off, buckets, slot_pt, slot_bid, slot_fl);
+  return launch_accum_g2(st, T1, nb, L, tabs, ent, off, buckets, slot_pt, slot_bid, slot_fl);
 }
 
 // Launches tail kernel K over `items` work items: a team of four lanes per item when the grid is small
@@ -681,14 +647,17 @@ inline int launch_coop(bool team, ps_stream_t st, size_t items, Args... args) {
   return ps_launch<K<F, false>>(st, items, args...);
 }
 
+// Runs the pipeline for a batch (plan + per-output tables); the nsets results (XYZZ) go to d_out[0..nsets).
 template <class F>
-int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scalars, int mont, XYZZ<F>* d_out) {
+int msm_run_batch(ps_ctx* ctx, const MsmPlan& g, const MsmTabs& tabs, XYZZ<F>* d_out) {
   ps_stream_t st = ctx->stream;
   Arena& ar = ctx->arena;
-  if (g.n == 0) return dev_memset(d_out, 0, sizeof(XYZZ<F>), st);
-  const uint32_t nb = (uint32_t)g.S * g.D;
-  const size_t max_ent = (size_t)g.n * g.W;
-  if (max_ent >= 0xFFFFFFFFull) return PS_ERR_UNSUPPORTED;
+  if (g.nsets < 1 || g.nsets > MSM_MAX_SEG || g.nseg < 0 || g.nseg > MSM_MAX_SEG) return PS_ERR_ARG;
+  if (g.total == 0) return dev_memset(d_out, 0, (size_t)g.nsets * sizeof(XYZZ<F>), st);
+  const int S_all = g.nsets * g.S;                 // bucket sets of the whole batch
+  const uint32_t nb = (uint32_t)S_all * g.D;
+  const size_t max_ent = (size_t)g.total * g.W;
+  if (max_ent >= 0xFFFFFFFFull || (uint64_t)S_all * g.D >= 0x7FFFFFFFull) return PS_ERR_UNSUPPORTED;
 
   // entries per accumulate thread.  Target L0: about one average bucket or more, so that a bucket spans
   // at most two or three threads (few boundary partials, short merge runs); twice that when the input
@@ -723,7 +692,7 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   PS_TRY(ctx_event(ctx, 0));
   PS_TRY(dev_memset(count, 0, ((size_t)nb + 1) * 4, st));
   PS_TRY(dev_memset(buckets, 0, (size_t)nb * sizeof(XYZZ<F>), st));
-  PS_LAUNCH(MsmCountK, st, g.n, g, d_scalars, mont, count, ranks);
+  PS_LAUNCH(MsmCountK, st, g.total, g, count, ranks);
   PS_TRY(exclusive_scan_u32(st, count, off, tile_sums, nb + 1));
   // scatter: one pass while the entry array fits in L2, two passes through a partitioned staging array above
   // (option msm_scatter: 0 = always one pass, 1 = automatic, 2 = two passes whenever W <= 16)
@@ -736,22 +705,19 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
     uint32_t* staging = ar.take<uint32_t>(2 * ((size_t)nparts << shift));
     if (!part_count || !staging) return PS_ERR_ALLOC;
     PS_TRY(dev_memset(part_count, 0, (size_t)nparts * 4, st));
-    PS_TRY(scatter_stage(st, g, d_scalars, mont, off, ranks, part_count, staging, shift, nparts));
+    PS_TRY(scatter_stage(st, g, off, ranks, part_count, staging, shift, nparts));
     PS_LAUNCH(MsmStageScatterK, st, (size_t)nparts << shift, shift, (const uint32_t*)part_count, (const uint32_t*)staging, ent);
   } else {
-    PS_LAUNCH(MsmScatterK, st, g.n, g, d_scalars, mont, (const uint32_t*)off, (const uint32_t*)ranks, ent);
+    PS_LAUNCH(MsmScatterK, st, g.total, g, (const uint32_t*)off, (const uint32_t*)ranks, ent);
   }
   PS_TRY(ctx_event(ctx, 1));
-  if (ctx->accum_mode == 1) {
-    PS_TRY(msm_accumulate_affine<F>(ctx, nb, max_ent, tab, ent, off, buckets));
-    PS_TRY(ctx_event(ctx, 2));
-  } else {
+  {
     size_t slots_a = 2 * T1, slots_b = 2 * ((slots_a + CF - 1) / CF);
     XYZZ<F>* sp[2] = {ar.take<XYZZ<F>>(slots_a), ar.take<XYZZ<F>>(slots_b)};
     int32_t* sb[2] = {ar.take<int32_t>(slots_a), ar.take<int32_t>(slots_b)};
     uint8_t* sf[2] = {ar.take<uint8_t>(slots_a), ar.take<uint8_t>(slots_b)};
     if (!sp[0] || !sp[1] || !sb[0] || !sb[1] || !sf[0] || !sf[1]) return PS_ERR_ALLOC;
-    PS_TRY((launch_accum<F>(st, T1, nb, L, tab, ent, off, buckets, sp[0], sb[0], sf[0])));
+    PS_TRY((launch_accum<F>(st, T1, nb, L, tabs, ent, off, buckets, sp[0], sb[0], sf[0])));
     PS_TRY(ctx_event(ctx, 2));
     PS_TRY((launch_coop<MsmRunMergeK, F>(team, st, T1, (uint32_t)T1, buckets, sp[0], sb[0], (const uint8_t*)sf[0])));
     {
@@ -773,13 +739,13 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
   {
     // first level: group size a power of two, about 128K threads
     uint32_t gsz = 1;
-    while ((uint64_t)g.S * (g.D / gsz) > 131072 && gsz < g.D) gsz <<= 1;
+    while ((uint64_t)S_all * (g.D / gsz) > 131072 && gsz < g.D) gsz <<= 1;
     if (gsz < 2 && g.D >= 2) gsz = 2;
     if (gsz > g.D) gsz = g.D;
     uint32_t G = g.D / gsz;
-    size_t e0 = (size_t)g.S * G;
-    XYZZ<F>* accv[2] = {ar.take<XYZZ<F>>(e0), ar.take<XYZZ<F>>(e0 / 2 + g.S)};
-    XYZZ<F>* runv[2] = {ar.take<XYZZ<F>>(e0), ar.take<XYZZ<F>>(e0 / 2 + g.S)};
+    size_t e0 = (size_t)S_all * G;
+    XYZZ<F>* accv[2] = {ar.take<XYZZ<F>>(e0), ar.take<XYZZ<F>>(e0 / 2 + S_all)};
+    XYZZ<F>* runv[2] = {ar.take<XYZZ<F>>(e0), ar.take<XYZZ<F>>(e0 / 2 + S_all)};
     if (!accv[0] || !accv[1] || !runv[0] || !runv[1]) return PS_ERR_ALLOC;
     PS_TRY((launch_coop<MsmReduceFirstK, F>(team && e0 <= 32768, st, e0, g.D, G, gsz, (const XYZZ<F>*)buckets, accv[0], runv[0])));
     uint32_t n_in = G;
@@ -789,7 +755,7 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
     // a few 4-way weighted merges while plenty of elements remain (work-bound levels)
     while (n_in > 8192) {
       uint32_t f = 4, n_out = n_in / f;
-      PS_TRY((launch_coop<MsmReduceK, F>(team, st, (size_t)g.S * n_out, n_in, n_out, f, log_len, (const XYZZ<F>*)accv[cur],
+      PS_TRY((launch_coop<MsmReduceK, F>(team, st, (size_t)S_all * n_out, n_in, n_out, f, log_len, (const XYZZ<F>*)accv[cur],
                                          (const XYZZ<F>*)runv[cur], accv[cur ^ 1], runv[cur ^ 1])));
       log_len += 2;
       n_in = n_out;
@@ -801,9 +767,9 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
       int gb = 0;
       while ((1u << gb) < n_in) gb++;
       const uint32_t half = n_in / 2;
-      size_t rows = (size_t)g.S * (gb + 1);
+      size_t rows = (size_t)S_all * (gb + 1);
       XYZZ<F>* Y[2] = {ar.take<XYZZ<F>>(rows * half), ar.take<XYZZ<F>>(rows * (half / 2 + 1))};
-      XYZZ<F>* set_out = ar.take<XYZZ<F>>(g.S);
+      XYZZ<F>* set_out = ar.take<XYZZ<F>>(S_all);
       if (!Y[0] || !Y[1] || !set_out) return PS_ERR_ALLOC;
       PS_TRY((launch_coop<MsmBitGatherK, F>(team, st, rows * half, n_in, gb, (const XYZZ<F>*)accv[cur], (const XYZZ<F>*)runv[cur], Y[0])));
       int yc = 0;
@@ -811,10 +777,10 @@ int msm_run(ps_ctx* ctx, MsmGeom g, const Affine<F>* tab, const uint32_t* d_scal
         PS_TRY((launch_coop<MsmPairSumK, F>(team, st, rows * (w / 2), w, (const XYZZ<F>*)Y[yc], Y[yc ^ 1])));
         yc ^= 1;
       }
-      PS_TRY((launch_coop<MsmBitFinalK, F>(team, st, (size_t)g.S, gb, log_len, (const XYZZ<F>*)Y[yc], set_out)));
+      PS_TRY((launch_coop<MsmBitFinalK, F>(team, st, (size_t)S_all, gb, log_len, (const XYZZ<F>*)Y[yc], set_out)));
       sets = set_out;
     }
-    PS_TRY((launch_coop<MsmFinalK, F>(team, st, 1, g.S, g.c * g.T, (const XYZZ<F>*)sets, d_out)));
+    PS_TRY((launch_coop<MsmFinalK, F>(team, st, (size_t)g.nsets, g.S, g.c * g.T, (const XYZZ<F>*)sets, d_out)));
   }
   PS_TRY(ctx_event(ctx, 4));
   ctx->ev_valid = true;

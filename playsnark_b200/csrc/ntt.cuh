@@ -7,7 +7,7 @@
 // between them; each launch fuses R <= 3 butterfly stages in registers (2^R elements per thread).
 // omega_n = 7^((r-1)/n); Fr has 2-adicity 32.
 #pragma once
-#include "backend.cuh"
+#include "context.cuh"
 
 namespace ps {
 
@@ -219,16 +219,9 @@ inline int ntt_inverse_unscaled(ps_stream_t st, Fr* a, int log_n, const Fr* tw_i
   return ntt_inverse_blocks_unscaled(st, a, (size_t)1 << log_n, log_n, tw_inv, 1u << log_n);
 }
 
-// Twiddle tables for one transform size, resident on the device.
-struct NttTables {
-  int log_n = -1;
-  Fr* tw = nullptr;      // omega^i, i < max(n/2, 1)
-  Fr* tw_inv = nullptr;  // omega^-i
-  void release() { dev_free(tw); dev_free(tw_inv); tw = tw_inv = nullptr; log_n = -1; }
-};
 inline int ntt_tables_build(ps_stream_t st, int log_n, NttTables* t) {
   if (log_n < 0 || log_n > 30) return PS_ERR_ARG;
-  t->log_n = log_n;
+  t->release();
   size_t half = log_n ? (size_t)1 << (log_n - 1) : 1;
   PS_TRY(dev_alloc((void**)&t->tw, half * sizeof(Fr)));
   PS_TRY(dev_alloc((void**)&t->tw_inv, half * sizeof(Fr)));
@@ -236,6 +229,7 @@ inline int ntt_tables_build(ps_stream_t st, int log_n, NttTables* t) {
   Fr wi = fr_host_pow(w, ((uint64_t)1 << log_n) - 1);  // w^-1 = w^(n-1)
   PS_LAUNCH(FrPowTableK, st, half, w, Fr::one(), t->tw);
   PS_LAUNCH(FrPowTableK, st, half, wi, Fr::one(), t->tw_inv);
+  t->log_n = log_n;   // only a completely built entry is marked valid
   return PS_OK;
 }
 

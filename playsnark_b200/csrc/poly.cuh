@@ -13,20 +13,8 @@
 // fails if one of the values is zero (never for the sizes in use: it needs g*omega^k in {1..n}).
 // The result h has exactly n-1 coefficients, as Div2 produces (algebra.go:140-159).
 #pragma once
-#include "context.cuh"
-
-struct ps_qap {
-  size_t n = 0, m = 0, n_io = 0;  // gates, variables, IO count
-  int log_np = 0;                 // n' = 2^log_np >= n (transform size)
-  bool dense = true;
-  ps::Fr *left = nullptr, *right = nullptr, *out = nullptr;  // m x n, Montgomery (dense form)
-  ps::NttTables tabs;
-  ps::Fr* gpow = nullptr;       // g^k, k < n'
-  ps::Fr* ginv_pow = nullptr;   // g^-k / n'
-  ps::Fr* zinv_coset = nullptr; // 1 / z(g * omega^k), bit-reversed order
-  ps::Fr* z_plain = nullptr;    // z(omega^k), bit-reversed order
-  void* sparse = nullptr;       // ps::SparseQap* when built from a sparse R1CS (interp.cuh)
-};
+#include "poly_api.cuh"
+#include "ntt.cuh"
 
 namespace ps {
 

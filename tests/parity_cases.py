@@ -131,6 +131,31 @@ def msm_errors(be):
     # empty MSM = identity
     empty = be.load_bases(L.PS_G1, b"")
     assert be.msm(empty, []) == O.g1_compress(None)
+    # points ON the curve but outside the prime-order subgroup are rejected at load, as kilic's
+    # FromCompressed does for the reference's keys (the MSM's k -> r-k folding relies on r*P = O)
+    for group, F, comp in ((L.PS_G1, O.F1, O.g1_compress), (L.PS_G2, O.F2, O.g2_compress)):
+        x = 1
+        while True:
+            x += 1
+            xx = x if group == L.PS_G1 else (x, 1)
+            rhs = F.add(F.mul(F.sqr(xx), xx), F.b)
+            y = O.fp_sqrt(rhs) if group == L.PS_G1 else O.fp2_sqrt(rhs)
+            if y is not None and not O.in_subgroup(F, (xx, y)):
+                break
+        enc = comp((xx, y))
+        with pytest.raises(api.L.PlaysnarkError) as e:
+            be.load_bases(group, [enc])
+        assert e.value.status == L.PS_ERR_ENCODING
+        be.set_option("subgroup_check", 0)       # a caller that vouches for its key may skip the check
+        try:
+            assert be.load_bases(group, [enc]).export() == [enc]
+        finally:
+            be.set_option("subgroup_check", 1)
+    # non-canonical encodings of infinity
+    for bad in (bytes([0xC0]) + bytes(46) + b"\x01", bytes([0xE0]) + bytes(47)):
+        with pytest.raises(api.L.PlaysnarkError) as e:
+            be.load_bases(L.PS_G1, [bad])
+        assert e.value.status == L.PS_ERR_ENCODING
 
 
 def codec_roundtrip(be, n=24):

@@ -78,19 +78,6 @@ def test_config_c2_shape_small(be): P.config_c2(be, n=16)
 def test_readme_flow_through_api(be): P.readme_flow_through_api(be)
 
 
-def test_msm_batched_affine_option(be):
-    """the alternative bucket accumulation (batched affine tree rounds, csrc/msm_affine.cuh) gives the same points"""
-    be.set_option("msm_accumulate", 1)
-    try:
-        P.msm_golden(be)
-        for kind in ("rand", "ones", "small", "edge"):
-            P.msm_exponent_check(be, L.PS_G1, 60, kind)
-        P.msm_exponent_check(be, L.PS_G2, 15, "rand")
-        P.readme_groth16(be)
-    finally:
-        be.set_option("msm_accumulate", 0)
-
-
 def test_sparse_phgr13_exponent_check(be): P.phgr13_sparse_exponent_check(be, 4, seed=11)
 
 

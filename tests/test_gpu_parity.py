@@ -139,19 +139,6 @@ def test_config_c2_dense_2p10(be):
 def test_readme_flow_through_api(be): P.readme_flow_through_api(be)
 
 
-def test_msm_batched_affine_option(be):
-    """the alternative bucket accumulation (batched affine tree rounds, csrc/msm_affine.cuh) gives the same points"""
-    be.set_option("msm_accumulate", 1)
-    try:
-        P.msm_golden(be)
-        for kind in ("rand", "ones", "small", "edge"):
-            P.msm_exponent_check(be, L.PS_G1, 4000, kind)
-        P.msm_exponent_check(be, L.PS_G2, 700, "rand")
-        P.readme_groth16(be)
-    finally:
-        be.set_option("msm_accumulate", 0)
-
-
 @pytest.mark.parametrize("log_n,parts,world", [(6, 1, 2), (10, 4, 8), (14, 2, 3)])
 def test_sharded_steps_recombine(be, log_n, parts, world):
     # every entry point of the multi-GPU Groth16 flow, recombined on one GPU against ps_g16_prove
