@@ -219,6 +219,52 @@ void ps_phgr13_key_free(ps_phgr13_key* key);
 int ps_phgr13_prove(ps_ctx* ctx, const ps_phgr13_key* key, const ps_qap* qap, const uint8_t* witness_be,
                     uint8_t* out432, uint8_t* out_h);
 
+/* ---- several GPUs behind ONE call ------------------------------------------------------------------------------
+ * A ps_mctx owns one context and one worker thread per listed device of this box.  A multi-GPU call does the
+ * whole choreography inside the library: the devices exchange data over NVLink peer memory (no NCCL, no second
+ * process), so a Go caller of Groth16Prove (groth16.go:122) makes exactly one cgo call per proof.
+ * Keys are SHARDED: each device holds its index ranges of Xi, Xi2, XiT, NioLP (with all window tables); the
+ * sparse QAP is replicated.  ps_mctx_set_option forwards ps_ctx options to every device; in addition
+ * "rank0_share_percent" = MSM share of device 0 relative to the others (it also divides; 0 = automatic).   */
+typedef struct ps_mctx ps_mctx;
+typedef struct ps_mbases ps_mbases;
+typedef struct ps_mqap ps_mqap;
+typedef struct ps_mg16_key ps_mg16_key;
+int ps_mctx_create(const int* devices, int ndev, ps_mctx** out);
+void ps_mctx_destroy(ps_mctx* m);
+int ps_mctx_size(const ps_mctx* m);
+ps_ctx* ps_mctx_ctx(ps_mctx* m, int i);           /* the context of device i, for single-device calls */
+int ps_mctx_set_option(ps_mctx* m, const char* name, int value);
+/* MSM with the bases sharded by point range: every device sums its range, the partial points are
+ * pushed to device 0 and added there.  Same contract as ps_bases_load / ps_bases_from_scalars / ps_msm.     */
+int ps_mbases_load(ps_mctx* m, int group, const uint8_t* points, size_t n, int format, int window_bits,
+                   int precompute_tables, ps_mbases** out);
+int ps_mbases_from_scalars(ps_mctx* m, int group, const uint8_t* scalars_be, size_t n, int window_bits,
+                           int precompute_tables, ps_mbases** out);
+size_t ps_mbases_len(const ps_mbases* b);
+void ps_mbases_free(ps_mbases* b);
+int ps_mmsm(ps_mctx* m, const ps_mbases* b, const uint8_t* scalars_be, size_t n, uint8_t* out);
+/* Groth16: same arguments as ps_g16_key_load / ps_qap_load_r1cs / ps_qap_load_dense / ps_g16_prove.
+ * With 2 * 2^j devices and a sparse QAP the whole proof is pipelined over the devices (interpolation split by
+ * subtree, MSM shards overlapped with the division); otherwise device 0 runs the quotient and every device
+ * its MSM shards.                                                                                           */
+int ps_mg16_key_load(ps_mctx* m, size_t n_gates, size_t n_nio, int format, const uint8_t* xi, const uint8_t* xi2,
+                     const uint8_t* xit, const uint8_t* niolp, const uint8_t* alpha, const uint8_t* beta,
+                     const uint8_t* delta, const uint8_t* beta2, const uint8_t* delta2, ps_mg16_key** key);
+void ps_mg16_key_free(ps_mg16_key* key);
+int ps_mqap_load_r1cs(ps_mctx* m, size_t n_gates, size_t n_vars, size_t n_io,
+                      const uint32_t* l_row_ptr, const uint32_t* l_col, const uint8_t* l_val,
+                      const uint32_t* r_row_ptr, const uint32_t* r_col, const uint8_t* r_val,
+                      const uint32_t* o_row_ptr, const uint32_t* o_col, const uint8_t* o_val, ps_mqap** qap);
+int ps_mqap_load_dense(ps_mctx* m, size_t n_gates, size_t n_vars, size_t n_io, const uint8_t* left,
+                       const uint8_t* right, const uint8_t* out, const uint8_t* z, ps_mqap** qap);
+void ps_mqap_free(ps_mqap* qap);
+int ps_mg16_prove(ps_mctx* m, const ps_mg16_key* key, const ps_mqap* qap, const uint8_t* witness_be,
+                  const uint8_t* r_be, const uint8_t* s_be, uint8_t* outA, uint8_t* outB, uint8_t* outC);
+/* stage marks of the last ps_mg16_prove on device `dev` (CUDA events on its stream): out_ms[k] = ms from the
+ * start of the call's device work to mark k + 1; *count = values written                                    */
+int ps_mg16_last_timeline(ps_mctx* m, int dev, float* out_ms, int max, int* count);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------------- */
 /* Integer-multiply pipe microbenchmark: variant 0 = IMAD (mad.lo), 1 = IMAD.HI, 2 = IMAD.WIDE
  * (independent), 3 = IMAD.WIDE.X carry chains as in the field multiplier; returns instructions/s
@@ -230,8 +276,8 @@ int ps_bench_fieldmul(ps_ctx* ctx, int field, int iters, double* mul_per_s, doub
  * [0] digits+sort, [1] bucket-accumulate kernel, [2] partial merge, [3] bucket reduce, [4] total */
 int ps_last_msm_timing(ps_ctx* ctx, float out_ms[5]);
 /* device time in ms of the last ps_g16_prove: [0] quotient (aggregate / interpolation / NTT division),
- * [1] MSM A (G1), [2] MSM C (G1), [3] normalise + encode A and C, [4] what then remains of MSM B and its
- * encoding (G2, concurrently on a second stream), [5] total                                      */
+ * [1] MSMs A and C (G1, one batched pipeline), [2] 0 (kept for layout), [3] normalise + encode A and C, [4] what
+ * then remains of MSM B and its encoding (G2, concurrently on a second stream), [5] total          */
 int ps_last_prove_timing(ps_ctx* ctx, float out_ms[6]);
 
 #ifdef __cplusplus

@@ -65,6 +65,23 @@ SYMBOLS = [
     ("ps_phgr13_key_load", _I, [_P, _SZ, _SZ, _I] + [_B] * 10 + [C.POINTER(_P)]),
     ("ps_phgr13_key_free", None, [_P]),
     ("ps_phgr13_prove", _I, [_P, _P, _P, _P, _P, _P]),
+    ("ps_mctx_create", _I, [C.POINTER(C.c_int), _I, C.POINTER(_P)]),
+    ("ps_mctx_destroy", None, [_P]),
+    ("ps_mctx_size", _I, [_P]),
+    ("ps_mctx_ctx", _P, [_P, _I]),
+    ("ps_mctx_set_option", _I, [_P, C.c_char_p, _I]),
+    ("ps_mbases_load", _I, [_P, _I, _P, _SZ, _I, _I, _I, C.POINTER(_P)]),
+    ("ps_mbases_from_scalars", _I, [_P, _I, _P, _SZ, _I, _I, C.POINTER(_P)]),
+    ("ps_mbases_len", _SZ, [_P]),
+    ("ps_mbases_free", None, [_P]),
+    ("ps_mmsm", _I, [_P, _P, _P, _SZ, _P]),
+    ("ps_mg16_key_load", _I, [_P, _SZ, _SZ, _I] + [_B] * 9 + [C.POINTER(_P)]),
+    ("ps_mg16_key_free", None, [_P]),
+    ("ps_mqap_load_r1cs", _I, [_P, _SZ, _SZ, _SZ] + [_P] * 9 + [C.POINTER(_P)]),
+    ("ps_mqap_load_dense", _I, [_P, _SZ, _SZ, _SZ, _B, _B, _B, _B, C.POINTER(_P)]),
+    ("ps_mqap_free", None, [_P]),
+    ("ps_mg16_prove", _I, [_P, _P, _P, _P, _B, _B, _P, _P, _P]),
+    ("ps_mg16_last_timeline", _I, [_P, _I, C.POINTER(C.c_float), _I, C.POINTER(C.c_int)]),
     ("ps_bench_intpipe", _I, [_P, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("ps_bench_fieldmul", _I, [_P, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("ps_last_msm_timing", _I, [_P, C.POINTER(C.c_float)]),

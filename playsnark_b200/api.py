@@ -76,6 +76,44 @@ def _count(x, per: int) -> int:
     return len(x) // per if isinstance(x, (bytes, bytearray, memoryview)) else len(x)
 
 
+class _DevHandle:
+    """Owner of a resident device object (QAP, proving key): freed on close() / garbage collection, and when the
+    host object is made resident on another backend."""
+
+    def __init__(self, backend, handle, free_name: str):
+        self.backend, self.handle, self._free = backend, handle, getattr(backend.lib, free_name)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _resident_handle(obj, backend, build, free_name: str):
+    """obj._dev caches one _DevHandle; a different backend frees the old handle first"""
+    dev = getattr(obj, "_dev", None)
+    if dev is not None and dev.backend is backend and dev.handle:
+        return dev.handle
+    if dev is not None:
+        dev.close()
+    obj._dev = _DevHandle(backend, build(), free_name)
+    return obj._dev.handle
+
+
+def _release(obj):
+    """frees the device copy of a QAP / key object (it is rebuilt on the next use)"""
+    dev = getattr(obj, "_dev", None)
+    if dev is not None:
+        dev.close()
+        obj._dev = None
+
+
 class Bases:
     """Device-resident []Commit (the blindedPoint argument of BlindEval)."""
 
@@ -107,6 +145,8 @@ class Bases:
 
 class Backend:
     """One context per process and GPU (ps_ctx)."""
+
+    multi = False
 
     def __init__(self, device: int = 0, lib=None):
         self.lib = lib if lib is not None else L.load()
@@ -180,6 +220,88 @@ class Backend:
         cz = None if coset is None else (coset % R).to_bytes(32, "big")
         self._check(self.lib.ps_ntt_fr(self.ctx, buf, log_n, 1 if inverse else 0, cz))
         return _fr_list(buf.raw)
+
+
+class MultiBases:
+    """[]Commit sharded by point range over the devices of a MultiBackend"""
+
+    def __init__(self, backend, handle, group):
+        self.backend, self.handle, self.group = backend, handle, group
+
+    def __len__(self):
+        return self.backend.lib.ps_mbases_len(self.handle)
+
+    def close(self):
+        if self.handle:
+            self.backend.lib.ps_mbases_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiBackend:
+    """Several GPUs of one box behind one handle (ps_mctx): Groth16Prove(tr, q, sol, backend=MultiBackend([0..7]))
+    is ONE library call; keys are sharded over the devices, the sparse QAP is replicated."""
+    multi = True
+
+    def __init__(self, devices: Sequence[int], lib=None):
+        self.lib = lib if lib is not None else L.load()
+        devs = (C.c_int * len(devices))(*devices)
+        ctx = C.c_void_p()
+        L.check(self.lib, self.lib.ps_mctx_create(devs, len(devices), C.byref(ctx)))
+        self.ctx = ctx
+        self.devices = list(devices)
+
+    def _check(self, status):
+        L.check(self.lib, status)
+
+    def __len__(self):
+        return len(self.devices)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.ps_mctx_destroy(self.ctx)
+            self.ctx = None
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.ps_mctx_set_option(self.ctx, name.encode(), value))
+
+    def launch_count(self) -> int:
+        return int(self.lib.ps_launch_count())
+
+    def bases_from_scalars(self, group: int, scalars, window_bits: int = 0, tables: int = 1) -> MultiBases:
+        buf = scalars if isinstance(scalars, (bytes, bytearray)) else _fr_bytes(scalars)
+        h = C.c_void_p()
+        self._check(self.lib.ps_mbases_from_scalars(self.ctx, group, bytes(buf), len(buf) // 32, window_bits, tables, C.byref(h)))
+        return MultiBases(self, h, group)
+
+    def load_bases(self, group: int, points, fmt: int = L.PS_FMT_COMPRESSED, window_bits: int = 0, tables: int = 1) -> MultiBases:
+        per = {(1, 0): 48, (1, 1): 96, (2, 0): 96, (2, 1): 192}[(group, fmt)]
+        buf = points if isinstance(points, (bytes, bytearray)) else b"".join(points)
+        h = C.c_void_p()
+        self._check(self.lib.ps_mbases_load(self.ctx, group, bytes(buf), len(buf) // per, fmt, window_bits, tables, C.byref(h)))
+        return MultiBases(self, h, group)
+
+    def msm(self, bases: MultiBases, scalars) -> bytes:
+        buf = scalars if isinstance(scalars, (bytes, bytearray)) else _fr_bytes(scalars)
+        n = len(buf) // 32 if not isinstance(buf, C.c_void_p) else len(scalars)
+        out = C.create_string_buffer(48 if bases.group == L.PS_G1 else 96)
+        st = self.lib.ps_mmsm(self.ctx, bases.handle, buf if isinstance(buf, C.c_void_p) else bytes(buf), n, out)
+        if st == L.PS_ERR_LENGTH:
+            raise ValueError("mismatch of length between poly %d and blinded eval points %d" % (n, len(bases)))
+        self._check(st)
+        return out.raw
+
+    def timeline(self, dev: int = 0):
+        """stage marks (ms since the start) of the last Groth16 proof on device `dev`"""
+        buf = (C.c_float * 16)()
+        cnt = C.c_int()
+        self._check(self.lib.ps_mg16_last_timeline(self.ctx, dev, buf, 16, C.byref(cnt)))
+        return [buf[i] for i in range(cnt.value)]
 
 
 _default: Optional[Backend] = None
@@ -290,7 +412,7 @@ class QAP:
     _dev: object = None
 
     def _resident(self, backend: Backend):
-        if self._dev is None or self._dev[0] is not backend:
+        def build():
             n, m = self.nbGates, self.nbVars
             if len(self.left) != m or len(self.right) != m or len(self.out) != m:
                 raise ValueError("different number of solution variables than polynomials")
@@ -302,10 +424,14 @@ class QAP:
                 raise ValueError("z must have nbGates+1 coefficients")
             h = C.c_void_p()
             flat = lambda polys: b"".join(_fr_bytes(p) for p in polys)
-            backend._check(backend.lib.ps_qap_load_dense(backend.ctx, n, m, self.nbIO, flat(self.left), flat(self.right),
-                                                         flat(self.out), _fr_bytes(self.z), C.byref(h)))
-            self._dev = (backend, h)
-        return self._dev[1]
+            load = backend.lib.ps_mqap_load_dense if backend.multi else backend.lib.ps_qap_load_dense
+            backend._check(load(backend.ctx, n, m, self.nbIO, flat(self.left), flat(self.right), flat(self.out), _fr_bytes(self.z),
+                                C.byref(h)))
+            return h
+        return _resident_handle(self, backend, build, "ps_mqap_free" if backend.multi else "ps_qap_free")
+
+    def close(self):
+        _release(self)
 
     def Quotient(self, sol: Vector, backend: Optional[Backend] = None) -> Poly:
         return Quotient(self, sol, backend)
@@ -340,8 +466,7 @@ class SparseQAP:
         return SparseQAP(nbVars, nbIO, len(left), csr(left), csr(right), csr(out))
 
     def _resident(self, backend: Backend):
-        if self._dev is None or self._dev[0] is not backend:
-            import array
+        def build():
             h = C.c_void_p()
             keep, args = [], []
             for rp, col, val in (self.left, self.right, self.out):
@@ -352,9 +477,13 @@ class SparseQAP:
                 b_val = _fr_bytes(val) or b"\0"
                 keep += [a_rp, a_col, b_val]
                 args += [C.cast(a_rp, C.c_void_p), C.cast(a_col, C.c_void_p), C.cast(C.c_char_p(b_val), C.c_void_p)]
-            backend._check(backend.lib.ps_qap_load_r1cs(backend.ctx, self.nbGates, self.nbVars, self.nbIO, *args, C.byref(h)))
-            self._dev = (backend, h)
-        return self._dev[1]
+            load = backend.lib.ps_mqap_load_r1cs if backend.multi else backend.lib.ps_qap_load_r1cs
+            backend._check(load(backend.ctx, self.nbGates, self.nbVars, self.nbIO, *args, C.byref(h)))
+            return h
+        return _resident_handle(self, backend, build, "ps_mqap_free" if backend.multi else "ps_qap_free")
+
+    def close(self):
+        _release(self)
 
     def Quotient(self, sol: Vector, backend: Optional[Backend] = None) -> Poly:
         return Quotient(self, sol, backend)
@@ -405,18 +534,22 @@ class Groth16Setup:
     _dev: object = None
 
     def _resident(self, backend: Backend):
-        if self._dev is None or self._dev[0] is not backend:
+        def build():
             g1b, g2b = (48, 96) if self.fmt == L.PS_FMT_COMPRESSED else (96, 192)
             n = _count(self.Xi, g1b)
             if _count(self.Xi2, g2b) != n or _count(self.XiT, g1b) != n - 1:
                 raise ValueError("mismatch of length between poly and blinded eval points")
             h = C.c_void_p()
             j = _join
-            backend._check(backend.lib.ps_g16_key_load(
+            load = backend.lib.ps_mg16_key_load if backend.multi else backend.lib.ps_g16_key_load
+            backend._check(load(
                 backend.ctx, n, _count(self.NioLP, g1b), self.fmt, j(self.Xi), j(self.Xi2), j(self.XiT), j(self.NioLP) or b"\0",
                 self.Alpha, self.Beta, self.Delta, self.Beta2, self.Delta2, C.byref(h)))
-            self._dev = (backend, h)
-        return self._dev[1]
+            return h
+        return _resident_handle(self, backend, build, "ps_mg16_key_free" if backend.multi else "ps_g16_key_free")
+
+    def close(self):
+        _release(self)
 
 
 @dataclass
@@ -447,7 +580,12 @@ def Groth16Prove(tr: Groth16Setup, q: QAP, sol: Vector, r: Optional[int] = None,
     kh, qh = tr._resident(b), q._resident(b)
     A, Bp, Cp = C.create_string_buffer(48), C.create_string_buffer(96), C.create_string_buffer(48)
     hb = C.create_string_buffer(max(1, (q.nbGates - 1) * 32)) if want_h else None
-    st = b.lib.ps_g16_prove(b.ctx, kh, qh, _fr_bytes(sol), _fr_bytes([r]), _fr_bytes([s]), A, Bp, Cp, hb)
+    if b.multi:
+        if want_h:
+            raise ValueError("want_h is a single-device debugging output")
+        st = b.lib.ps_mg16_prove(b.ctx, kh, qh, _fr_bytes(sol), _fr_bytes([r]), _fr_bytes([s]), A, Bp, Cp)
+    else:
+        st = b.lib.ps_g16_prove(b.ctx, kh, qh, _fr_bytes(sol), _fr_bytes([r]), _fr_bytes([s]), A, Bp, Cp, hb)
     if st == L.PS_ERR_REMAINDER:
         raise ArithmeticError("apocalypse")
     if st == L.PS_ERR_LENGTH:
@@ -473,14 +611,17 @@ class PHGR13EvalKey:
     _dev: object = None
 
     def _resident(self, backend: Backend):
-        if self._dev is None or self._dev[0] is not backend:
+        def build():
             h = C.c_void_p()
             j = b"".join
             backend._check(backend.lib.ps_phgr13_key_load(
                 backend.ctx, len(self.gsi) + 1, len(self.vs), L.PS_FMT_COMPRESSED, j(self.gsi), j(self.vs), j(self.ws),
                 j(self.ys), j(self.vas), j(self.was), j(self.yas), j(self.vbs), j(self.wbs), j(self.ybs), C.byref(h)))
-            self._dev = (backend, h)
-        return self._dev[1]
+            return h
+        return _resident_handle(self, backend, build, "ps_phgr13_key_free")
+
+    def close(self):
+        _release(self)
 
 
 @dataclass

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <vector>
 
 #include "../../include/playsnark_b200.h"
@@ -70,7 +71,7 @@ PS_DEV void ps_atomic_max(uint32_t* p, uint32_t v) {
 #endif
 }
 
-inline uint64_t& launch_counter() { static uint64_t c = 0; return c; }
+inline std::atomic<uint64_t>& launch_counter() { static std::atomic<uint64_t> c{0}; return c; }
 
 // optional K::MIN_BLOCKS (resident blocks per SM the register allocator must allow)
 template <class K, class = void> struct MinBlocks { static constexpr int V = 1; };

@@ -5,7 +5,7 @@
 // polynomial side through poly_api.cuh (capi_poly.cu).
 #include "group_ops.cuh"
 #include "microbench.cuh"
-#include "poly_api.cuh"
+#include "multi_api.cuh"
 
 #include <new>
 
@@ -532,6 +532,69 @@ int ps_g16_prove(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const ui
   memcpy(outB, ctx->h_stage + 96, 96);
   return PS_OK;
 }
+
+extern "C++" {
+namespace ps {
+int g16_key_load_slice(ps_ctx* ctx, const KeySlice& sl, int format, int window_bits, const uint8_t* xi, const uint8_t* xi2,
+                       const uint8_t* xit, const uint8_t* niolp, const uint8_t* alpha, const uint8_t* beta, const uint8_t* delta,
+                       const uint8_t* beta2, const uint8_t* delta2, ps_g16_key** key) {
+  if (!key || sl.x_hi < sl.x_lo || sl.t_hi < sl.t_lo || sl.n_hi < sl.n_lo) return PS_ERR_ARG;
+  if (format != PS_FMT_COMPRESSED && format != PS_FMT_AFFINE) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  ps_g16_key* k = new (std::nothrow) ps_g16_key();
+  if (!k) return PS_ERR_ALLOC;
+  const size_t g1 = point_bytes(PS_G1, format), g2 = point_bytes(PS_G2, format);
+  const size_t nx = sl.x_hi - sl.x_lo, nt = sl.t_hi - sl.t_lo, nn = sl.n_hi - sl.n_lo, one = sl.consts ? 1 : 0;
+  k->n = nx; k->n_nio = nn;   // sizes of this slice (the orchestration keeps the global ones)
+  const uint8_t* pa[3] = {xi + sl.x_lo * g1, delta, alpha};
+  const size_t ca[3] = {nx, one, one};
+  const uint8_t* pb[3] = {xi2 + sl.x_lo * g2, delta2, beta2};
+  const uint8_t* pc[6] = {niolp ? niolp + sl.n_lo * g1 : niolp, xit + sl.t_lo * g1, xi + sl.x_lo * g1, alpha, beta, delta};
+  const size_t cc[6] = {nn, nt, nx, one, one, one};
+  int rc = bases_concat<Fp>(ctx, format, pa, ca, 3, window_bits, &k->A);
+  if (rc == PS_OK) rc = ctx->arena.reset();
+  if (rc == PS_OK) rc = bases_concat<Fp2>(ctx, format, pb, ca, 3, window_bits, &k->B);
+  if (rc == PS_OK) rc = ctx->arena.reset();
+  if (rc == PS_OK) rc = bases_concat<Fp>(ctx, format, pc, cc, 6, window_bits, &k->C);
+  if (rc != PS_OK) { ps_g16_key_free(k); return rc; }
+  *key = k;
+  return PS_OK;
+}
+
+int g16_slice_msm_early(ps_ctx* ctx, const ps_g16_key* key, const KeySlice& sl, const Fr* scA, const Fr* scB, const Fr* scC,
+                        void* d_partials) {
+  PS_TRY(begin_call(ctx));
+  uint8_t* out = (uint8_t*)d_partials;  // [A: 192 B | C early: 192 B | B: 384 B]
+  const size_t nx = sl.x_hi - sl.x_lo, nt = sl.t_hi - sl.t_lo, nn = sl.n_hi - sl.n_lo, k3 = sl.consts ? 3 : 0, k2 = sl.consts ? 2 : 0;
+  PS_TRY(ctx_fork(ctx));
+  ForkGuard fg(ctx);
+  {
+    SecondaryScope scope(ctx);
+    PS_TRY(msm_on_bases<Fp2>(ctx, key->B, 0, (const uint32_t*)scB, nx + k2, 0, (G2XYZZ*)(out + 384)));
+  }
+  const SegSpec segs[3] = {{key->A, 0, (const uint32_t*)scA, nx + k2, 0, 0},
+                           {key->C, 0, (const uint32_t*)scC, nn, 0, 1},
+                           {key->C, nn + nt, (const uint32_t*)(scC + nn + nt), nx + k3, 0, 1}};
+  PS_TRY(msm_batch<Fp>(ctx, segs, 3, 2, (G1XYZZ*)out));
+  return fg.join();
+}
+
+int msm_partial_host_scalars(ps_ctx* ctx, const ps_bases* b, const uint8_t* scalars_be, size_t n, void* d_out_xyzz, uint32_t** d_err_out) {
+  if (!b || n != b->n) return PS_ERR_LENGTH;
+  PS_TRY(begin_call(ctx));
+  uint32_t* d_sc = nullptr;
+  PS_TRY(stage_scalars(ctx, scalars_be, n, 0, &d_sc, d_err_out));
+  if (b->group == PS_G1) return msm_on_bases<Fp>(ctx, b, 0, d_sc, n, 0, (G1XYZZ*)d_out_xyzz);
+  return msm_on_bases<Fp2>(ctx, b, 0, d_sc, n, 0, (G2XYZZ*)d_out_xyzz);
+}
+
+int g16_slice_msm_late(ps_ctx* ctx, const ps_g16_key* key, const KeySlice& sl, const Fr* scC, void* d_partial) {
+  PS_TRY(begin_call(ctx));
+  const size_t nt = sl.t_hi - sl.t_lo, nn = sl.n_hi - sl.n_lo;
+  return msm_on_bases<Fp>(ctx, key->C, nn, (const uint32_t*)(scC + nn), nt, 0, (G1XYZZ*)d_partial);
+}
+}  // namespace ps
+}  // extern "C++"
 
 size_t ps_g16_scalar_count(const ps_g16_key* key, int which) {
   if (!key) return 0;

@@ -5,6 +5,7 @@
 // reaches them through poly_api.cuh.
 #include "codec.cuh"
 #include "interp.cuh"
+#include "multi_api.cuh"
 
 #include <new>
 
@@ -170,6 +171,33 @@ int interp_part_run(ps_ctx* ctx, const ps_qap* qap, const Fr* d_w, const uint32_
   PS_LAUNCH(StatusMergeK, st, 1, d_err, (const uint32_t*)flag, (uint32_t*)d_status);
   return PS_OK;
 }
+// dst[k] = (s a[lo + k] + r b[lo + k]) in standard form
+struct FrAxpbyStdK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t k, Fr s, const Fr* a, Fr r, const Fr* b, Fr* dst) { dst[k] = (s * a[k] + r * b[k]).from_mont(); }
+};
+
+int g16_slice_scalars(ps_ctx* ctx, const KeySlice& sl, const uint8_t* r_be, const uint8_t* s_be, const Fr* d_a, const Fr* d_b,
+                      const Fr* d_w, size_t diff, Fr* scA, Fr* scB, Fr* scC) {
+  PS_TRY(begin_call(ctx));
+  ps_stream_t st = ctx->stream;
+  Fr r, s;
+  PS_TRY(parse_fr(r_be, &r));
+  PS_TRY(parse_fr(s_be, &s));
+  const Fr rs = r * s;
+  const size_t nx = sl.x_hi - sl.x_lo, nn = sl.n_hi - sl.n_lo, nt = sl.t_hi - sl.t_lo;
+  PS_LAUNCH(FrStdCopyK, st, nx, d_a + sl.x_lo, scA);
+  PS_LAUNCH(FrStdCopyK, st, nx, d_b + sl.x_lo, scB);
+  PS_LAUNCH(FrStdCopyK, st, nn, d_w + diff + sl.n_lo, scC);
+  PS_LAUNCH(FrAxpbyStdK, st, nx, s, d_a + sl.x_lo, r, d_b + sl.x_lo, scC + nn + nt);
+  if (sl.consts) {
+    PS_LAUNCH(FrSet3K, st, 2, r.from_mont(), Fr::one().from_mont(), Fr::zero(), 2, scA + nx);
+    PS_LAUNCH(FrSet3K, st, 2, s.from_mont(), Fr::one().from_mont(), Fr::zero(), 2, scB + nx);
+    PS_LAUNCH(FrSet3K, st, 3, s.from_mont(), r.from_mont(), rs.from_mont(), 3, scC + nn + nt + nx);
+  }
+  return PS_OK;
+}
+
 }  // namespace ps
 
 extern "C" {

@@ -205,11 +205,15 @@ def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device=
     every rank sums its index range of each MSM (G2 on its second stream), the 768-byte partials are
     all-gathered and rank 0 adds and encodes.  Returns (A, B, C) compressed on rank 0, None elsewhere."""
     import torch
-    from .api import _fr_bytes
+    from .api import _fr_bytes, _sanity
     lib = be.lib
     world = dist.get_world_size() if dist is not None else 1
     rank = dist.get_rank() if dist is not None else 0
     parts = world // 2
+    # QAP.sanityCheck (qap.go:177-189) on every rank that reads the witness, BEFORE any C call or collective: the C side
+    # trusts qap->m when it reads witness bytes
+    if witness is not None and q is not None:
+        _sanity(q, witness)
     if rank0_share is None:
         # rank 0 also divides (about 1/16 of the single-GPU MSM time): its MSM share shrinks with the world
         # size so that it reaches the h broadcast together with the others; 0.4 measured best on 8 GPUs
@@ -224,8 +228,15 @@ def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device=
     status = torch.zeros(1, dtype=torch.int32, device=device)
     ptr = lambda t: C.c_void_p(t.data_ptr())
     if rank == 0:
-        status[0] = lib.ps_g16_scalars(be.ctx, kh, q._resident(be), _fr_bytes(witness), _fr_bytes([r]), _fr_bytes([s]),
-                                       ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]))
+        try:
+            status[0] = lib.ps_g16_scalars(be.ctx, kh, q._resident(be), _fr_bytes(witness), _fr_bytes([r]), _fr_bytes([s]),
+                                           ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]))
+        except Exception:
+            # the other ranks are about to enter the status broadcast: hand them an error instead of leaving them blocked
+            status[0] = L.PS_ERR_ARG
+            if world > 1:
+                dist.broadcast(status, src=0)
+            raise
     if world > 1:
         dist.broadcast(status, src=0)
     st = int(status[0])

@@ -588,3 +588,82 @@ def phgr13_sparse_exponent_check(be, log_n, seed):
     for f in O.PHGR13_FIELDS:
         assert getattr(pp, f) == want[f], f
     assert len(pp.h) == n - 1
+
+
+def multi_groth16_case(lib, be, ndev, log_n, seed, devices=None, rank0_share=None):
+    """ps_mg16_prove on `ndev` devices (one host call, key sharded, sparse QAP replicated) must return the proof
+    of ps_g16_prove on one device bit for bit; a broken witness must raise "apocalypse" from whichever device
+    owns the gate; a witness of the wrong length the sanityCheck error (qap.go:177-189)."""
+    import pytest
+    n = 1 << log_n
+    sq, wit = H.sparse_circuit(n, seed, n // 2)
+    tr, tw = H.sparse_groth16_setup(be, sq, seed)
+    smp = O.Sampler(seed + 5)
+    r, s = smp.fr(), smp.fr()
+    want = api.Groth16Prove(tr, sq, wit, r, s, backend=be)
+    A, B, Cc, _ = H.sparse_groth16_expected(sq, wit, tw, r, s)
+    assert (want.A, want.B, want.C) == (A, B, Cc)
+    sq.close(); tr.close()
+    mb = api.MultiBackend(devices if devices is not None else [0] * ndev, lib=lib)
+    try:
+        if rank0_share is not None:
+            mb.set_option("rank0_share_percent", rank0_share)
+        for _ in range(2):      # second call: workspaces and tables are reused
+            got = api.Groth16Prove(tr, sq, wit, r, s, backend=mb)
+            assert (got.A, got.B, got.C) == (A, B, Cc)
+        bad = list(wit); bad[-1] = (bad[-1] + 1) % O.R
+        with pytest.raises(ArithmeticError, match="apocalypse"):
+            api.Groth16Prove(tr, sq, bad, r, s, backend=mb)
+        with pytest.raises(ValueError):
+            api.Groth16Prove(tr, sq, wit[:-1], r, s, backend=mb)
+        got = api.Groth16Prove(tr, sq, wit, r, s, backend=mb)       # still healthy after the failed calls
+        assert (got.A, got.B, got.C) == (A, B, Cc)
+        tl = mb.timeline(0)
+    finally:
+        sq.close(); tr.close()
+        mb.close()
+    return tl
+
+
+def multi_groth16_dense_case(lib, be, ndev, devices=None):
+    """dense QAP (configs[0] / [1] shapes): the quotient runs on device 0, the MSM shards everywhere"""
+    c = O.create_r1cs(); w = O.create_witness(c); oq = O.to_qap(c)
+    smp = O.Sampler(0)
+    otr = O.groth16_setup(oq, smp)
+    r, s = smp.fr(), smp.fr()
+    want = O.groth16_prove(otr, oq, w, r, s)
+    tr, q = H.mirror_g16_setup(otr), H.mirror_qap(oq)
+    mb = api.MultiBackend(devices if devices is not None else [0] * ndev, lib=lib)
+    try:
+        got = api.Groth16Prove(tr, q, w, r, s, backend=mb)
+        assert (got.A, got.B, got.C) == (O.g1_compress(want["A"]), O.g2_compress(want["B"]), O.g1_compress(want["C"]))
+    finally:
+        q.close(); tr.close()
+        mb.close()
+
+
+def multi_msm_case(lib, ndev, group, n, devices=None, window_bits=0, tables=1):
+    import pytest
+    F, gen, comp, _ = _grp(group)
+    rng = random.Random(n * 31 + ndev)
+    ks = [rng.randrange(1, O.R) for _ in range(n)]
+    sc = [rng.randrange(O.R) for _ in range(n)]
+    mb = api.MultiBackend(devices if devices is not None else [0] * ndev, lib=lib)
+    try:
+        bases = mb.bases_from_scalars(group, ks, window_bits, tables)
+        assert len(bases) == n
+        want = comp(O.pt_mul(F, sum(k * s for k, s in zip(ks, sc)) % O.R, gen))
+        assert mb.msm(bases, sc) == want
+        with pytest.raises(ValueError):
+            mb.msm(bases, sc[:-1])
+        with pytest.raises(api.L.PlaysnarkError):
+            mb.msm(bases, b"\xff" * (32 * n))
+        # the same points through the wire format
+        single = api.Backend(0, lib=lib)
+        pts = single.bases_from_scalars(group, ks).export()
+        single.close()
+        b2 = mb.load_bases(group, pts)
+        assert mb.msm(b2, sc) == want
+        b2.close(); bases.close()
+    finally:
+        mb.close()
