@@ -145,6 +145,17 @@ int ps_g16_prove(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const ui
                  const uint8_t* r_be, const uint8_t* s_be, uint8_t* outA, uint8_t* outB, uint8_t* outC,
                  uint8_t* out_h);
 
+/* NewGroth16TrustedSetup (groth16.go:64-101, 238-264) on the device for a resident QAP, the toxic waste supplied by
+ * the caller (the shim samples it with Pick(random.New()) and keeps it in Groth16Setup.tw): toxic_be = alpha, beta,
+ * delta, x, gamma (5 x 32 B).  Produces the resident proving key; out_iolp ((n_vars - n_io) x 48 B, optional) and
+ * out_gamma (96 B, optional) receive the verifier's IoLP and Gamma, compressed.  u_i(x), v_i(x), w_i(x) come from the
+ * Lagrange basis at x (sparse QAP) or Horner (dense), the points from the fixed-base kernel.                       */
+int ps_g16_setup(ps_ctx* ctx, const ps_qap* qap, const uint8_t* toxic_be, ps_g16_key** key, uint8_t* out_iolp,
+                 uint8_t* out_gamma);
+/* the elements of a resident key as wire bytes, to fill Groth16Setup's fields (any output may be NULL) */
+int ps_g16_key_export(ps_ctx* ctx, const ps_g16_key* key, int format, uint8_t* xi, uint8_t* xi2, uint8_t* xit,
+                      uint8_t* niolp, uint8_t* alpha, uint8_t* beta, uint8_t* delta, uint8_t* beta2, uint8_t* delta2);
+
 /* Groth16 across several GPUs (one process per GPU, every process holds the key): rank 0 runs the
  * quotient and emits the scalar vectors of the proof's three MSMs (`which` 0 = A over G1, 1 = C over
  * G1, 2 = B over G2; standard-form limbs, 8 x u32 each, device memory sized by ps_g16_scalar_count);
@@ -214,6 +225,14 @@ int ps_phgr13_key_load(ps_ctx* ctx, size_t n_gates, size_t n_mid, int format, co
                        const uint8_t* was, const uint8_t* yas, const uint8_t* vbs, const uint8_t* wbs,
                        const uint8_t* ybs, ps_phgr13_key** key);
 void ps_phgr13_key_free(ps_phgr13_key* key);
+/* NewPHGR13TrustedSetup (pinochio.go:93-176) on the device: toxic_be = s, av, aw, ay, rv, rw, beta, gamma (8 x 32 B,
+ * the reference's sampling order).  Produces the resident evaluation key and, on request, the verification key,
+ * compressed: out_vk_fixed (576 B) = av (G2) | aw (G1) | ay (G2) | gamma (G2) | bgamma (G1) | bgamma2 (G2) | yts (G2);
+ * out_vk_vs / _ws / _ys = the commitments of ALL n_vars variables (48 / 96 / 48 B each).                          */
+int ps_phgr13_setup(ps_ctx* ctx, const ps_qap* qap, const uint8_t* toxic_be, ps_phgr13_key** key, uint8_t* out_vk_fixed,
+                    uint8_t* out_vk_vs, uint8_t* out_vk_ws, uint8_t* out_vk_ys);
+int ps_phgr13_key_export(ps_ctx* ctx, const ps_phgr13_key* key, int format, uint8_t* gsi, uint8_t* vs, uint8_t* ws,
+                         uint8_t* ys, uint8_t* vas, uint8_t* was, uint8_t* yas, uint8_t* vbs, uint8_t* wbs, uint8_t* ybs);
 /* PHGR13Prove (pinochio.go:207-254).  out: hs, vss, yss, vass, wass, yass, gz (7 x 48 B, in this
  * order) then wss (96 B) = 432 bytes.                                                           */
 int ps_phgr13_prove(ps_ctx* ctx, const ps_phgr13_key* key, const ps_qap* qap, const uint8_t* witness_be,

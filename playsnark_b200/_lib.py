@@ -46,6 +46,10 @@ SYMBOLS = [
     ("ps_quotient", _I, [_P, _P, _P, _P, _P]),
     ("ps_g16_key_load", _I, [_P, _SZ, _SZ, _I] + [_B] * 9 + [C.POINTER(_P)]),
     ("ps_g16_key_free", None, [_P]),
+    ("ps_g16_setup", _I, [_P, _P, _B, C.POINTER(_P), _P, _P]),
+    ("ps_g16_key_export", _I, [_P, _P, _I] + [_P] * 9),
+    ("ps_phgr13_setup", _I, [_P, _P, _B, C.POINTER(_P), _P, _P, _P, _P]),
+    ("ps_phgr13_key_export", _I, [_P, _P, _I] + [_P] * 10),
     ("ps_g16_prove", _I, [_P, _P, _P, _P, _B, _B, _P, _P, _P, _P]),
     ("ps_g16_scalar_count", _SZ, [_P, _I]),
     ("ps_g16_key_bases", _P, [_P, _I]),

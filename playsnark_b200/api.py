@@ -531,6 +531,7 @@ class Groth16Setup:
     IoLP: List[bytes] = field(default_factory=list)   # verifier side, carried for completeness
     Gamma: bytes = b""
     fmt: int = L.PS_FMT_COMPRESSED    # PS_FMT_AFFINE for bulk keys (every point field then uncompressed)
+    tw: Optional[dict] = None         # toxic waste, kept like the reference's Groth16Setup.tw (testing)
     _dev: object = None
 
     def _resident(self, backend: Backend):
@@ -550,6 +551,39 @@ class Groth16Setup:
 
     def close(self):
         _release(self)
+
+
+def NewGroth16TrustedSetup(qap, backend: Optional[Backend] = None, toxic=None, fmt: int = L.PS_FMT_AFFINE,
+                           export: bool = True) -> "Groth16Setup":
+    """NewGroth16TrustedSetup, groth16.go:64-101, computed on the device (ps_g16_setup).  `toxic` = (alpha, beta,
+    delta, x, gamma); fresh randomness when omitted, kept in the result's `tw` like the reference's Groth16Setup.tw.
+    The proving key stays resident on `backend`; with `export` the struct's point fields are filled as well
+    (uncompressed blobs by default: they are what a key file or another backend would be loaded from)."""
+    b = backend or default_backend()
+    if toxic is None:
+        toxic = tuple(secrets.randbelow(R - 1) + 1 for _ in range(5))
+    qh = qap._resident(b)
+    n, m, nio = qap.nbGates, qap.nbVars, qap.nbIO
+    diff = m - nio
+    kh = C.c_void_p()
+    iolp = C.create_string_buffer(max(1, diff * 48))
+    gamma = C.create_string_buffer(96)
+    b._check(b.lib.ps_g16_setup(b.ctx, qh, _fr_bytes(list(toxic)), C.byref(kh), iolp, gamma))
+    tr = Groth16Setup(Alpha=b"", Beta=b"", Delta=b"", Xi=b"", NioLP=b"", XiT=b"", Beta2=b"", Delta2=b"", Xi2=b"",
+                      IoLP=[iolp.raw[i * 48:(i + 1) * 48] for i in range(diff)], Gamma=gamma.raw, fmt=fmt)
+    tr.tw = dict(zip(("Alpha", "Beta", "Delta", "X", "Gamma"), toxic))
+    tr._dev = _DevHandle(b, kh, "ps_g16_key_free")
+    if export:
+        g1b, g2b = (48, 96) if fmt == L.PS_FMT_COMPRESSED else (96, 192)
+        bufs = {"xi": n * g1b, "xi2": n * g2b, "xit": (n - 1) * g1b, "niolp": nio * g1b, "alpha": g1b, "beta": g1b, "delta": g1b,
+                "beta2": g2b, "delta2": g2b}
+        cb = {k: C.create_string_buffer(max(1, v)) for k, v in bufs.items()}
+        b._check(b.lib.ps_g16_key_export(b.ctx, kh, fmt, *[cb[k] for k in ("xi", "xi2", "xit", "niolp", "alpha", "beta", "delta",
+                                                                            "beta2", "delta2")]))
+        raw = {k: cb[k].raw[:bufs[k]] for k in bufs}
+        tr.Xi, tr.Xi2, tr.XiT, tr.NioLP = raw["xi"], raw["xi2"], raw["xit"], raw["niolp"]
+        tr.Alpha, tr.Beta, tr.Delta, tr.Beta2, tr.Delta2 = raw["alpha"], raw["beta"], raw["delta"], raw["beta2"], raw["delta2"]
+    return tr
 
 
 @dataclass
@@ -620,8 +654,50 @@ class PHGR13EvalKey:
             return h
         return _resident_handle(self, backend, build, "ps_phgr13_key_free")
 
+    def export(self):
+        """fills the byte fields from the resident key (after NewPHGR13TrustedSetup)"""
+        dev = self._dev
+        n, nmid = self._shape
+        b = dev.backend
+        names = ("gsi", "vs", "ws", "ys", "vas", "was", "yas", "vbs", "wbs", "ybs")
+        sizes = {k: (n - 1 if k == "gsi" else nmid) * (96 if k == "ws" else 48) for k in names}
+        cb = {k: C.create_string_buffer(max(1, sizes[k])) for k in names}
+        b._check(b.lib.ps_phgr13_key_export(b.ctx, dev.handle, L.PS_FMT_COMPRESSED, *[cb[k] for k in names]))
+        for k in names:
+            per = 96 if k == "ws" else 48
+            raw = cb[k].raw[:sizes[k]]
+            setattr(self, k, [raw[i:i + per] for i in range(0, len(raw), per)])
+        return self
+
     def close(self):
         _release(self)
+
+
+def NewPHGR13TrustedSetup(qap, backend: Optional[Backend] = None, toxic=None, with_vk: bool = False):
+    """NewPHGR13TrustedSetup, pinochio.go:93-176, on the device (ps_phgr13_setup).  `toxic` = (s, av, aw, ay, rv, rw,
+    beta, gamma) in the reference's sampling order.  Returns (PHGR13EvalKey resident on `backend`, vk dict or None,
+    toxic); the evaluation key's byte fields are filled on demand by PHGR13EvalKey.export()."""
+    b = backend or default_backend()
+    if toxic is None:
+        toxic = tuple(secrets.randbelow(R - 1) + 1 for _ in range(8))
+    qh = qap._resident(b)
+    m = qap.nbVars
+    kh = C.c_void_p()
+    fixed = C.create_string_buffer(576) if with_vk else None
+    vs = C.create_string_buffer(m * 48) if with_vk else None
+    ws = C.create_string_buffer(m * 96) if with_vk else None
+    ys = C.create_string_buffer(m * 48) if with_vk else None
+    b._check(b.lib.ps_phgr13_setup(b.ctx, qh, _fr_bytes(list(toxic)), C.byref(kh), fixed, vs, ws, ys))
+    ek = PHGR13EvalKey(vs=[], ws=[], ys=[], vas=[], was=[], yas=[], gsi=[], vbs=[], wbs=[], ybs=[])
+    ek._shape = (qap.nbGates, qap.nbIO)
+    ek._dev = _DevHandle(b, kh, "ps_phgr13_key_free")
+    vk = None
+    if with_vk:
+        f = fixed.raw
+        cut = lambda raw, per: [raw[i:i + per] for i in range(0, len(raw), per)]
+        vk = {"av": f[0:96], "aw": f[96:144], "ay": f[144:240], "gamma": f[240:336], "bgamma": f[336:384], "bgamma2": f[384:480],
+              "yts": f[480:576], "vs": cut(vs.raw, 48), "ws": cut(ws.raw, 96), "ys": cut(ys.raw, 48)}
+    return ek, vk, toxic
 
 
 @dataclass

@@ -55,27 +55,64 @@ int bases_alloc(int group, size_t n, int window_bits, int tables, int shards, in
   size_t pt = group == PS_G1 ? sizeof(G1Affine) : sizeof(G2Affine);
   int rc = dev_alloc(&b->tab, n * tables * pt);
   if (rc != PS_OK) { delete b; return rc; }
+  b->slab = b->tab;
   *out = b;
   return PS_OK;
+}
+
+// `nsets` base sets of one group, all with window `window_bits` and all its tables, carved out of ONE device allocation
+// (*slab_out, owned by the caller) so that their MSMs can run as one batched pipeline
+int bases_alloc_slab(int group, const size_t* counts, int nsets, int window_bits, void** slab_out, ps_bases** out) {
+  if (window_bits < 2 || window_bits > 24) return PS_ERR_ARG;
+  const size_t pt = group == PS_G1 ? sizeof(G1Affine) : sizeof(G2Affine);
+  int tables = msm_windows(window_bits);
+  size_t total = 0;
+  for (int i = 0; i < nsets; i++) total += counts[i];
+  size_t free_b = total * tables * pt * 8, total_b = 0;
+#if PS_GPU
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+#endif
+  (void)total_b;
+  if (total * tables * pt > free_b / 4) tables = 1;   // not enough HBM for all windows: one table, per-window bucket sets
+  if ((unsigned long long)total * (unsigned long long)tables >= 0x7FFFFFFFull) return PS_ERR_UNSUPPORTED;
+  void* slab = nullptr;
+  PS_TRY(dev_alloc(&slab, total * tables * pt));
+  size_t off = 0;
+  for (int i = 0; i < nsets; i++) {
+    ps_bases* b = new (std::nothrow) ps_bases();
+    if (!b) { for (int j = 0; j < i; j++) { delete out[j]; out[j] = nullptr; } dev_free(slab); return PS_ERR_ALLOC; }
+    b->group = group; b->n = counts[i]; b->c = window_bits; b->T = tables;
+    b->tab = (char*)slab + off * pt; b->slab = slab; b->owns = false;
+    off += counts[i] * tables;
+    out[i] = b;
+  }
+  *slab_out = slab;
+  return PS_OK;
+}
+
+// decodes `b->n` host points into the first table of an allocated base set and builds the other tables
+template <class F>
+int bases_fill_t(ps_ctx* ctx, ps_bases* b, const uint8_t* points, int format) {
+  ps_stream_t st = ctx->stream;
+  const size_t n = b->n, bytes = n * point_bytes(PointBytes<F>::GROUP, format);
+  uint8_t* d_in = ctx->arena.take<uint8_t>(bytes);
+  uint32_t* d_err = ctx->arena.take<uint32_t>(1);
+  if (!d_in || !d_err) return PS_ERR_ALLOC;
+  if (bytes) PS_TRY(dev_h2d(d_in, points, bytes, st));
+  PS_TRY(dev_memset(d_err, 0, 4, st));
+  PS_TRY(GroupOps<F>::decode(ctx, d_in, n, format, (Affine<F>*)b->tab, d_err, ctx->subgroup_check != 0));
+  PS_TRY(GroupOps<F>::tables_finish(ctx, (Affine<F>*)b->tab, b->n, b->c, b->T));
+  uint32_t herr = 0;
+  PS_TRY(dev_d2h(&herr, d_err, 4, st));
+  PS_TRY(dev_sync(st));
+  return herr ? PS_ERR_ENCODING : PS_OK;
 }
 
 template <class F>
 int bases_load_t(ps_ctx* ctx, const uint8_t* points, size_t n, int format, int window_bits, int tables, ps_bases** out) {
   ps_bases* b = nullptr;
   PS_TRY(bases_alloc(PointBytes<F>::GROUP, n, window_bits, tables, ctx->msm_shards, ctx->msm_bucket_cost, &b));
-  ps_stream_t st = ctx->stream;
-  size_t bytes = n * point_bytes(PointBytes<F>::GROUP, format);
-  uint8_t* d_in = ctx->arena.take<uint8_t>(bytes);
-  uint32_t* d_err = ctx->arena.take<uint32_t>(1);
-  int rc = (!d_in || !d_err) ? PS_ERR_ALLOC : PS_OK;
-  if (rc == PS_OK) rc = dev_h2d(d_in, points, bytes, st);
-  if (rc == PS_OK) rc = dev_memset(d_err, 0, 4, st);
-  if (rc == PS_OK) rc = GroupOps<F>::decode(ctx, d_in, n, format, (Affine<F>*)b->tab, d_err, ctx->subgroup_check != 0);
-  if (rc == PS_OK) rc = GroupOps<F>::tables_finish(ctx, (Affine<F>*)b->tab, b->n, b->c, b->T);
-  uint32_t herr = 0;
-  if (rc == PS_OK) rc = dev_d2h(&herr, d_err, 4, st);
-  if (rc == PS_OK) rc = dev_sync(st);
-  if (rc == PS_OK && herr) rc = PS_ERR_ENCODING;
+  int rc = bases_fill_t<F>(ctx, b, points, format);
   if (rc != PS_OK) { ps_bases_free(b); return rc; }
   *out = b;
   return PS_OK;
@@ -92,9 +129,7 @@ template <class F>
 int msm_batch(ps_ctx* ctx, const SegSpec* segs, int nseg, int nsets, XYZZ<F>* d_out) {
   if (nseg < 1 || nseg > MSM_MAX_SEG || nsets < 1 || nsets > MSM_MAX_SEG) return PS_ERR_ARG;
   MsmPlan p;
-  MsmTabs tabs;
   memset(&p, 0, sizeof p);
-  memset(&tabs, 0, sizeof tabs);
   size_t total = 0;
   const ps_bases* of_set[MSM_MAX_SEG] = {nullptr};
   for (int k = 0; k < nseg; k++) {
@@ -106,13 +141,26 @@ int msm_batch(ps_ctx* ctx, const SegSpec* segs, int nseg, int nsets, XYZZ<F>* d_
     total += sg.n;
   }
   if (total >= 0xFFFFFFFFull) return PS_ERR_UNSUPPORTED;
-  // window geometry: the (common) fixed window of the base sets, or a per-call choice when none is fixed
+  // one pipeline needs one table allocation and one window geometry; base sets loaded separately run one after the other
+  const void* slab = nullptr;
   int c = 0, T = 0;
+  bool uniform = true;
   for (int s = 0; s < nsets; s++) {
     const ps_bases* b = of_set[s];
     if (!b) continue;
-    if (T == 0) { c = b->c; T = b->T; }
-    else if (b->c != c || b->T != T) return PS_ERR_ARG;
+    if (T == 0) { c = b->c; T = b->T; slab = b->slab; }
+    else if (b->c != c || b->T != T || b->slab != slab) uniform = false;
+  }
+  if (!uniform) {
+    for (int s = 0; s < nsets; s++) {
+      SegSpec sub[MSM_MAX_SEG];
+      int cnt = 0;
+      for (int k = 0; k < nseg; k++)
+        if (segs[k].set == s) { sub[cnt] = segs[k]; sub[cnt].set = 0; cnt++; }
+      if (cnt) PS_TRY(msm_batch<F>(ctx, sub, cnt, 1, d_out + s));
+      else PS_TRY(dev_memset(d_out + s, 0, sizeof(XYZZ<F>), ctx->stream));
+    }
+    return PS_OK;
   }
   if (T == 0) { c = 0; T = 1; }
   if (c == 0) c = msm_pick_window(total ? total : 1);
@@ -126,11 +174,11 @@ int msm_batch(ps_ctx* ctx, const SegSpec* segs, int nseg, int nsets, XYZZ<F>* d_
     start += (uint32_t)sg.n;
   }
   for (int s = 0; s < nsets; s++) {
-    tabs.tab[s] = of_set[s] ? of_set[s]->tab : nullptr;
-    p.nbase[s] = of_set[s] ? (uint32_t)of_set[s]->n : 0;
+    const ps_bases* b = of_set[s];
+    p.nbase[s] = b ? (uint32_t)b->n : 0;
+    p.toff[s] = b ? (uint32_t)(((const char*)b->tab - (const char*)slab) / sizeof(Affine<F>)) : 0;
   }
-  tabs.log_d = c - 1; tabs.S = p.S;
-  return GroupOps<F>::msm_batch(ctx, p, tabs, d_out);
+  return GroupOps<F>::msm_batch(ctx, p, (const Affine<F>*)slab, d_out);
 }
 
 template <class F>
@@ -157,12 +205,12 @@ int encode_points_staged(ps_ctx* ctx, const XYZZ<F>* d_pts, size_t count, size_t
   return encode_points<F>(ctx, d_pts, count, ctx->h_stage + stage_off);
 }
 
-// concatenates host point arrays into one device base set with the given window (0 = automatic)
+// concatenates host point arrays and loads them into the allocated base set `b` (sum of counts == b->n)
 template <class F>
-int bases_concat(ps_ctx* ctx, int format, const uint8_t* const* parts, const size_t* counts, int nparts, int window_bits,
-                 ps_bases** out) {
+int bases_concat_into(ps_ctx* ctx, ps_bases* b, int format, const uint8_t* const* parts, const size_t* counts, int nparts) {
   size_t per = point_bytes(PointBytes<F>::GROUP, format), total = 0;
   for (int i = 0; i < nparts; i++) total += counts[i];
+  if (total != b->n) return PS_ERR_ARG;
   std::vector<uint8_t> buf(total * per);
   size_t o = 0;
   for (int i = 0; i < nparts; i++) {
@@ -170,7 +218,7 @@ int bases_concat(ps_ctx* ctx, int format, const uint8_t* const* parts, const siz
     memcpy(buf.data() + o, parts[i], counts[i] * per);
     o += counts[i] * per;
   }
-  return bases_load_t<F>(ctx, buf.data(), total, format, window_bits, -1, out);
+  return bases_fill_t<F>(ctx, b, buf.data(), format);
 }
 
 // one window for every base set of a key, so that their MSMs can share a pipeline (msm_batch): sized for the
@@ -178,6 +226,27 @@ int bases_concat(ps_ctx* ctx, int format, const uint8_t* const* parts, const siz
 int key_window(ps_ctx* ctx, size_t total_points, int nsets) {
   const size_t shards = (size_t)(ctx->msm_shards > 0 ? ctx->msm_shards : 1);
   return msm_pick_window_full(total_points / (size_t)(nsets > 0 ? nsets : 1) / shards + 1, (double)ctx->msm_bucket_cost);
+}
+
+// allocates the three base sets of a Groth16 key: A and C carved out of one G1 slab, B (G2) on its own
+int g16_key_alloc(ps_g16_key* k, size_t nA, size_t nB, size_t nC, int window_bits) {
+  const size_t g1counts[2] = {nA, nC};
+  ps_bases* g1[2] = {nullptr, nullptr};
+  PS_TRY(bases_alloc_slab(PS_G1, g1counts, 2, window_bits, &k->slab_g1, g1));
+  k->A = g1[0]; k->C = g1[1];
+  void* slab_b = nullptr;
+  PS_TRY(bases_alloc_slab(PS_G2, &nB, 1, window_bits, &slab_b, &k->B));
+  k->B->owns = true;    // a one-set slab: the base set owns its allocation
+  return PS_OK;
+}
+// the eight base sets of a PHGR13 evaluation key: the seven G1 ones in one slab
+int phgr13_key_alloc(ps_phgr13_key* k, size_t n_gates, size_t n_mid, int window_bits) {
+  const size_t counts[7] = {n_gates - 1, n_mid, n_mid, n_mid, n_mid, n_mid, 3 * n_mid};
+  PS_TRY(bases_alloc_slab(PS_G1, counts, 7, window_bits, &k->slab_g1, k->g1));
+  void* slab_w = nullptr;
+  PS_TRY(bases_alloc_slab(PS_G2, &n_mid, 1, window_bits, &slab_w, &k->ws));
+  k->ws->owns = true;
+  return PS_OK;
 }
 
 }  // namespace
@@ -343,7 +412,7 @@ int ps_bases_info(const ps_bases* b, int out[4]) {
 
 void ps_bases_free(ps_bases* b) {
   if (!b) return;
-  dev_free(b->tab);
+  if (b->owns) dev_free(b->tab);
   delete b;
 }
 
@@ -478,11 +547,12 @@ int ps_g16_key_load(ps_ctx* ctx, size_t n_gates, size_t n_nio, int format, const
   const size_t cc[6] = {n_nio, n_gates - 1, n_gates, 1, 1, 1};
   // one window for the whole key: A and C share a pipeline
   const int c = key_window(ctx, 4 * n_gates + n_nio + 6, 3);
-  int rc = bases_concat<Fp>(ctx, format, pa, ca, 3, c, &k->A);
+  int rc = g16_key_alloc(k, n_gates + 2, n_gates + 2, n_nio + (n_gates - 1) + n_gates + 3, c);
+  if (rc == PS_OK) rc = bases_concat_into<Fp>(ctx, k->A, format, pa, ca, 3);
   if (rc == PS_OK) rc = ctx->arena.reset();
-  if (rc == PS_OK) rc = bases_concat<Fp2>(ctx, format, pb, ca, 3, c, &k->B);
+  if (rc == PS_OK) rc = bases_concat_into<Fp2>(ctx, k->B, format, pb, ca, 3);
   if (rc == PS_OK) rc = ctx->arena.reset();
-  if (rc == PS_OK) rc = bases_concat<Fp>(ctx, format, pc, cc, 6, c, &k->C);
+  if (rc == PS_OK) rc = bases_concat_into<Fp>(ctx, k->C, format, pc, cc, 6);
   if (rc != PS_OK) { ps_g16_key_free(k); return rc; }
   *key = k;
   return PS_OK;
@@ -491,6 +561,7 @@ int ps_g16_key_load(ps_ctx* ctx, size_t n_gates, size_t n_nio, int format, const
 void ps_g16_key_free(ps_g16_key* key) {
   if (!key) return;
   ps_bases_free(key->A); ps_bases_free(key->B); ps_bases_free(key->C);
+  dev_free(key->slab_g1);
   delete key;
 }
 
@@ -551,11 +622,12 @@ int g16_key_load_slice(ps_ctx* ctx, const KeySlice& sl, int format, int window_b
   const uint8_t* pb[3] = {xi2 + sl.x_lo * g2, delta2, beta2};
   const uint8_t* pc[6] = {niolp ? niolp + sl.n_lo * g1 : niolp, xit + sl.t_lo * g1, xi + sl.x_lo * g1, alpha, beta, delta};
   const size_t cc[6] = {nn, nt, nx, one, one, one};
-  int rc = bases_concat<Fp>(ctx, format, pa, ca, 3, window_bits, &k->A);
+  int rc = g16_key_alloc(k, nx + 2 * one, nx + 2 * one, nn + nt + nx + 3 * one, window_bits);
+  if (rc == PS_OK) rc = bases_concat_into<Fp>(ctx, k->A, format, pa, ca, 3);
   if (rc == PS_OK) rc = ctx->arena.reset();
-  if (rc == PS_OK) rc = bases_concat<Fp2>(ctx, format, pb, ca, 3, window_bits, &k->B);
+  if (rc == PS_OK) rc = bases_concat_into<Fp2>(ctx, k->B, format, pb, ca, 3);
   if (rc == PS_OK) rc = ctx->arena.reset();
-  if (rc == PS_OK) rc = bases_concat<Fp>(ctx, format, pc, cc, 6, window_bits, &k->C);
+  if (rc == PS_OK) rc = bases_concat_into<Fp>(ctx, k->C, format, pc, cc, 6);
   if (rc != PS_OK) { ps_g16_key_free(k); return rc; }
   *key = k;
   return PS_OK;
@@ -595,6 +667,93 @@ int g16_slice_msm_late(ps_ctx* ctx, const ps_g16_key* key, const KeySlice& sl, c
 }
 }  // namespace ps
 }  // extern "C++"
+
+extern "C++" {
+namespace {
+// out[first .. first + cnt) of the base set's first table = scalars[i] * generator
+template <class F>
+int fill_from_scalars(ps_ctx* ctx, ps_bases* b, size_t first, const Fr* d_scalars, size_t cnt) {
+  if (!cnt) return PS_OK;
+  return GroupOps<F>::from_scalars(ctx, (const uint32_t*)d_scalars, cnt, (Affine<F>*)b->tab + first);
+}
+template <class F>
+int export_range(ps_ctx* ctx, const ps_bases* b, size_t first, size_t count, int format, uint8_t* out) {
+  if (!out || !count) return PS_OK;
+  size_t per = point_bytes(b->group, format);
+  uint8_t* d_bytes = ctx->arena.take<uint8_t>(count * per);
+  if (!d_bytes) return PS_ERR_ALLOC;
+  PS_TRY(GroupOps<F>::encode_affine(ctx, (const Affine<F>*)b->tab + first, count, format, d_bytes));
+  return dev_d2h(out, d_bytes, count * per, ctx->stream);
+}
+// a few points scalar[i] * generator straight to host bytes (verification-key elements)
+template <class F>
+int export_multiples(ps_ctx* ctx, const Fr* d_scalars, size_t count, int format, uint8_t* out) {
+  if (!out || !count) return PS_OK;
+  Affine<F>* pts = ctx->arena.take<Affine<F>>(count);
+  size_t per = point_bytes(PointBytes<F>::GROUP, format);
+  uint8_t* d_bytes = ctx->arena.take<uint8_t>(count * per);
+  if (!pts || !d_bytes) return PS_ERR_ALLOC;
+  PS_TRY(GroupOps<F>::from_scalars(ctx, (const uint32_t*)d_scalars, count, pts));
+  PS_TRY(GroupOps<F>::encode_affine(ctx, (const Affine<F>*)pts, count, format, d_bytes));
+  return dev_d2h(out, d_bytes, count * per, ctx->stream);
+}
+}  // namespace
+}  // extern "C++"
+
+// NewGroth16TrustedSetup (groth16.go:64-101) on the device.  A = [Xi | Delta | Alpha], B = [Xi2 | Delta2 | Beta2],
+// C = [NioLP | XiT | Xi | Alpha Beta Delta] are filled by the fixed-base kernel from the exponents of setup.cuh.
+int ps_g16_setup(ps_ctx* ctx, const ps_qap* qap, const uint8_t* toxic_be, ps_g16_key** key, uint8_t* out_iolp, uint8_t* out_gamma) {
+  if (!ctx || !qap || !toxic_be || !key || qap->n < 2) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  const size_t n = qap->n, m = qap->m, nio = qap->n_io, diff = m - nio;
+  G16SetupScalars sc;
+  PS_TRY(g16_setup_scalars(ctx, qap, toxic_be, &sc));
+  ps_g16_key* k = new (std::nothrow) ps_g16_key();
+  if (!k) return PS_ERR_ALLOC;
+  k->n = n; k->n_nio = nio;
+  const int c = key_window(ctx, 4 * n + nio + 6, 3);
+  const Fr *alpha = sc.consts, *beta = sc.consts + 1, *delta = sc.consts + 2, *gamma = sc.consts + 3;
+  int rc = g16_key_alloc(k, n + 2, n + 2, nio + (n - 1) + n + 3, c);
+  if (rc == PS_OK) rc = fill_from_scalars<Fp>(ctx, k->A, 0, sc.pw, n);
+  if (rc == PS_OK) rc = fill_from_scalars<Fp>(ctx, k->A, n, delta, 1);
+  if (rc == PS_OK) rc = fill_from_scalars<Fp>(ctx, k->A, n + 1, alpha, 1);
+  if (rc == PS_OK) rc = fill_from_scalars<Fp2>(ctx, k->B, 0, sc.pw, n);
+  if (rc == PS_OK) rc = fill_from_scalars<Fp2>(ctx, k->B, n, delta, 1);
+  if (rc == PS_OK) rc = fill_from_scalars<Fp2>(ctx, k->B, n + 1, beta, 1);
+  if (rc == PS_OK) rc = fill_from_scalars<Fp>(ctx, k->C, 0, sc.lp + diff, nio);
+  if (rc == PS_OK) rc = fill_from_scalars<Fp>(ctx, k->C, nio, sc.pwt, n - 1);
+  if (rc == PS_OK) rc = fill_from_scalars<Fp>(ctx, k->C, nio + (n - 1), sc.pw, n);
+  if (rc == PS_OK) rc = fill_from_scalars<Fp>(ctx, k->C, nio + (n - 1) + n, alpha, 3);     // alpha, beta, delta are consecutive
+  if (rc == PS_OK) rc = GroupOps<Fp>::tables_finish(ctx, (G1Affine*)k->A->tab, k->A->n, k->A->c, k->A->T);
+  if (rc == PS_OK) rc = GroupOps<Fp2>::tables_finish(ctx, (G2Affine*)k->B->tab, k->B->n, k->B->c, k->B->T);
+  if (rc == PS_OK) rc = GroupOps<Fp>::tables_finish(ctx, (G1Affine*)k->C->tab, k->C->n, k->C->c, k->C->T);
+  // verifier side: IoLP (the first m - n_io variables, divided by gamma) and Gamma in G2, compressed
+  if (rc == PS_OK) rc = export_multiples<Fp>(ctx, sc.lp, out_iolp ? diff : 0, PS_FMT_COMPRESSED, out_iolp);
+  if (rc == PS_OK) rc = export_multiples<Fp2>(ctx, gamma, out_gamma ? 1 : 0, PS_FMT_COMPRESSED, out_gamma);
+  if (rc == PS_OK) rc = dev_sync(ctx->stream);
+  if (rc != PS_OK) { ps_g16_key_free(k); return rc; }
+  *key = k;
+  return PS_OK;
+}
+
+// the key's elements back as wire bytes (any output may be NULL): what the Go shim stores into Groth16Setup's fields
+int ps_g16_key_export(ps_ctx* ctx, const ps_g16_key* key, int format, uint8_t* xi, uint8_t* xi2, uint8_t* xit, uint8_t* niolp,
+                      uint8_t* alpha, uint8_t* beta, uint8_t* delta, uint8_t* beta2, uint8_t* delta2) {
+  if (!ctx || !key || (format != PS_FMT_COMPRESSED && format != PS_FMT_AFFINE)) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  const size_t n = key->n, nio = key->n_nio;
+  if (key->A->n != n + 2 || key->C->n != nio + (n - 1) + n + 3) return PS_ERR_ARG;   // a per-device slice of a sharded key
+  PS_TRY(export_range<Fp>(ctx, key->A, 0, n, format, xi));
+  PS_TRY(export_range<Fp>(ctx, key->A, n, 1, format, delta));
+  PS_TRY(export_range<Fp>(ctx, key->A, n + 1, 1, format, alpha));
+  PS_TRY(export_range<Fp2>(ctx, key->B, 0, n, format, xi2));
+  PS_TRY(export_range<Fp2>(ctx, key->B, n, 1, format, delta2));
+  PS_TRY(export_range<Fp2>(ctx, key->B, n + 1, 1, format, beta2));
+  PS_TRY(export_range<Fp>(ctx, key->C, 0, nio, format, niolp));
+  PS_TRY(export_range<Fp>(ctx, key->C, nio, n - 1, format, xit));
+  PS_TRY(export_range<Fp>(ctx, key->C, nio + (n - 1) + n + 1, 1, format, beta));
+  return dev_sync(ctx->stream);
+}
 
 size_t ps_g16_scalar_count(const ps_g16_key* key, int which) {
   if (!key) return 0;
@@ -687,25 +846,84 @@ int ps_phgr13_key_load(ps_ctx* ctx, size_t n_gates, size_t n_mid, int format, co
   // one window for the whole key: its seven G1 sums share a pipeline (pinochio.go:218-242 sums the same
   // solution[diff:] against eight base vectors)
   const int c = key_window(ctx, n_gates - 1 + 9 * n_mid, 8);
-  int rc = PS_OK;
+  int rc = phgr13_key_alloc(k, n_gates, n_mid, c);
   for (int i = 0; i < 6 && rc == PS_OK; i++) {
-    rc = bases_concat<Fp>(ctx, format, &singles[i], &counts[i], 1, c, &k->g1[i]);
+    rc = bases_concat_into<Fp>(ctx, k->g1[i], format, &singles[i], &counts[i], 1);
     if (rc == PS_OK) rc = ctx->arena.reset();
   }
   const uint8_t* zs[3] = {vbs, wbs, ybs};
   const size_t zc[3] = {n_mid, n_mid, n_mid};
-  if (rc == PS_OK) rc = bases_concat<Fp>(ctx, format, zs, zc, 3, c, &k->g1[6]);
+  if (rc == PS_OK) rc = bases_concat_into<Fp>(ctx, k->g1[6], format, zs, zc, 3);
   if (rc == PS_OK) rc = ctx->arena.reset();
-  if (rc == PS_OK) rc = bases_concat<Fp2>(ctx, format, &ws, &n_mid, 1, c, &k->ws);
+  if (rc == PS_OK) rc = bases_concat_into<Fp2>(ctx, k->ws, format, &ws, &n_mid, 1);
   if (rc != PS_OK) { ps_phgr13_key_free(k); return rc; }
   *key = k;
   return PS_OK;
+}
+
+// NewPHGR13TrustedSetup (pinochio.go:93-176) on the device: the resident evaluation key and, on request, the
+// verification key as compressed bytes:
+//   out_vk_fixed (7 elements): av (G2 96 B) | aw (G1 48) | ay (G2 96) | gamma (G2 96) | bgamma (G1 48) | bgamma2 (G2 96) | yts (G2 96)
+//   out_vk_vs / out_vk_ws / out_vk_ys: the commitments of ALL n_vars variables (48 / 96 / 48 B each)
+int ps_phgr13_setup(ps_ctx* ctx, const ps_qap* qap, const uint8_t* toxic_be, ps_phgr13_key** key, uint8_t* out_vk_fixed,
+                    uint8_t* out_vk_vs, uint8_t* out_vk_ws, uint8_t* out_vk_ys) {
+  if (!ctx || !qap || !toxic_be || !key || qap->n < 2) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  const size_t n = qap->n, m = qap->m, nmid = qap->n_io, diff = m - nmid;
+  Phgr13SetupScalars sc;
+  PS_TRY(phgr13_setup_scalars(ctx, qap, toxic_be, &sc));
+  ps_phgr13_key* k = new (std::nothrow) ps_phgr13_key();
+  if (!k) return PS_ERR_ALLOC;
+  k->n = n; k->n_mid = nmid;
+  const int c = key_window(ctx, n - 1 + 9 * nmid, 8);
+  // g1[]: gsi vs ys vas was yas [vbs|wbs|ybs];  ek[]: vs ws ys vas was yas vbs wbs ybs
+  const int ek_of_g1[6] = {-1, 0, 2, 3, 4, 5};
+  int rc = phgr13_key_alloc(k, n, nmid, c);
+  if (rc == PS_OK) rc = fill_from_scalars<Fp>(ctx, k->g1[0], 0, sc.pw, n - 1);
+  for (int i = 1; i < 6 && rc == PS_OK; i++) rc = fill_from_scalars<Fp>(ctx, k->g1[i], 0, sc.ek[ek_of_g1[i]] + diff, nmid);
+  for (int t = 0; t < 3 && rc == PS_OK; t++) rc = fill_from_scalars<Fp>(ctx, k->g1[6], (size_t)t * nmid, sc.ek[6 + t] + diff, nmid);
+  if (rc == PS_OK) rc = fill_from_scalars<Fp2>(ctx, k->ws, 0, sc.ek[1] + diff, nmid);
+  for (int i = 0; i < 7 && rc == PS_OK; i++) rc = GroupOps<Fp>::tables_finish(ctx, (G1Affine*)k->g1[i]->tab, k->g1[i]->n, k->g1[i]->c, k->g1[i]->T);
+  if (rc == PS_OK) rc = GroupOps<Fp2>::tables_finish(ctx, (G2Affine*)k->ws->tab, k->ws->n, k->ws->c, k->ws->T);
+  if (rc == PS_OK && out_vk_fixed) {
+    const Fr* cs = sc.consts;   // av aw ay gamma bgamma t(s)*ry
+    uint8_t* o = out_vk_fixed;
+    rc = export_multiples<Fp2>(ctx, cs + 0, 1, PS_FMT_COMPRESSED, o);
+    if (rc == PS_OK) rc = export_multiples<Fp>(ctx, cs + 1, 1, PS_FMT_COMPRESSED, o + 96);
+    if (rc == PS_OK) rc = export_multiples<Fp2>(ctx, cs + 2, 1, PS_FMT_COMPRESSED, o + 144);
+    if (rc == PS_OK) rc = export_multiples<Fp2>(ctx, cs + 3, 1, PS_FMT_COMPRESSED, o + 240);
+    if (rc == PS_OK) rc = export_multiples<Fp>(ctx, cs + 4, 1, PS_FMT_COMPRESSED, o + 336);
+    if (rc == PS_OK) rc = export_multiples<Fp2>(ctx, cs + 4, 1, PS_FMT_COMPRESSED, o + 384);
+    if (rc == PS_OK) rc = export_multiples<Fp2>(ctx, cs + 5, 1, PS_FMT_COMPRESSED, o + 480);
+  }
+  if (rc == PS_OK) rc = export_multiples<Fp>(ctx, sc.ek[0], out_vk_vs ? m : 0, PS_FMT_COMPRESSED, out_vk_vs);
+  if (rc == PS_OK) rc = export_multiples<Fp2>(ctx, sc.ek[1], out_vk_ws ? m : 0, PS_FMT_COMPRESSED, out_vk_ws);
+  if (rc == PS_OK) rc = export_multiples<Fp>(ctx, sc.ek[2], out_vk_ys ? m : 0, PS_FMT_COMPRESSED, out_vk_ys);
+  if (rc == PS_OK) rc = dev_sync(ctx->stream);
+  if (rc != PS_OK) { ps_phgr13_key_free(k); return rc; }
+  *key = k;
+  return PS_OK;
+}
+
+// the evaluation key back as wire bytes (any output may be NULL), the order of ps_phgr13_key_load's arguments
+int ps_phgr13_key_export(ps_ctx* ctx, const ps_phgr13_key* key, int format, uint8_t* gsi, uint8_t* vs, uint8_t* ws, uint8_t* ys,
+                         uint8_t* vas, uint8_t* was, uint8_t* yas, uint8_t* vbs, uint8_t* wbs, uint8_t* ybs) {
+  if (!ctx || !key || (format != PS_FMT_COMPRESSED && format != PS_FMT_AFFINE)) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  const size_t nm = key->n_mid;
+  uint8_t* singles[6] = {gsi, vs, ys, vas, was, yas};
+  for (int i = 0; i < 6; i++) PS_TRY(export_range<Fp>(ctx, key->g1[i], 0, key->g1[i]->n, format, singles[i]));
+  uint8_t* zs[3] = {vbs, wbs, ybs};
+  for (int t = 0; t < 3; t++) PS_TRY(export_range<Fp>(ctx, key->g1[6], (size_t)t * nm, nm, format, zs[t]));
+  PS_TRY(export_range<Fp2>(ctx, key->ws, 0, nm, format, ws));
+  return dev_sync(ctx->stream);
 }
 
 void ps_phgr13_key_free(ps_phgr13_key* key) {
   if (!key) return;
   for (auto* b : key->g1) ps_bases_free(b);
   ps_bases_free(key->ws);
+  dev_free(key->slab_g1);
   delete key;
 }
 

@@ -6,6 +6,7 @@
 #include "codec.cuh"
 #include "interp.cuh"
 #include "multi_api.cuh"
+#include "setup.cuh"
 
 #include <new>
 
@@ -198,6 +199,87 @@ int g16_slice_scalars(ps_ctx* ctx, const KeySlice& sl, const uint8_t* r_be, cons
   return PS_OK;
 }
 
+// dst[k] = src[idx[k]]
+struct FrGatherK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t k, const Fr* src, const uint32_t* idx, Fr* dst) { dst[k] = src[idx[k]]; }
+};
+// dst[k] = c[k] in standard form, k < cnt <= 8 (constants passed by value)
+struct FrConstsK {
+  static constexpr int BLOCK = 32;
+  struct Pack { Fr v[8]; };
+  PS_DEV static void run(uint32_t k, Pack c, Fr* dst) { dst[k] = c.v[k].from_mont(); }
+};
+
+int g16_setup_scalars(ps_ctx* ctx, const ps_qap* q, const uint8_t* toxic_be, G16SetupScalars* o) {
+  ps_stream_t st = ctx->stream;
+  const size_t n = q->n, m = q->m, diff = q->m - q->n_io;
+  Fr tox[5];   // alpha, beta, delta, x, gamma
+  for (int i = 0; i < 5; i++) {
+    PS_TRY(parse_fr(toxic_be + 32 * i, &tox[i]));
+    if (tox[i].is_zero()) return PS_ERR_ARG;
+  }
+  const Fr alpha = tox[0], beta = tox[1], delta = tox[2], x = tox[3], gamma = tox[4];
+  Fr* ev = ctx->arena.take<Fr>(3 * m);
+  Fr* zx = ctx->arena.take<Fr>(1);
+  o->pw = ctx->arena.take<Fr>(n); o->pwt = ctx->arena.take<Fr>(n); o->lp = ctx->arena.take<Fr>(m); o->consts = ctx->arena.take<Fr>(8);
+  if (!ev || !zx || !o->pw || !o->pwt || !o->lp || !o->consts) return PS_ERR_ALLOC;
+  PS_TRY(qap_eval_all_at(ctx, q, x, ev, zx));
+  const Fr dinv = fr_inv(delta), ginv = fr_inv(gamma);
+  // lp[i] = (beta u_i + alpha v_i + w_i) / gamma (i < diff) or / delta   (linearPolyForVar, groth16.go:238-264)
+  PS_LAUNCH(LinCombStdK, st, m, (uint32_t)m, (const Fr*)ev, beta, alpha, Fr::one(), (uint32_t)diff, ginv, dinv, o->lp);
+  PS_LAUNCH(FrPowStdK, st, n, x, Fr::one(), o->pw);                    // GeneratePowersCommit(x, 1, n-1), groth16.go:79
+  // XiT: x^k t(x) / delta, k <= n - 2 (groth16.go:93-96): t(x) lives on the device
+  PS_LAUNCH(FrPowTableK, st, n - 1, x, dinv, o->pwt);
+  PS_LAUNCH(FrScaleByK, st, n - 1, (const Fr*)zx, o->pwt);
+  PS_LAUNCH(FrFromMontK, st, n - 1, o->pwt);
+  FrConstsK::Pack pk;
+  pk.v[0] = alpha; pk.v[1] = beta; pk.v[2] = delta; pk.v[3] = gamma;
+  for (int i = 4; i < 8; i++) pk.v[i] = Fr::zero();
+  PS_LAUNCH(FrConstsK, st, 4, pk, o->consts);
+  return PS_OK;
+}
+
+int phgr13_setup_scalars(ps_ctx* ctx, const ps_qap* q, const uint8_t* toxic_be, Phgr13SetupScalars* o) {
+  ps_stream_t st = ctx->stream;
+  const size_t n = q->n, m = q->m;
+  Fr tox[8];   // s, av, aw, ay, rv, rw, beta, gamma  (sampling order of pinochio.go:93-141)
+  for (int i = 0; i < 8; i++) {
+    PS_TRY(parse_fr(toxic_be + 32 * i, &tox[i]));
+    if (tox[i].is_zero()) return PS_ERR_ARG;
+  }
+  const Fr s = tox[0], av = tox[1], aw = tox[2], ay = tox[3], rv = tox[4], rw = tox[5], beta = tox[6], gamma = tox[7];
+  const Fr ry = rv * rw, zero = Fr::zero();
+  Fr* ev = ctx->arena.take<Fr>(3 * m);
+  Fr* zx = ctx->arena.take<Fr>(1);
+  o->pw = ctx->arena.take<Fr>(n);
+  for (int k = 0; k < 9; k++) o->ek[k] = ctx->arena.take<Fr>(m);
+  o->consts = ctx->arena.take<Fr>(8);
+  if (!ev || !zx || !o->pw || !o->consts) return PS_ERR_ALLOC;
+  for (int k = 0; k < 9; k++) if (!o->ek[k]) return PS_ERR_ALLOC;
+  PS_TRY(qap_eval_all_at(ctx, q, s, ev, zx));
+  PS_LAUNCH(FrPowStdK, st, n - 1, s, Fr::one(), o->pw);                // gsi, pinochio.go:101
+  // generateEvalCommit(base r*G, polys, s, shift) = (shift r p_i(s)) * G  (pinochio.go:381-388); all m variables are
+  // computed (the verification key commits to all of them, the evaluation key to the last nbIO)
+  const Fr cu[9] = {rv, zero, zero, rv * av, zero, zero, rv * beta, zero, zero};   // vs ws ys vas was yas vbs wbs ybs
+  const Fr cv[9] = {zero, rw, zero, zero, rw * aw, zero, zero, rw * beta, zero};
+  const Fr cw[9] = {zero, zero, ry, zero, zero, ry * ay, zero, zero, ry * beta};
+  for (int k = 0; k < 9; k++)
+    PS_LAUNCH(LinCombStdK, st, m, (uint32_t)m, (const Fr*)ev, cu[k], cv[k], cw[k], 0u, Fr::one(), Fr::one(), o->ek[k]);
+  // verification-key constants: av, aw, ay, gamma, beta*gamma, t(s)*ry
+  Fr* tsy = ctx->arena.take<Fr>(1);
+  if (!tsy) return PS_ERR_ALLOC;
+  FrConstsK::Pack pk;
+  pk.v[0] = av; pk.v[1] = aw; pk.v[2] = ay; pk.v[3] = gamma; pk.v[4] = beta * gamma; pk.v[5] = ry; pk.v[6] = zero; pk.v[7] = zero;
+  PS_LAUNCH(FrConstsK, st, 6, pk, o->consts);
+  // consts[5] = t(s) * ry
+  PS_TRY(dev_d2d(tsy, zx, sizeof(Fr), st));
+  PS_LAUNCH(FrPowTableK, st, 1, Fr::one(), ry, tsy + 0);   // tsy[0] = ry (Montgomery)
+  PS_LAUNCH(FrScaleByK, st, 1, (const Fr*)zx, tsy);        // * t(s)
+  PS_LAUNCH(FrStdCopyK, st, 1, (const Fr*)tsy, o->consts + 5);
+  return PS_OK;
+}
+
 }  // namespace ps
 
 extern "C" {
@@ -314,6 +396,32 @@ int ps_qap_load_r1cs(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, co
     if (rc == PS_OK && !d_bytes) rc = PS_ERR_ALLOC;
     if (rc == PS_OK && nnz) rc = dev_h2d(d_bytes, vals[i], nnz * 32, st);
     if (rc == PS_OK) rc = ps_launch<FrFromBytesK>(st, nnz, (const uint8_t*)d_bytes, (uint32_t*)m.val, 1, d_err);
+  }
+  // transposes (per variable: the gates that use it) for the trusted setups: counting sort on the host, values gathered
+  // on the device from the already converted CSR values
+  for (int i = 0; i < 3 && rc == PS_OK; i++) {
+    const size_t nnz = rps[i][n_gates];
+    std::vector<uint32_t> cp(n_vars + 1, 0), gate(nnz ? nnz : 1), src(nnz ? nnz : 1);
+    for (size_t t = 0; t < nnz; t++) cp[cols[i][t] + 1]++;
+    for (size_t v = 0; v < n_vars; v++) cp[v + 1] += cp[v];
+    std::vector<uint32_t> fill(cp.begin(), cp.end() - 1);
+    for (size_t j = 0; j < n_gates; j++)
+      for (uint32_t t = rps[i][j]; t < rps[i][j + 1]; t++) {
+        const uint32_t pos = fill[cols[i][t]]++;
+        gate[pos] = (uint32_t)j; src[pos] = t;
+      }
+    CsrDev& mt = sq->matT[i];
+    mt.nnz = nnz;
+    rc = dev_alloc((void**)&mt.row_ptr, (n_vars + 1) * 4);
+    if (rc == PS_OK) rc = dev_alloc((void**)&mt.col, nnz * 4);
+    if (rc == PS_OK) rc = dev_alloc((void**)&mt.val, nnz * sizeof(Fr));
+    uint32_t* d_src = ctx->arena.take<uint32_t>(nnz);
+    if (rc == PS_OK && !d_src) rc = PS_ERR_ALLOC;
+    if (rc == PS_OK) rc = dev_h2d(mt.row_ptr, cp.data(), (n_vars + 1) * 4, st);
+    if (rc == PS_OK && nnz) rc = dev_h2d(mt.col, gate.data(), nnz * 4, st);
+    if (rc == PS_OK && nnz) rc = dev_h2d(d_src, src.data(), nnz * 4, st);
+    if (rc == PS_OK) rc = ps_launch<FrGatherK>(st, nnz, (const Fr*)sq->mat[i].val, (const uint32_t*)d_src, mt.val);
+    if (rc == PS_OK) rc = dev_sync(st);   // the host vectors go out of scope
   }
   Fr* d_z = ctx->arena.take<Fr>(n_gates + 1);
   if (rc == PS_OK && !d_z) rc = PS_ERR_ALLOC;

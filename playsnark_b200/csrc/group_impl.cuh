@@ -105,8 +105,8 @@ struct RecordSumK {
 
 // ---- GroupOps members ---------------------------------------------------------------------------------
 template <class F>
-int GroupOps<F>::msm_batch(ps_ctx* ctx, const MsmPlan& plan, const MsmTabs& tabs, XYZZ<F>* d_out) {
-  return msm_run_batch<F>(ctx, plan, tabs, d_out);
+int GroupOps<F>::msm_batch(ps_ctx* ctx, const MsmPlan& plan, const Affine<F>* slab, XYZZ<F>* d_out) {
+  return msm_run_batch<F>(ctx, plan, slab, d_out);
 }
 
 template <class F>

@@ -37,13 +37,8 @@ struct MsmPlan {
   int nseg, nsets;
   MsmSeg seg[MSM_MAX_SEG];
   uint32_t nbase[MSM_MAX_SEG];  // per output: points per table (table stride)
+  uint32_t toff[MSM_MAX_SEG];   // per output: offset (in points) of its first table inside the slab all outputs share
 };
-// per output: table base pointer; bucket b belongs to output (b >> log_d) / S
-struct MsmTabs {
-  const void* tab[MSM_MAX_SEG];
-  int log_d, S;
-};
-// ---- planning ------------------------------------------------------------------------------------------
 inline int msm_windows(int c) { return (255 + c - 1) / c; }
 
 // cost model (field multiplications) used to pick c when the bases carry no precomputed tables
@@ -84,8 +79,9 @@ template <> struct PointBytes<Fp2> { static constexpr int COMP = 96, AFF = 192; 
 // Every member enqueues kernels on ctx->stream and returns a PS_* status; scratch comes from ctx->arena.
 template <class F>
 struct GroupOps {
-  // the batched Pippenger pipeline (msm.cuh); results (XYZZ) to d_out[0..plan.nsets)
-  static int msm_batch(ps_ctx* ctx, const MsmPlan& plan, const MsmTabs& tabs, XYZZ<F>* d_out);
+  // the batched Pippenger pipeline (msm.cuh) over base sets that live in one allocation (`slab`; plan.toff gives each
+  // output's table offset); results (XYZZ) to d_out[0..plan.nsets)
+  static int msm_batch(ps_ctx* ctx, const MsmPlan& plan, const Affine<F>* slab, XYZZ<F>* d_out);
   // wire bytes (device) -> affine Montgomery points; *d_err |= 2 on a bad encoding / a point off the curve,
   // |= 4 on a point outside the prime-order subgroup (checked when subgroup_check is set)
   static int decode(ps_ctx* ctx, const uint8_t* d_in, size_t n, int format, Affine<F>* d_out, uint32_t* d_err, bool subgroup_check);

@@ -30,6 +30,7 @@ struct CsrDev {
 
 struct SparseQap {
   CsrDev mat[3];                 // left, right, out
+  CsrDev matT[3];                // their transposes (row_ptr over the variables, col = gate): the trusted setups sum over gates
   Fr* inv_zprime = nullptr;      // 1 / z'(j), j = 1..n
   std::vector<Fr*> ztree;        // level l: NTT_{2s} of every node's Z (s = 2^l), n/s nodes x 2s
   Fr* twist = nullptr;           // level l at offset 2s - 2 (s = 2^l): (1/2s) * omega_{4s}^t, t < 2s; l < k - 1
@@ -37,6 +38,7 @@ struct SparseQap {
   Fr* z_hat = nullptr;           // NTT_{2n} of z                                          (bit-reversed)
   void release() {
     for (auto& m : mat) { dev_free(m.row_ptr); dev_free(m.col); dev_free(m.val); }
+    for (auto& m : matT) { dev_free(m.row_ptr); dev_free(m.col); dev_free(m.val); }
     dev_free(inv_zprime); dev_free(s_hat); dev_free(z_hat); dev_free(twist);
     for (auto* p : ztree) dev_free(p);
     ztree.clear();

@@ -103,7 +103,7 @@ struct MsmScatterK {
     uint32_t k[8]; bool neg;
     msm_load_scalar(sg.scalars, i - sg.start, (int)sg.mont, k, neg);
     uint32_t carry = 0;
-    const uint32_t b0 = sg.set * (uint32_t)p.S * p.D, nbase = p.nbase[sg.set], pt = sg.first + (i - sg.start);
+    const uint32_t b0 = sg.set * (uint32_t)p.S * p.D, nbase = p.nbase[sg.set], pt = p.toff[sg.set] + sg.first + (i - sg.start);
     for (int w = 0; w < p.W; w++) {
       uint32_t mag; bool dneg;
       if (msm_next_digit(k, p.c, carry, mag, dneg)) {
@@ -149,10 +149,7 @@ struct MsmAccumK {
   // registers: G1 fits 3 resident blocks per SM without spilling; G2 (Fp2) is register-bound
   static constexpr int MIN_BLOCKS = sizeof(F) == sizeof(Fp) ? PS_G1_MINB : PS_G2_MINB;
   using Self = MsmAccumK<F>;
-  PS_DEV static const Affine<F>* table_of(const MsmTabs& tabs, uint32_t b) {
-    return (const Affine<F>*)tabs.tab[(b >> tabs.log_d) / (uint32_t)tabs.S];
-  }
-  PS_DEV static void run(uint32_t tid, uint32_t nb, uint32_t L, MsmTabs tabs, const uint32_t* ent,
+  PS_DEV static void run(uint32_t tid, uint32_t nb, uint32_t L, const Affine<F>* tab, const uint32_t* ent,
                          const uint32_t* off, XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid,
                          uint8_t* slot_fl) {
     const uint32_t M = off[nb];
@@ -165,7 +162,6 @@ struct MsmAccumK {
     uint32_t b = msm_find_bucket(off, nb, cur);
     bool head_open = off[b] < cur;
     uint32_t bend = off[b + 1];
-    const Affine<F>* tab = table_of(tabs, b);
     XYZZ<F> acc = XYZZ<F>::inf();
     // One flat loop of (at most) L iterations: every lane of the warp reaches the madd together; the
     // bucket hand-over is a short predicated block in front of it.
@@ -177,7 +173,6 @@ struct MsmAccumK {
         b++;
         while (off[b + 1] <= cur) b++;
         bend = off[b + 1];
-        tab = table_of(tabs, b);
       }
       // (an L2 prefetch of the next entry's base was measured slightly slower: 79.8 vs 78.8 ms at 2^24 --
       // the other resident warps already cover the gather latency)
@@ -561,7 +556,7 @@ static __global__ void __launch_bounds__(SCATTER2_BLOCK) k_scatter_stage(MsmPlan
     uint32_t k[8]; bool neg;
     msm_load_scalar(sg.scalars, i - sg.start, (int)sg.mont, k, neg);
     uint32_t carry = 0;
-    const uint32_t b0 = sg.set * (uint32_t)p.S * p.D, nbase = p.nbase[sg.set], pt = sg.first + (i - sg.start);
+    const uint32_t b0 = sg.set * (uint32_t)p.S * p.D, nbase = p.nbase[sg.set], pt = p.toff[sg.set] + sg.first + (i - sg.start);
 #pragma unroll
     for (int w = 0; w < SCATTER2_WMAX; w++) {
       if (w < p.W) {
@@ -604,7 +599,7 @@ inline int scatter_stage(ps_stream_t st, const MsmPlan& p, const uint32_t* off, 
     uint32_t k[8]; bool neg;
     msm_load_scalar(sg.scalars, i - sg.start, (int)sg.mont, k, neg);
     uint32_t carry = 0;
-    const uint32_t b0 = sg.set * (uint32_t)p.S * p.D, nbase = p.nbase[sg.set], pt = sg.first + (i - sg.start);
+    const uint32_t b0 = sg.set * (uint32_t)p.S * p.D, nbase = p.nbase[sg.set], pt = p.toff[sg.set] + sg.first + (i - sg.start);
     for (int w = 0; w < p.W; w++) {
       uint32_t mag; bool dneg;
       if (!msm_next_digit(k, p.c, carry, mag, dneg)) continue;
@@ -622,18 +617,18 @@ inline int scatter_stage(ps_stream_t st, const MsmPlan& p, const uint32_t* off, 
 
 // the hot kernel: G1 as is; G2 through the layout-identical Fp2I (inlined base-field products)
 template <class F>
-inline int launch_accum(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const MsmTabs& tabs, const uint32_t* ent, const uint32_t* off,
+inline int launch_accum(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const Affine<F>* tab, const uint32_t* ent, const uint32_t* off,
                         XYZZ<F>* buckets, XYZZ<F>* slot_pt, int32_t* slot_bid, uint8_t* slot_fl) {
-  PS_LAUNCH(MsmAccumK<F>, st, T1, nb, L, tabs, ent, off, buckets, slot_pt, slot_bid, slot_fl);
+  PS_LAUNCH(MsmAccumK<F>, st, T1, nb, L, tab, ent, off, buckets, slot_pt, slot_bid, slot_fl);
   return PS_OK;
 }
 // defined in accum_g2.cu (its own translation unit: the fully inlined kernel dominates compile time)
-int launch_accum_g2(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const MsmTabs& tabs, const uint32_t* ent, const uint32_t* off,
+int launch_accum_g2(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const Affine<Fp2>* tab, const uint32_t* ent, const uint32_t* off,
                     XYZZ<Fp2>* buckets, XYZZ<Fp2>* slot_pt, int32_t* slot_bid, uint8_t* slot_fl);
 template <>
-inline int launch_accum<Fp2>(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const MsmTabs& tabs, const uint32_t* ent,
+inline int launch_accum<Fp2>(ps_stream_t st, size_t T1, uint32_t nb, uint32_t L, const Affine<Fp2>* tab, const uint32_t* ent,
                              const uint32_t* off, XYZZ<Fp2>* buckets, XYZZ<Fp2>* slot_pt, int32_t* slot_bid, uint8_t* slot_fl) {
-  return launch_accum_g2(st, T1, nb, L, tabs, ent, off, buckets, slot_pt, slot_bid, slot_fl);
+  return launch_accum_g2(st, T1, nb, L, tab, ent, off, buckets, slot_pt, slot_bid, slot_fl);
 }
 
 // Launches tail kernel K over `items` work items: a team of four lanes per item when the grid is small
@@ -649,7 +644,7 @@ inline int launch_coop(bool team, ps_stream_t st, size_t items, Args... args) {
 
 // Runs the pipeline for a batch (plan + per-output tables); the nsets results (XYZZ) go to d_out[0..nsets).
 template <class F>
-int msm_run_batch(ps_ctx* ctx, const MsmPlan& g, const MsmTabs& tabs, XYZZ<F>* d_out) {
+int msm_run_batch(ps_ctx* ctx, const MsmPlan& g, const Affine<F>* tab, XYZZ<F>* d_out) {
   ps_stream_t st = ctx->stream;
   Arena& ar = ctx->arena;
   if (g.nsets < 1 || g.nsets > MSM_MAX_SEG || g.nseg < 0 || g.nseg > MSM_MAX_SEG) return PS_ERR_ARG;
@@ -717,7 +712,7 @@ int msm_run_batch(ps_ctx* ctx, const MsmPlan& g, const MsmTabs& tabs, XYZZ<F>* d
     int32_t* sb[2] = {ar.take<int32_t>(slots_a), ar.take<int32_t>(slots_b)};
     uint8_t* sf[2] = {ar.take<uint8_t>(slots_a), ar.take<uint8_t>(slots_b)};
     if (!sp[0] || !sp[1] || !sb[0] || !sb[1] || !sf[0] || !sf[1]) return PS_ERR_ALLOC;
-    PS_TRY((launch_accum<F>(st, T1, nb, L, tabs, ent, off, buckets, sp[0], sb[0], sf[0])));
+    PS_TRY((launch_accum<F>(st, T1, nb, L, tab, ent, off, buckets, sp[0], sb[0], sf[0])));
     PS_TRY(ctx_event(ctx, 2));
     PS_TRY((launch_coop<MsmRunMergeK, F>(team, st, T1, (uint32_t)T1, buckets, sp[0], sb[0], (const uint8_t*)sf[0])));
     {

@@ -22,18 +22,22 @@ struct ps_bases {
   size_t n = 0;
   int c = 0;  // fixed window (0 = choose per call)
   int T = 1;  // precomputed tables
-  void* tab = nullptr;
+  void* tab = nullptr;    // T tables of n affine points
+  void* slab = nullptr;   // the device allocation `tab` lives in: base sets of one slab can share an MSM pipeline
+  bool owns = true;       // false: a view into a slab owned by a key
 };
 
 struct ps_g16_key {
   size_t n = 0, n_nio = 0;
   ps_bases *A = nullptr, *B = nullptr, *C = nullptr;
+  void* slab_g1 = nullptr;   // A and C live in one allocation (their MSMs run as one batch)
 };
 
 struct ps_phgr13_key {
   size_t n = 0, n_mid = 0;
   ps_bases* g1[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // gsi vs ys vas was yas [vbs|wbs|ybs]
   ps_bases* ws = nullptr;
+  void* slab_g1 = nullptr;   // the seven G1 base sets live in one allocation
 };
 
 namespace ps {
@@ -49,6 +53,16 @@ int export_fr(ps_ctx* ctx, const Fr* d_src, size_t count, uint8_t* host_out);
 int run_quotient(ps_ctx* ctx, const ps_qap* q, const uint8_t* witness_be, QuotientBufs* o, bool want_c = false);
 int g16_build_scalars(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const uint8_t* witness_be, const uint8_t* r_be,
                       const uint8_t* s_be, G16Scalars* o);
+
+// Exponents of the trusted setups for a resident QAP (device memory, standard form; setup.cuh):
+//   Groth16: pw[n] = x^k; pwt[n-1] = x^k t(x) / delta; lp[m] = (beta u_i + alpha v_i + w_i) / gamma (i < m - n_io) or / delta;
+//            consts = alpha, beta, delta, gamma.       toxic = alpha, beta, delta, x, gamma (5 x 32 B big-endian)
+struct G16SetupScalars { Fr *pw, *pwt, *lp, *consts; };
+int g16_setup_scalars(ps_ctx* ctx, const ps_qap* q, const uint8_t* toxic_be, G16SetupScalars* o);
+//   PHGR13: pw[n-1] = s^k; ek[k][m] for k = vs ws ys vas was yas vbs wbs ybs (every variable; the evaluation key uses the
+//            last n_io); consts = av, aw, ay, gamma, beta*gamma, t(s)*ry.   toxic = s, av, aw, ay, rv, rw, beta, gamma
+struct Phgr13SetupScalars { Fr* pw; Fr* ek[9]; Fr* consts; };
+int phgr13_setup_scalars(ps_ctx* ctx, const ps_qap* q, const uint8_t* toxic_be, Phgr13SetupScalars* o);
 
 // host-only helpers shared by both translation units
 inline int parse_fr(const uint8_t* src, Fr* out) {   // 32 B big-endian, canonical -> Montgomery

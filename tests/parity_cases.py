@@ -667,3 +667,52 @@ def multi_msm_case(lib, ndev, group, n, devices=None, window_bits=0, tables=1):
         b2.close(); bases.close()
     finally:
         mb.close()
+
+
+def device_setups_vs_oracle(be, n=12, seed=3):
+    """ps_g16_setup / ps_phgr13_setup (the trusted setups on the device, from injected toxic waste) against the
+    oracle's NewGroth16TrustedSetup / NewPHGR13TrustedSetup restatements: every key element byte for byte, for the
+    dense QAP and for the sparse R1CS form of the same circuit; then prove with the device-made keys."""
+    r, w = H.mixed_circuit(n, seed, max(1, n // 2)) if n & (n - 1) == 0 else H.mixed_circuit(n, seed, max(1, n // 2))
+    oq = O.to_qap(r)
+    dense = H.mirror_qap(oq)
+    forms = [dense]
+    if n & (n - 1) == 0:
+        forms.append(api.SparseQAP.from_dense_rows(len(r.vars), r.nb_io(), r.left, r.right, r.out))
+    g1, g2 = O.g1_compress, O.g2_compress
+    otr = O.groth16_setup(oq, O.Sampler(seed))
+    toxic = tuple(otr.tw[k] for k in ("Alpha", "Beta", "Delta", "X", "Gamma"))
+    smp = O.Sampler(seed + 50)
+    rr, ss = smp.fr(), smp.fr()
+    want = O.groth16_prove(otr, oq, w, rr, ss)
+    ost = O.phgr13_setup(oq, O.Sampler(seed + 1))
+    s2 = O.Sampler(seed + 1)
+    ptoxic = [s2.fr() for _ in range(7)]            # s av aw ay rv rw beta
+    ptoxic.append(s2.fr())                          # gamma
+    pwant = O.phgr13_prove(ost["EK"], oq, w)
+    for q in forms:
+        tr = api.NewGroth16TrustedSetup(q, backend=be, toxic=toxic, fmt=L.PS_FMT_COMPRESSED)
+        cut = lambda raw, per: [raw[i:i + per] for i in range(0, len(raw), per)]
+        assert cut(tr.Xi, 48) == [g1(p) for p in otr.Xi] and cut(tr.Xi2, 96) == [g2(p) for p in otr.Xi2]
+        assert cut(tr.XiT, 48) == [g1(p) for p in otr.XiT] and cut(tr.NioLP, 48) == [g1(p) for p in otr.NioLP]
+        assert tr.IoLP == [g1(p) for p in otr.IoLP] and tr.Gamma == g2(otr.Gamma)
+        assert (tr.Alpha, tr.Beta, tr.Delta, tr.Beta2, tr.Delta2) == (g1(otr.Alpha), g1(otr.Beta), g1(otr.Delta), g2(otr.Beta2), g2(otr.Delta2))
+        pr = api.Groth16Prove(tr, q, w, rr, ss, backend=be)       # resident key straight from the setup
+        assert (pr.A, pr.B, pr.C) == (g1(want["A"]), g2(want["B"]), g1(want["C"]))
+        tr.close()
+        pr = api.Groth16Prove(tr, q, w, rr, ss, backend=be)       # the same key reloaded from its exported bytes
+        assert (pr.A, pr.B, pr.C) == (g1(want["A"]), g2(want["B"]), g1(want["C"]))
+        tr.close()
+        ek, vk, _ = api.NewPHGR13TrustedSetup(q, backend=be, toxic=ptoxic, with_vk=True)
+        pp = api.PHGR13Prove(ek, q, w, backend=be)
+        for f in O.PHGR13_FIELDS:
+            assert getattr(pp, f) == (g2 if f == "wss" else g1)(pwant[f]), f
+        ek.export()
+        for name, pts in ost["EK"].items():
+            assert getattr(ek, name) == [(g2 if name == "ws" else g1)(p) for p in pts], name
+        ovk = ost["VK"]
+        assert vk["av"] == g2(ovk["av"]) and vk["aw"] == g1(ovk["aw"]) and vk["ay"] == g2(ovk["ay"])
+        assert vk["gamma"] == g2(ovk["gamma"]) and vk["bgamma"] == g1(ovk["bgamma"]) and vk["bgamma2"] == g2(ovk["bgamma2"])
+        assert vk["yts"] == g2(ovk["yts"])
+        assert vk["vs"] == [g1(p) for p in ovk["vs"]] and vk["ws"] == [g2(p) for p in ovk["ws"]] and vk["ys"] == [g1(p) for p in ovk["ys"]]
+        ek.close(); q.close()

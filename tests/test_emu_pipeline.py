@@ -81,6 +81,10 @@ def test_readme_flow_through_api(be): P.readme_flow_through_api(be)
 def test_sparse_phgr13_exponent_check(be): P.phgr13_sparse_exponent_check(be, 4, seed=11)
 
 
+@pytest.mark.parametrize("n", [8, 5])
+def test_device_setups_vs_oracle(be, n): P.device_setups_vs_oracle(be, n, seed=n)
+
+
 @pytest.mark.parametrize("parts,world", [(1, 2), (2, 3), (4, 5)])
 def test_sharded_steps_recombine(be, parts, world): P.sharded_steps_recombine(be, 4, parts, world, seed=21 + parts)
 

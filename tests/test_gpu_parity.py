@@ -139,6 +139,10 @@ def test_config_c2_dense_2p10(be):
 def test_readme_flow_through_api(be): P.readme_flow_through_api(be)
 
 
+@pytest.mark.parametrize("n", [16, 13, 64])
+def test_device_setups_vs_oracle(be, n): P.device_setups_vs_oracle(be, n, seed=n)
+
+
 @pytest.mark.parametrize("log_n,parts,world", [(6, 1, 2), (10, 4, 8), (14, 2, 3)])
 def test_sharded_steps_recombine(be, log_n, parts, world):
     # every entry point of the multi-GPU Groth16 flow, recombined on one GPU against ps_g16_prove
