@@ -100,6 +100,9 @@ int ps_msm(ps_ctx* ctx, const ps_bases* b, const uint8_t* scalars_be, size_t n, 
  * in device memory `d_out_xyzz` (192 B G1 / 384 B G2).                                          */
 int ps_msm_device(ps_ctx* ctx, const ps_bases* b, size_t first, const void* d_scalars_le, size_t n,
                   void* d_out_xyzz);
+/* the same with the scalars in Montgomery form, as ps_fr_upload leaves them (host wire bytes -> device limbs) */
+int ps_msm_device_mont(ps_ctx* ctx, const ps_bases* b, size_t first, const void* d_scalars_mont, size_t n,
+                       void* d_out_xyzz);
 /* sum `count` XYZZ partials (device memory, contiguous) and emit the compressed point: the single
  * small gather of the multi-GPU MSM.                                                            */
 int ps_msm_combine(ps_ctx* ctx, int group, const void* d_partials_xyzz, size_t count, uint8_t* out);

@@ -38,6 +38,7 @@ SYMBOLS = [
     ("ps_bases_export", _I, [_P, _P, _SZ, _SZ, _I, _P]),
     ("ps_msm", _I, [_P, _P, _P, _SZ, _P]),
     ("ps_msm_device", _I, [_P, _P, _SZ, _P, _SZ, _P]),
+    ("ps_msm_device_mont", _I, [_P, _P, _SZ, _P, _SZ, _P]),
     ("ps_msm_combine", _I, [_P, _I, _P, _SZ, _P]),
     ("ps_ntt_fr", _I, [_P, _P, C.c_uint, _I, _B]),
     ("ps_qap_load_dense", _I, [_P, _SZ, _SZ, _SZ, _B, _B, _B, _B, C.POINTER(_P)]),

@@ -221,30 +221,40 @@ int bases_concat_into(ps_ctx* ctx, ps_bases* b, int format, const uint8_t* const
   return bases_fill_t<F>(ctx, b, buf.data(), format);
 }
 
-// one window for every base set of a key, so that their MSMs can share a pipeline (msm_batch): sized for the
-// average base set of the key, per shard
-int key_window(ps_ctx* ctx, size_t total_points, int nsets) {
+// window of a batch of `nsets` MSMs over `total_points` points in all (per shard): every set pays its own bucket
+// merge + reduction, the mixed additions are shared (same model as msm_pick_window_full, which is the case nsets = 1)
+int batch_window(ps_ctx* ctx, size_t total_points, int nsets) {
   const size_t shards = (size_t)(ctx->msm_shards > 0 ? ctx->msm_shards : 1);
-  return msm_pick_window_full(total_points / (size_t)(nsets > 0 ? nsets : 1) / shards + 1, (double)ctx->msm_bucket_cost);
+  const double n = (double)(total_points / shards + 1), bucket_cost = (double)ctx->msm_bucket_cost * (nsets > 0 ? nsets : 1);
+  int best = 4; double best_cost = 1e300;
+  for (int c = 4; c <= 24; c++) {
+    double W = msm_windows(c);
+    if (n * W >= 2.0e9) continue;
+    double cost = n * W * 10.0 + (double)(1u << (c - 1)) * bucket_cost;
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
 }
 
 // allocates the three base sets of a Groth16 key: A and C carved out of one G1 slab, B (G2) on its own
-int g16_key_alloc(ps_g16_key* k, size_t nA, size_t nB, size_t nC, int window_bits) {
+int g16_key_alloc(ps_g16_key* k, size_t nA, size_t nB, size_t nC, int window_g1, int window_g2) {
   const size_t g1counts[2] = {nA, nC};
   ps_bases* g1[2] = {nullptr, nullptr};
-  PS_TRY(bases_alloc_slab(PS_G1, g1counts, 2, window_bits, &k->slab_g1, g1));
+  PS_TRY(bases_alloc_slab(PS_G1, g1counts, 2, window_g1, &k->slab_g1, g1));
   k->A = g1[0]; k->C = g1[1];
   void* slab_b = nullptr;
-  PS_TRY(bases_alloc_slab(PS_G2, &nB, 1, window_bits, &slab_b, &k->B));
+  PS_TRY(bases_alloc_slab(PS_G2, &nB, 1, window_g2, &slab_b, &k->B));
   k->B->owns = true;    // a one-set slab: the base set owns its allocation
   return PS_OK;
 }
 // the eight base sets of a PHGR13 evaluation key: the seven G1 ones in one slab
-int phgr13_key_alloc(ps_phgr13_key* k, size_t n_gates, size_t n_mid, int window_bits) {
+int phgr13_key_alloc(ps_ctx* ctx, ps_phgr13_key* k, size_t n_gates, size_t n_mid) {
   const size_t counts[7] = {n_gates - 1, n_mid, n_mid, n_mid, n_mid, n_mid, 3 * n_mid};
-  PS_TRY(bases_alloc_slab(PS_G1, counts, 7, window_bits, &k->slab_g1, k->g1));
+  // the seven G1 sums of a proof run as one batch (pinochio.go:218-242 sums the same solution[diff:] against eight base
+  // vectors); wss (G2) on its own
+  PS_TRY(bases_alloc_slab(PS_G1, counts, 7, batch_window(ctx, n_gates - 1 + 8 * n_mid, 7), &k->slab_g1, k->g1));
   void* slab_w = nullptr;
-  PS_TRY(bases_alloc_slab(PS_G2, &n_mid, 1, window_bits, &slab_w, &k->ws));
+  PS_TRY(bases_alloc_slab(PS_G2, &n_mid, 1, batch_window(ctx, n_mid, 1), &slab_w, &k->ws));
   k->ws->owns = true;
   return PS_OK;
 }
@@ -479,6 +489,14 @@ int ps_msm_device(ps_ctx* ctx, const ps_bases* b, size_t first, const void* d_sc
   return msm_on_bases<Fp2>(ctx, b, first, (const uint32_t*)d_scalars_le, n, 0, (G2XYZZ*)d_out_xyzz);
 }
 
+/* the same with the scalars in Montgomery form (what ps_fr_upload leaves on the device) */
+int ps_msm_device_mont(ps_ctx* ctx, const ps_bases* b, size_t first, const void* d_scalars_mont, size_t n, void* d_out_xyzz) {
+  if (!b || !d_out_xyzz || (n && !d_scalars_mont)) return PS_ERR_ARG;
+  PS_TRY(begin_call(ctx));
+  if (b->group == PS_G1) return msm_on_bases<Fp>(ctx, b, first, (const uint32_t*)d_scalars_mont, n, 1, (G1XYZZ*)d_out_xyzz);
+  return msm_on_bases<Fp2>(ctx, b, first, (const uint32_t*)d_scalars_mont, n, 1, (G2XYZZ*)d_out_xyzz);
+}
+
 int ps_msm_combine(ps_ctx* ctx, int group, const void* d_partials_xyzz, size_t count, uint8_t* out) {
   if (!d_partials_xyzz || !out || (group != PS_G1 && group != PS_G2)) return PS_ERR_ARG;
   PS_TRY(begin_call(ctx));
@@ -545,9 +563,9 @@ int ps_g16_key_load(ps_ctx* ctx, size_t n_gates, size_t n_nio, int format, const
   const uint8_t* pb[3] = {xi2, delta2, beta2};
   const uint8_t* pc[6] = {niolp, xit, xi, alpha, beta, delta};
   const size_t cc[6] = {n_nio, n_gates - 1, n_gates, 1, 1, 1};
-  // one window for the whole key: A and C share a pipeline
-  const int c = key_window(ctx, 4 * n_gates + n_nio + 6, 3);
-  int rc = g16_key_alloc(k, n_gates + 2, n_gates + 2, n_nio + (n_gates - 1) + n_gates + 3, c);
+  // A and C share a pipeline (one window for both); B has its own
+  int rc = g16_key_alloc(k, n_gates + 2, n_gates + 2, n_nio + (n_gates - 1) + n_gates + 3,
+                         batch_window(ctx, 3 * n_gates + n_nio + 4, 2), batch_window(ctx, n_gates + 2, 1));
   if (rc == PS_OK) rc = bases_concat_into<Fp>(ctx, k->A, format, pa, ca, 3);
   if (rc == PS_OK) rc = ctx->arena.reset();
   if (rc == PS_OK) rc = bases_concat_into<Fp2>(ctx, k->B, format, pb, ca, 3);
@@ -606,7 +624,7 @@ int ps_g16_prove(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap, const ui
 
 extern "C++" {
 namespace ps {
-int g16_key_load_slice(ps_ctx* ctx, const KeySlice& sl, int format, int window_bits, const uint8_t* xi, const uint8_t* xi2,
+int g16_key_load_slice(ps_ctx* ctx, const KeySlice& sl, int format, int window_g1, int window_g2, const uint8_t* xi, const uint8_t* xi2,
                        const uint8_t* xit, const uint8_t* niolp, const uint8_t* alpha, const uint8_t* beta, const uint8_t* delta,
                        const uint8_t* beta2, const uint8_t* delta2, ps_g16_key** key) {
   if (!key || sl.x_hi < sl.x_lo || sl.t_hi < sl.t_lo || sl.n_hi < sl.n_lo) return PS_ERR_ARG;
@@ -622,7 +640,7 @@ int g16_key_load_slice(ps_ctx* ctx, const KeySlice& sl, int format, int window_b
   const uint8_t* pb[3] = {xi2 + sl.x_lo * g2, delta2, beta2};
   const uint8_t* pc[6] = {niolp ? niolp + sl.n_lo * g1 : niolp, xit + sl.t_lo * g1, xi + sl.x_lo * g1, alpha, beta, delta};
   const size_t cc[6] = {nn, nt, nx, one, one, one};
-  int rc = g16_key_alloc(k, nx + 2 * one, nx + 2 * one, nn + nt + nx + 3 * one, window_bits);
+  int rc = g16_key_alloc(k, nx + 2 * one, nx + 2 * one, nn + nt + nx + 3 * one, window_g1, window_g2);
   if (rc == PS_OK) rc = bases_concat_into<Fp>(ctx, k->A, format, pa, ca, 3);
   if (rc == PS_OK) rc = ctx->arena.reset();
   if (rc == PS_OK) rc = bases_concat_into<Fp2>(ctx, k->B, format, pb, ca, 3);
@@ -711,9 +729,8 @@ int ps_g16_setup(ps_ctx* ctx, const ps_qap* qap, const uint8_t* toxic_be, ps_g16
   ps_g16_key* k = new (std::nothrow) ps_g16_key();
   if (!k) return PS_ERR_ALLOC;
   k->n = n; k->n_nio = nio;
-  const int c = key_window(ctx, 4 * n + nio + 6, 3);
   const Fr *alpha = sc.consts, *beta = sc.consts + 1, *delta = sc.consts + 2, *gamma = sc.consts + 3;
-  int rc = g16_key_alloc(k, n + 2, n + 2, nio + (n - 1) + n + 3, c);
+  int rc = g16_key_alloc(k, n + 2, n + 2, nio + (n - 1) + n + 3, batch_window(ctx, 3 * n + nio + 4, 2), batch_window(ctx, n + 2, 1));
   if (rc == PS_OK) rc = fill_from_scalars<Fp>(ctx, k->A, 0, sc.pw, n);
   if (rc == PS_OK) rc = fill_from_scalars<Fp>(ctx, k->A, n, delta, 1);
   if (rc == PS_OK) rc = fill_from_scalars<Fp>(ctx, k->A, n + 1, alpha, 1);
@@ -843,10 +860,7 @@ int ps_phgr13_key_load(ps_ctx* ctx, size_t n_gates, size_t n_mid, int format, co
   k->n = n_gates; k->n_mid = n_mid;
   const uint8_t* singles[6] = {gsi, vs, ys, vas, was, yas};
   const size_t counts[6] = {n_gates - 1, n_mid, n_mid, n_mid, n_mid, n_mid};
-  // one window for the whole key: its seven G1 sums share a pipeline (pinochio.go:218-242 sums the same
-  // solution[diff:] against eight base vectors)
-  const int c = key_window(ctx, n_gates - 1 + 9 * n_mid, 8);
-  int rc = phgr13_key_alloc(k, n_gates, n_mid, c);
+  int rc = phgr13_key_alloc(ctx, k, n_gates, n_mid);
   for (int i = 0; i < 6 && rc == PS_OK; i++) {
     rc = bases_concat_into<Fp>(ctx, k->g1[i], format, &singles[i], &counts[i], 1);
     if (rc == PS_OK) rc = ctx->arena.reset();
@@ -875,10 +889,9 @@ int ps_phgr13_setup(ps_ctx* ctx, const ps_qap* qap, const uint8_t* toxic_be, ps_
   ps_phgr13_key* k = new (std::nothrow) ps_phgr13_key();
   if (!k) return PS_ERR_ALLOC;
   k->n = n; k->n_mid = nmid;
-  const int c = key_window(ctx, n - 1 + 9 * nmid, 8);
   // g1[]: gsi vs ys vas was yas [vbs|wbs|ybs];  ek[]: vs ws ys vas was yas vbs wbs ybs
   const int ek_of_g1[6] = {-1, 0, 2, 3, 4, 5};
-  int rc = phgr13_key_alloc(k, n, nmid, c);
+  int rc = phgr13_key_alloc(ctx, k, n, nmid);
   if (rc == PS_OK) rc = fill_from_scalars<Fp>(ctx, k->g1[0], 0, sc.pw, n - 1);
   for (int i = 1; i < 6 && rc == PS_OK; i++) rc = fill_from_scalars<Fp>(ctx, k->g1[i], 0, sc.ek[ek_of_g1[i]] + diff, nmid);
   for (int t = 0; t < 3 && rc == PS_OK; t++) rc = fill_from_scalars<Fp>(ctx, k->g1[6], (size_t)t * nmid, sc.ek[6 + t] + diff, nmid);

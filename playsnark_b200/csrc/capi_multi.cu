@@ -454,11 +454,21 @@ int ps_mg16_key_load(ps_mctx* m, size_t n_gates, size_t n_nio, int format, const
   const std::vector<double> w = shard_weights(m);
   const std::vector<size_t> cx = weighted_cuts(n_gates, w), ct = weighted_cuts(n_gates - 1, w), cn = weighted_cuts(n_nio, w);
   for (int d = 0; d < m->ndev; d++) k->slice[d] = KeySlice{cx[d], cx[d + 1], ct[d], ct[d + 1], cn[d], cn[d + 1], d == 0};
-  // one window for every base set of every device: sized for the average MSM a device runs
-  const size_t per_dev = (4 * n_gates + n_nio) / (size_t)m->ndev / 3 + 1;
-  const int c = msm_pick_window_full(per_dev, (double)m->ctx[0]->msm_bucket_cost);
+  // windows sized for what one device runs: the early G1 batch (A_d and the h-free pieces of C_d: two outputs) and B_d
+  const size_t nd = (size_t)m->ndev;
+  const double bc = (double)m->ctx[0]->msm_bucket_cost;
+  auto window = [&](size_t points, int nsets) {
+    int best = 4; double best_cost = 1e300;
+    for (int c = 4; c <= 24; c++) {
+      double W = msm_windows(c), cost = (double)(points + 1) * W * 10.0 + (double)(1u << (c - 1)) * bc * nsets;
+      if ((double)points * W >= 2.0e9) continue;
+      if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+  };
+  const int c_g1 = window((2 * n_gates + n_nio) / nd, 2), c_g2 = window(n_gates / nd, 1);
   int rc = run_all(m, [&](int d) -> int {
-    return g16_key_load_slice(m->ctx[d], k->slice[d], format, c, xi, xi2, xit, niolp, alpha, beta, delta, beta2, delta2, &k->part[d]);
+    return g16_key_load_slice(m->ctx[d], k->slice[d], format, c_g1, c_g2, xi, xi2, xit, niolp, alpha, beta, delta, beta2, delta2, &k->part[d]);
   });
   if (rc != PS_OK) { ps_mg16_key_free(k); return rc; }
   *key = k;

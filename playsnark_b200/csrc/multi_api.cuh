@@ -11,8 +11,9 @@ namespace ps {
 struct KeySlice { size_t x_lo, x_hi, t_lo, t_hi, n_lo, n_hi; bool consts; };
 
 // the per-device part of a sharded Groth16 key: base sets A_d = [Xi_d | Delta Alpha], B_d = [Xi2_d | Delta2 Beta2],
-// C_d = [NioLP_d | XiT_d | Xi_d | Alpha Beta Delta] (single points on the `consts` device only), one window
-int g16_key_load_slice(ps_ctx* ctx, const KeySlice& sl, int format, int window_bits, const uint8_t* xi, const uint8_t* xi2,
+// C_d = [NioLP_d | XiT_d | Xi_d | Alpha Beta Delta] (single points on the `consts` device only); one window for the G1
+// pair (they share a pipeline), one for B_d
+int g16_key_load_slice(ps_ctx* ctx, const KeySlice& sl, int format, int window_g1, int window_g2, const uint8_t* xi, const uint8_t* xi2,
                        const uint8_t* xit, const uint8_t* niolp, const uint8_t* alpha, const uint8_t* beta, const uint8_t* delta,
                        const uint8_t* beta2, const uint8_t* delta2, ps_g16_key** key);
 
