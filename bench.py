@@ -54,6 +54,38 @@ def env_int(name, default):
         return default
 
 
+_T0 = time.perf_counter()
+_STATE = {"section": "start", "line": None, "printed": False}
+
+
+def progress(section: str):
+    """one stderr line per section (the JSON line is printed once, at the end): where a slow or hung run stopped"""
+    _STATE["section"] = section
+    print("[bench %7.1fs] %s" % (time.perf_counter() - _T0, section), file=sys.stderr, flush=True)
+
+
+def start_watchdog(limit_s: float):
+    """The driver needs ONE JSON line within minutes.  If a secondary section (after the headline was measured) does
+    not finish by `limit_s`, print the line as far as it got -- naming the section -- and leave; before the headline
+    exists there is nothing to print and the run fails loudly."""
+    def fire():
+        import faulthandler
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        line = _STATE["line"]
+        if line is not None and not _STATE["printed"]:
+            line["watchdog"] = "section %r did not finish within %.0f s; later sections are missing" % (_STATE["section"], limit_s)
+            print(json.dumps(line), flush=True)
+            os._exit(0)
+        if _STATE.get("rank", 0) != 0:
+            os._exit(0)
+        print("bench.py: watchdog fired in section %r before the headline line existed" % _STATE["section"], file=sys.stderr, flush=True)
+        os._exit(4)
+    t = threading.Timer(limit_s, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def random_scalars_be(n: int, seed: int):
     """n uniform 254-bit scalars as big-endian 32-byte rows (numpy uint8 [n, 32])."""
     import numpy as np
@@ -229,6 +261,7 @@ def main():
                     help="also time a full Groth16 prove on a sparse synthetic circuit of 2^k constraints (0 = skip)")
     ap.add_argument("--phgr13-log-n", default="16,20", help="PHGR13 prove sizes (one GPU; '' = skip)")
     ap.add_argument("--cpu-budget-s", type=float, default=30.0, help="time budget of the CPU Groth16 flow")
+    ap.add_argument("--watchdog-s", type=float, default=900.0, help="print the line as far as it got after this many seconds")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3
@@ -241,6 +274,9 @@ def main():
     from playsnark_b200 import _lib as L
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    _STATE["rank"] = rank
+    start_watchdog(args.watchdog_s)
+    progress("init (rank %d of %d)" % (rank, world))
     dist = None
     host_group = None
     if world > 1:
@@ -256,6 +292,7 @@ def main():
     lib = be.lib
 
     n = 1 << args.log_n
+    progress("G1 bases 2^%d" % args.log_n)
     # synthetic inputs: bases k_i*G (fixed-base kernel on the device, untimed), scalars uniform < 2^254
     ks = random_scalars_be(n, 1000 + rank)
     sc_be = random_scalars_be(n, 2000 + rank)
@@ -295,6 +332,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    progress("G1 warm-up + parity")
     for _ in range(args.warmup):
         step_resident()
     barrier()
@@ -313,6 +351,7 @@ def main():
     be._check(lib.ps_bench_fieldmul(be.ctx, 1, 1000, C.byref(v), C.byref(ms_)))
     fpmul_rate = v.value
 
+    progress("G1 timed region")
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -334,6 +373,7 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     # e2e: host buffers in, host bytes out, copies inside the timed region
+    progress("G1 e2e")
     for _ in range(2):
         step_e2e()
     barrier()
@@ -354,6 +394,7 @@ def main():
     # its points, base set loaded with the window sized for that share), partials all-gathered, summed on rank 0
     strong = None
     if world > 1:
+        progress("G1 strong scaling")
         ns = n // world
         bases_s = be.bases_from_scalars(L.PS_G1, ks[:ns].tobytes(), args.window_bits, args.tables)
         d_sc_s = d_scalars[:ns].contiguous()
@@ -385,6 +426,7 @@ def main():
     for tok in [t for t in str(args.g2_log_n).split(",") if t.strip()]:
         k2 = int(tok)
         n2 = 1 << k2
+        progress("G2 MSM 2^%d" % k2)
         ks2, sc2 = random_scalars_be(n2, 3000 + rank + 16 * k2), random_scalars_be(n2, 4000 + rank + 16 * k2)
         bases2 = be.bases_from_scalars(L.PS_G2, ks2.tobytes(), args.window_bits, args.tables)
         d_sc2 = torch.from_numpy(be_to_le_limbs(sc2).view(np.int32)).to(dev)
@@ -483,6 +525,7 @@ def main():
         line["msm_strong"] = {"metric": "g1_msm_points_per_s", "scaling": "strong", "total_points": n, "n_gpus": world,
                               "points_per_gpu": n // world, "ms_per_step": strong["ms"] / args.steps,
                               "value": float(n) * args.steps / (strong["ms"] * 1e-3), "window_bits": strong["c"], "windows": strong["W"]}
+    _STATE["line"] = line
     if g2_runs:
         def g2_entry(g):
             n2 = 1 << g["log_n"]
@@ -498,6 +541,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         from oracle import c_oracle as CO
         threads = CO.max_threads()
+        progress("CPU baseline: BlindEval")
         rate1, reps1, _ = cpu_blind_eval(10, 1, 3.0, 20)
         rate, reps, dt = cpu_blind_eval(args.ref_log_n, threads, 6.0, 40)
         line["cpu_baseline"] = {
@@ -506,11 +550,13 @@ def main():
                       "term as algebra.go:348-359), terms spread over %d OpenMP threads of %d host cores; single-threaded "
                       "(as the Go reference runs): %.0f points/s" % (reps, args.ref_log_n, threads, os.cpu_count() or 0, rate1),
             "single_thread_value": rate1}
+        progress("CPU baseline: Groth16 flow")
         try:
             line["cpu_baseline"]["groth16_flow"] = cpu_groth16_flow(args.cpu_budget_s)
         except Exception as e:
             line["cpu_baseline"]["groth16_flow"] = {"error": repr(e)}
     if args.groth16_log_n:
+        progress("Groth16 2^%d" % args.groth16_log_n)
         try:
             line["groth16"] = groth16_section(be, args, world)
         except Exception as e:  # the headline metric must still be reported
@@ -527,7 +573,9 @@ def main():
                 line["small_configs"] = small_configs_section(be, line.get("cpu_baseline", {}).get("groth16_flow"))
             except Exception as e:
                 line["small_configs"] = {"error": repr(e)}
+    _STATE["printed"] = True
     print(json.dumps(line), flush=True)
+    progress("done")
     if world > 1:
         dist.barrier(group=host_group)
         dist.destroy_process_group()
@@ -562,10 +610,12 @@ def groth16_section(be, args, world):
     smp = O.Sampler(99)
     toxic = tuple(smp.fr() for _ in range(5))
     r, s = smp.fr(), smp.fr()
+    progress("Groth16: setup on the device")
     t0 = time.perf_counter()
     tr = ps.NewGroth16TrustedSetup(sq, backend=be, toxic=toxic, export=world > 1)
     be.sync()
     t_setup = time.perf_counter() - t0
+    progress("Groth16: prove")
     reps = max(3, args.steps)
     out = {"constraints": n, "variables": sq.nbVars, "nio_points": sq.nbIO, "n_gpus": world, "setup_on_device_s": round(t_setup, 2),
            "h2d_bytes_per_proof": 32 * sq.nbVars + 64, "d2h_bytes_per_proof": 192}
@@ -597,6 +647,7 @@ def groth16_section(be, args, world):
     out["proof_ms_e2e"] = avg * 1e3
     out["proof_ms_e2e_best"] = best * 1e3
     out["proofs_per_s_e2e"] = 1.0 / avg
+    progress("Groth16: expectation")
     A, B, Cc, _, _ = E.groth16_expected(sq, wit, toxic, r, s)
     out["parity"] = ("A, B, C equal the exponent-level recomputation from the toxic waste"
                      if (pr.A, pr.B, pr.C) == (A, B, Cc) else "MISMATCH")
@@ -616,16 +667,20 @@ def phgr13_section(be, sizes):
     res = {}
     for k in sizes:
         n = 1 << k
+        progress("PHGR13 2^%d: circuit" % k)
         sq, wit = synth.sparse_circuit(n, 11 + k, n // 2)
         smp = O.Sampler(500 + k)
         toxic = tuple(smp.fr() for _ in range(8))
+        progress("PHGR13 2^%d: setup" % k)
         t0 = time.perf_counter()
         ek, _, _ = ps.NewPHGR13TrustedSetup(sq, backend=be, toxic=toxic)
         be.sync()
         t_setup = time.perf_counter() - t0
+        progress("PHGR13 2^%d: prove" % k)
         wb = ps.HostBuffer(be, b"".join(v.to_bytes(32, "big") for v in wit))
         avg, best = _time_calls(lambda: ps.PHGR13Prove(ek, sq, wb, backend=be), 5)
         pp = ps.PHGR13Prove(ek, sq, wb, backend=be)
+        progress("PHGR13 2^%d: expectation" % k)
         want = E.phgr13_expected(sq, wit, toxic)
         okp = all(getattr(pp, f) == want[f] for f in O.PHGR13_FIELDS)
         res["2p%d" % k] = {"constraints": n, "mid_points": sq.nbIO, "prove_ms_e2e": avg * 1e3, "prove_ms_e2e_best": best * 1e3,
@@ -650,6 +705,7 @@ def small_configs_section(be, cpu_flow):
     cpu_by_n = {row["gates"]: row for row in (cpu_flow or {}).get("runs", [])} if isinstance(cpu_flow, dict) else {}
     for k in (4, 6, 8, 10):
         n = 1 << k
+        progress("chain circuit 2^%d" % k)
         c, w = synth.squaring_chain(n, -1)
         q = ps.ToQAP(c)
         tr = ps.NewGroth16TrustedSetup(q, backend=be, toxic=toxic, export=False)
@@ -670,6 +726,7 @@ def small_configs_section(be, cpu_flow):
         out["chain_2p%d" % k] = row
         tr.close(); ek.close(); q.close()
     k = 16
+    progress("sparse circuit 2^16")
     nn = 1 << k
     sq, wit = synth.sparse_circuit(nn, 7, nn // 2)
     tr = ps.NewGroth16TrustedSetup(sq, backend=be, toxic=toxic, export=False)

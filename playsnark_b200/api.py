@@ -569,8 +569,9 @@ def NewGroth16TrustedSetup(qap, backend: Optional[Backend] = None, toxic=None, f
     iolp = C.create_string_buffer(max(1, diff * 48))
     gamma = C.create_string_buffer(96)
     b._check(b.lib.ps_g16_setup(b.ctx, qh, _fr_bytes(list(toxic)), C.byref(kh), iolp, gamma))
+    iolp_raw = iolp.raw          # ONE copy of the buffer (ctypes' .raw copies on every access)
     tr = Groth16Setup(Alpha=b"", Beta=b"", Delta=b"", Xi=b"", NioLP=b"", XiT=b"", Beta2=b"", Delta2=b"", Xi2=b"",
-                      IoLP=[iolp.raw[i * 48:(i + 1) * 48] for i in range(diff)], Gamma=gamma.raw, fmt=fmt)
+                      IoLP=[iolp_raw[i * 48:(i + 1) * 48] for i in range(diff)], Gamma=gamma.raw, fmt=fmt)
     tr.tw = dict(zip(("Alpha", "Beta", "Delta", "X", "Gamma"), toxic))
     tr._dev = _DevHandle(b, kh, "ps_g16_key_free")
     if export:

@@ -83,6 +83,32 @@ def build_cuda(force: bool = False, verbose: bool = False, out: str = LIB, extra
     return out
 
 
+def build_variant(name: str, flags, tus=("capi_poly.cu",)) -> str:
+    """A/B builds for kernel tuning: the listed translation units recompiled with extra -D flags, linked with the
+    standard objects of the others into playsnark_b200/variants/lib_<name>.so (loaded through
+    PLAYSNARK_B200_LIB by the tools/ab_*.py scripts)."""
+    build_cuda()
+    nvcc = os.environ.get("NVCC", "nvcc")
+    vdir = os.path.join(OBJ, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for src in CU_SOURCES:
+        base = os.path.basename(src)
+        if base in tus:
+            obj = os.path.join(vdir, "%s_%s.o" % (base[:-3], name))
+            if stale(obj, _deps(src)):
+                cmd = [nvcc] + NVCC_FLAGS + list(flags) + ["-split-compile", "0", "-c", "-o", obj, src]
+                print("[playsnark_b200] " + " ".join(cmd), file=sys.stderr)
+                subprocess.check_call(cmd, cwd=ROOT)
+        else:
+            obj = os.path.join(OBJ, base[:-3] + ".o")
+        objs.append(obj)
+    os.makedirs(os.path.join(HERE, "variants"), exist_ok=True)
+    out = os.path.join(HERE, "variants", "lib_%s.so" % name)     # outside _build/: shipped to the GPU box
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs, cwd=ROOT)
+    return out
+
+
 def build_host_emulation(out_dir: str) -> str:
     """TEST-ONLY: the same sources with -DPS_HOST_EMU (kernel bodies driven by serial loops)."""
     os.makedirs(out_dir, exist_ok=True)

@@ -350,6 +350,11 @@ int ps_ctx_set_stream(ps_ctx* ctx, void* cuda_stream) {
 
 int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return PS_ERR_ARG;
+  if (!strcmp(name, "interp_fused")) {
+    if (value != 0 && value != 1) return PS_ERR_ARG;
+    ctx->interp_fused = value;
+    return PS_OK;
+  }
   if (!strcmp(name, "subgroup_check")) {
     if (value != 0 && value != 1) return PS_ERR_ARG;
     ctx->subgroup_check = value;

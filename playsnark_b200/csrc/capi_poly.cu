@@ -157,18 +157,16 @@ int interp_part_run(ps_ctx* ctx, const ps_qap* qap, const Fr* d_w, const uint32_
   ps_stream_t st = ctx->stream;
   if (d_w_nio_out) PS_LAUNCH(FrStdCopyK, st, qap->n_io, d_w + (qap->m - qap->n_io), (Fr*)d_w_nio_out);
   Fr* ev = ctx->arena.take<Fr>((size_t)3 * ns);
-  Fr* E0 = ctx->arena.take<Fr>((size_t)2 * ns);
   uint32_t* flag = ctx->arena.take<uint32_t>(1);
-  if (!ev || !E0 || !flag) return PS_ERR_ALLOC;
+  if (!ev || !flag) return PS_ERR_ALLOC;
   PS_TRY(dev_memset(flag, 0, 4, st));
   PS_LAUNCH(SpmvK, st, (size_t)3 * ns, ns, lo, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
             (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
             (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, d_w, ev);
   PS_LAUNCH(GateCheckK, st, ns, ns, (const Fr*)ev, flag);   // this rank's gates; every gate is checked by some rank
-  PS_LAUNCH(InterpLeafK, st, ns, ns, (const Fr*)(ev + (size_t)which * ns), (const Fr*)(sq->inv_zprime + lo), E0);
   // parts == 1: the whole tree, d_out_evals receives the n coefficients
-  PS_TRY(interpolate_levels(ctx, sq, n, qap->log_np, 1, lo, ns, 0, qap->log_np - lp, E0, lp ? (Fr*)d_out_evals : (Fr*)nullptr,
-                            lp ? (Fr*)nullptr : (Fr*)d_out_evals));
+  PS_TRY(interpolate_from_leaves(ctx, sq, n, qap->log_np, 1, lo, ns, qap->log_np - lp, (const Fr*)(ev + (size_t)which * ns),
+                                 lp ? (Fr*)d_out_evals : (Fr*)nullptr, lp ? (Fr*)nullptr : (Fr*)d_out_evals));
   PS_LAUNCH(StatusMergeK, st, 1, d_err, (const uint32_t*)flag, (uint32_t*)d_status);
   return PS_OK;
 }

@@ -44,6 +44,8 @@ struct ps_ctx {
   // point decoding rejects points outside the prime-order subgroup (kilic's FromCompressed does); 0 skips the
   // r-multiplication for key material the caller vouches for
   int subgroup_check = 1;
+  // lowest levels of the interpolation tree in one shared-memory kernel (interp.cuh); 0 = level by level
+  int interp_fused = 1;
   // latency-bound tail kernels of the MSM: 1 = a team of four lanes per group operation (team.cuh), 0 = one thread
   int msm_team = 1;
   // base sets loaded from now on are meant to be summed in this many index ranges (sharded proofs)

@@ -218,6 +218,84 @@ struct FrScaleK {
   PS_DEV static void run(uint32_t i, Fr scale, Fr* a) { a[i] = a[i] * scale; }
 };
 
+// ---- the lowest levels of the tree in ONE kernel --------------------------------------------------------------
+// Levels 0 .. LOW_LEVELS-1 work on nodes of at most LOW_G = 2^LOW_LEVELS leaves: a thread block keeps the 2 LOW_G
+// evaluations of its group of leaves in shared memory and runs leaf weights, combines, inverse transforms, twists and
+// forward transforms of all those levels without leaving the SM; only the Z-tree slices stream in from HBM.  Per
+// launch-bound subtree (a rank of the sharded prover works on n/parts gates; 2^16-gate circuits) this replaces ~50
+// grid launches of a few microseconds each; the arithmetic is the same (same twiddle tables, same order), so the
+// coefficients are bit-identical to the level-by-level path, which host emulation keeps using.
+constexpr int LOW_LEVELS = 9;
+constexpr uint32_t LOW_G = 1u << LOW_LEVELS;
+struct LowTreePtrs { const Fr* z[LOW_LEVELS]; };
+#if PS_GPU
+static __global__ void __launch_bounds__(256) k_interp_low(uint32_t ns, uint32_t lo, const Fr* ev, const Fr* izp, LowTreePtrs zt,
+                                                           const Fr* twist, const Fr* tw, const Fr* tw_inv, uint32_t n_tw, Fr* Eout) {
+  extern __shared__ uint4 sm_raw[];
+  Fr* E = reinterpret_cast<Fr*>(sm_raw);   // 2 LOW_G evaluations (children, then parents, in place)
+  Fr* Cb = E + 2 * LOW_G;                  // LOW_G values: one transform per parent
+  const uint32_t groups = ns / LOW_G;
+  const uint32_t poly = blockIdx.x / groups, grp = blockIdx.x % groups;
+  const uint32_t leaf0 = grp * LOW_G;
+  const uint32_t T = blockDim.x, tid = threadIdx.x;
+  for (uint32_t i = tid; i < LOW_G; i += T) {
+    Fr w = ev[(size_t)poly * ns + leaf0 + i] * izp[leaf0 + i];
+    E[2 * i] = w; E[2 * i + 1] = w;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int l = 0; l < LOW_LEVELS; l++) {
+    const uint32_t two_s = 2u << l;
+    const Fr* Zhat = zt.z[l] + 2 * (size_t)(lo + leaf0);
+    // combine: parent p occupies the range of its two children; every thread overwrites what only it has read
+    for (uint32_t idx = tid; idx < LOW_G; idx += T) {
+      const uint32_t p = idx / two_s, e = idx % two_s;
+      Fr* El = E + (size_t)(2 * p) * two_s;
+      const Fr* Zl = Zhat + (size_t)(2 * p) * two_s;
+      Fr o = El[e] * fe_ld(Zl + two_s + e) + El[two_s + e] * fe_ld(Zl + e);
+      El[e] = o;
+      Cb[idx] = o;
+    }
+    __syncthreads();
+    // inverse transforms (DIT, bit-reversed -> natural), all parents at once: blocks of two_s are multiples of 2h
+    for (uint32_t h = 1; h < two_s; h <<= 1) {
+      const uint32_t step = n_tw / (2 * h);
+      for (uint32_t b = tid; b < LOW_G / 2; b += T) {
+        const uint32_t j = b % h, i0 = (b / h) * 2 * h + j;
+        Fr u = Cb[i0], v = Cb[i0 + h];
+        if (j) v = v * fe_ld(tw_inv + (size_t)j * step);
+        Cb[i0] = u + v; Cb[i0 + h] = u - v;
+      }
+      __syncthreads();
+    }
+    // twist: coefficient t times (1 / two_s) omega_{2 two_s}^t
+    const Fr* tws = twist + (two_s - 2);
+    for (uint32_t idx = tid; idx < LOW_G; idx += T) Cb[idx] = Cb[idx] * fe_ld(tws + (idx & (two_s - 1)));
+    __syncthreads();
+    // forward transforms (DIF, natural -> bit-reversed)
+    for (uint32_t h = two_s / 2; h >= 1; h >>= 1) {
+      const uint32_t step = n_tw / (2 * h);
+      for (uint32_t b = tid; b < LOW_G / 2; b += T) {
+        const uint32_t j = b % h, i0 = (b / h) * 2 * h + j;
+        Fr u = Cb[i0], v = Cb[i0 + h];
+        Cb[i0] = u + v;
+        Fr d = u - v;
+        Cb[i0 + h] = j ? d * fe_ld(tw + (size_t)j * step) : d;
+      }
+      __syncthreads();
+    }
+    // odd halves of the parents' next-level blocks
+    for (uint32_t idx = tid; idx < LOW_G; idx += T) {
+      const uint32_t p = idx / two_s, e = idx % two_s;
+      E[(size_t)p * 2 * two_s + two_s + e] = Cb[idx];
+    }
+    __syncthreads();
+  }
+  Fr* out = Eout + (size_t)poly * 2 * ns + (size_t)grp * 2 * LOW_G;
+  for (uint32_t i = tid; i < 2 * LOW_G; i += T) out[i] = E[i];
+}
+#endif
+
 // Levels [l0, l1) of the interpolation tree over the leaves [lo, lo + ns) of the domain {1..n} (ns a power
 // of two that divides lo; the whole tree is lo = 0, ns = n, l0 = 0, l1 = k).  E0 holds the evaluations
 // entering level l0: P polynomials x ns/s nodes x 2s values (s = 2^l0); it is used as scratch.
@@ -263,12 +341,40 @@ inline int interpolate_levels(ps_ctx* ctx, const SparseQap* sq, uint32_t n, int 
   return PS_OK;
 }
 
+// The tree from the leaves: ev holds P x ns gate evaluations (polynomial-major) of the gates [lo, lo + ns); levels
+// [0, l1) as interpolate_levels.  On the device the lowest LOW_LEVELS levels run fused (k_interp_low) when the subtree is
+// large enough; `fused` = 0 forces the level-by-level path (option "interp_fused", tests).
+inline int interpolate_from_leaves(ps_ctx* ctx, const SparseQap* sq, uint32_t n, int k, int P, uint32_t lo, uint32_t ns, int l1,
+                                   const Fr* ev, Fr* Eout, Fr* coef) {
+  Fr* E0 = ctx->arena.take<Fr>((size_t)P * 2 * ns);
+  if (!E0) return PS_ERR_ALLOC;
+#if PS_GPU
+  if (ctx->interp_fused && ns >= LOW_G && l1 >= LOW_LEVELS && k > LOW_LEVELS) {
+    const NttTables* tabs = nullptr;
+    PS_TRY(ctx_ntt_tables(ctx, k + 1, &tabs));
+    LowTreePtrs zt;
+    for (int l = 0; l < LOW_LEVELS; l++) zt.z[l] = sq->ztree[l];
+    const size_t smem = (size_t)3 * LOW_G * sizeof(Fr);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+      PS_CUDA_TRY(cudaFuncSetAttribute(k_interp_low, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    k_interp_low<<<(uint32_t)P * (ns / LOW_G), 256, smem, ctx->stream>>>(ns, lo, ev, sq->inv_zprime + lo, zt, sq->twist, tabs->tw, tabs->tw_inv,
+                                                                          2 * n, E0);
+    PS_CUDA_TRY(cudaGetLastError());
+    launch_counter()++;
+    if (l1 == LOW_LEVELS) return dev_d2d(Eout, E0, (size_t)P * 2 * ns * sizeof(Fr), ctx->stream);
+    return interpolate_levels(ctx, sq, n, k, P, lo, ns, LOW_LEVELS, l1, E0, Eout, coef);
+  }
+#endif
+  PS_LAUNCH(InterpLeafK, ctx->stream, (size_t)P * ns, ns, ev, (const Fr*)(sq->inv_zprime + lo), E0);
+  return interpolate_levels(ctx, sq, n, k, P, lo, ns, 0, l1, E0, Eout, coef);
+}
+
 // ev: P polynomials' evaluations on {1..n} (P*n) -> coef: their coefficients (P*n).
 inline int interpolate_ap(ps_ctx* ctx, const SparseQap* sq, uint32_t n, int k, int P, const Fr* ev, Fr* coef) {
-  Fr* E0 = ctx->arena.take<Fr>((size_t)P * 2 * n);
-  if (!E0) return PS_ERR_ALLOC;
-  PS_LAUNCH(InterpLeafK, ctx->stream, (size_t)P * n, n, ev, (const Fr*)sq->inv_zprime, E0);
-  return interpolate_levels(ctx, sq, n, k, P, 0, n, 0, k, E0, (Fr*)nullptr, coef);
+  return interpolate_from_leaves(ctx, sq, n, k, P, 0, n, k, ev, (Fr*)nullptr, coef);
 }
 
 // ---- division by z through the power-series inverse of rev(z) -----------------------------------------

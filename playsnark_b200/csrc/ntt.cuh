@@ -70,7 +70,10 @@ PS_DEV void ntt_io_store(const NttIO& io, Fr* a, size_t idx, const Fr& v) {
   }
 }
 
-template <int R, int MODE = NTT_ST_PLAIN>
+// TRIV: the pass in which the sub-transforms have shrunk to 2^R elements (q == 1, the last pass of a forward transform):
+// there the twiddle of every butterfly with i == 0 is omega^0 = 1 and its product is skipped -- 7 of the 12 products of
+// a radix-8 pass, which is most of the work of the small transforms at the bottom of the interpolation tree.
+template <int R, int MODE = NTT_ST_PLAIN, bool TRIV = false>
 struct NttDifK {
   static constexpr int BLOCK = PS_NTT_BLOCK;
   static constexpr int MIN_BLOCKS = PS_NTT_MINB;   // 8 field elements per thread: cap registers for 4 warps / scheduler
@@ -94,7 +97,8 @@ struct NttDifK {
           uint32_t p = j + (uint32_t)i * q;
           Fr u = x[k], v = x[k2];
           x[k] = u + v;
-          x[k2] = (u - v) * fe_ld(tw + (size_t)p * tw_mul);
+          if (TRIV && i == 0) x[k2] = u - v;
+          else x[k2] = (u - v) * fe_ld(tw + (size_t)p * tw_mul);
         }
       }
     }
@@ -103,7 +107,8 @@ struct NttDifK {
   }
 };
 
-template <int R, int MODE = NTT_ST_PLAIN>
+// TRIV: the first pass of an inverse transform (B0 == 1): twiddles with i == 0 are 1, as above
+template <int R, int MODE = NTT_ST_PLAIN, bool TRIV = false>
 struct NttDitK {
   static constexpr int BLOCK = PS_NTT_BLOCK;
   static constexpr int MIN_BLOCKS = PS_NTT_MINB;
@@ -124,7 +129,8 @@ struct NttDitK {
         for (int i = 0; i < hl; i++) {
           const int k = grp * 2 * hl + i, k2 = k + hl;
           uint32_t p = j + (uint32_t)i * B0;
-          Fr u = x[k], v = x[k2] * fe_ld(tw_inv + (size_t)p * tw_mul);
+          Fr u = x[k], v = x[k2];
+          if (!(TRIV && i == 0)) v = v * fe_ld(tw_inv + (size_t)p * tw_mul);
           x[k] = u + v;
           x[k2] = u - v;
         }
@@ -167,20 +173,20 @@ inline Fr fr_root_of_unity(int log_n) {
 #ifndef PS_NTT_MAXR
 #define PS_NTT_MAXR 3
 #endif
-template <template <int, int> class K, int MODE>
+template <template <int, int, bool> class K, int MODE, bool TRIV>
 inline int ntt_launch_pass(ps_stream_t st, int r, size_t len, Fr* a, uint32_t n_tw, uint32_t B, const Fr* tw, const NttIO& io) {
-  if (r == 3) PS_LAUNCH(K<3 PS_COMMA MODE>, st, len >> 3, a, n_tw, B, tw, io);
-  else if (r == 2) PS_LAUNCH(K<2 PS_COMMA MODE>, st, len >> 2, a, n_tw, B, tw, io);
-  else PS_LAUNCH(K<1 PS_COMMA MODE>, st, len >> 1, a, n_tw, B, tw, io);
+  if (r == 3) PS_LAUNCH(K<3 PS_COMMA MODE PS_COMMA TRIV>, st, len >> 3, a, n_tw, B, tw, io);
+  else if (r == 2) PS_LAUNCH(K<2 PS_COMMA MODE PS_COMMA TRIV>, st, len >> 2, a, n_tw, B, tw, io);
+  else PS_LAUNCH(K<1 PS_COMMA MODE PS_COMMA TRIV>, st, len >> 1, a, n_tw, B, tw, io);
   return PS_OK;
 }
-template <template <int, int> class K>
+template <template <int, int, bool> class K, bool TRIV>
 inline int ntt_launch_pass_mode(ps_stream_t st, int mode, int r, size_t len, Fr* a, uint32_t n_tw, uint32_t B, const Fr* tw, const NttIO& io) {
   switch (mode) {
-    case NTT_ST_TWIST: return ntt_launch_pass<K, NTT_ST_TWIST>(st, r, len, a, n_tw, B, tw, io);
-    case NTT_ST_SCALE: return ntt_launch_pass<K, NTT_ST_SCALE>(st, r, len, a, n_tw, B, tw, io);
-    case NTT_ST_ODD: return ntt_launch_pass<K, NTT_ST_ODD>(st, r, len, a, n_tw, B, tw, io);
-    default: return ntt_launch_pass<K, NTT_ST_PLAIN>(st, r, len, a, n_tw, B, tw, io);
+    case NTT_ST_TWIST: return ntt_launch_pass<K, NTT_ST_TWIST, TRIV>(st, r, len, a, n_tw, B, tw, io);
+    case NTT_ST_SCALE: return ntt_launch_pass<K, NTT_ST_SCALE, TRIV>(st, r, len, a, n_tw, B, tw, io);
+    case NTT_ST_ODD: return ntt_launch_pass<K, NTT_ST_ODD, TRIV>(st, r, len, a, n_tw, B, tw, io);
+    default: return ntt_launch_pass<K, NTT_ST_PLAIN, TRIV>(st, r, len, a, n_tw, B, tw, io);
   }
 }
 // `store_mode` / `io`: output handling of the LAST pass (the earlier passes store in place).
@@ -192,7 +198,9 @@ inline int ntt_forward_blocks(ps_stream_t st, Fr* a, size_t len, int log_block, 
     int r = log_block - done >= PS_NTT_MAXR ? PS_NTT_MAXR : log_block - done;
     uint32_t B = 1u << (log_block - done);
     const bool lastp = done + r == log_block;
-    PS_TRY(ntt_launch_pass_mode<NttDifK>(st, lastp ? store_mode : NTT_ST_PLAIN, r, len, a, n_tw, B, tw, (lastp && io) ? *io : none));
+    // the last pass works on sub-transforms of exactly 2^r elements: its i == 0 twiddles are 1
+    if (lastp) PS_TRY((ntt_launch_pass_mode<NttDifK, true>(st, store_mode, r, len, a, n_tw, B, tw, io ? *io : none)));
+    else PS_TRY((ntt_launch_pass_mode<NttDifK, false>(st, NTT_ST_PLAIN, r, len, a, n_tw, B, tw, none)));
     done += r;
   }
   return PS_OK;
@@ -206,7 +214,9 @@ inline int ntt_inverse_blocks_unscaled(ps_stream_t st, Fr* a, size_t len, int lo
     int r = log_block - done >= PS_NTT_MAXR ? PS_NTT_MAXR : log_block - done;
     uint32_t B0 = 1u << done;
     const bool lastp = done + r == log_block;
-    PS_TRY(ntt_launch_pass_mode<NttDitK>(st, lastp ? store_mode : NTT_ST_PLAIN, r, len, a, n_tw, B0, tw_inv, (lastp && io) ? *io : none));
+    // the first pass (B0 == 1) has unit twiddles for i == 0
+    if (done == 0) PS_TRY((ntt_launch_pass_mode<NttDitK, true>(st, lastp ? store_mode : NTT_ST_PLAIN, r, len, a, n_tw, B0, tw_inv, (lastp && io) ? *io : none)));
+    else PS_TRY((ntt_launch_pass_mode<NttDitK, false>(st, lastp ? store_mode : NTT_ST_PLAIN, r, len, a, n_tw, B0, tw_inv, (lastp && io) ? *io : none)));
     done += r;
   }
   return PS_OK;

@@ -26,18 +26,18 @@ def be(lib):
     b.close()
 
 
-@pytest.mark.parametrize("ndev", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("ndev", [1, 2, 3, 8])
 def test_mg16_prove_matches_single_device(lib, be, ndev):
-    P.multi_groth16_case(lib, be, ndev, log_n=5, seed=ndev)
+    P.multi_groth16_case(lib, be, ndev, log_n=4, seed=ndev)
 
 
 def test_mg16_prove_dense_qap(lib, be):
     P.multi_groth16_dense_case(lib, be, 2)
 
 
-@pytest.mark.parametrize("ndev,group", [(2, L.PS_G1), (3, L.PS_G1), (4, L.PS_G2)])
+@pytest.mark.parametrize("ndev,group", [(3, L.PS_G1), (4, L.PS_G2)])
 def test_mmsm_matches_exponent(lib, ndev, group):
-    P.multi_msm_case(lib, ndev, group, 97)
+    P.multi_msm_case(lib, ndev, group, 41)
 
 
 def test_mctx_argument_errors(lib):
