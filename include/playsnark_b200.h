@@ -119,7 +119,7 @@ int ps_qap_load_dense(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, c
                       const uint8_t* right, const uint8_t* out, const uint8_t* z, ps_qap** qap);
 /* Sparse R1CS twin of the same object for sizes where the dense QAP cannot exist (3*m*n*32 B):
  * CSR matrices over the gates (row_ptr[n+1], col[nnz], val[nnz] as 32 B big-endian Fr); the
- * polynomials are implicit (interpolants on the domain {1..n}).                                */
+ * polynomials are implicit (interpolants on the domain {1..n}).  Any n_gates >= 2, like ToQAP.   */
 int ps_qap_load_r1cs(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io,
                      const uint32_t* l_row_ptr, const uint32_t* l_col, const uint8_t* l_val,
                      const uint32_t* r_row_ptr, const uint32_t* r_col, const uint8_t* r_val,
@@ -185,12 +185,13 @@ int ps_g16_scalars_from_ab(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap
 /* Groth16 over 2 * parts GPUs (parts a power of two; sparse QAP), no host round trip between the
  * steps (errors are OR-ed into a device status word: bit 0 = scalar encoding, bit 1 = remainder, i.e.
  * the reference's "apocalypse" qap.go:159):
- *  - ps_qap_interp_part: rank (which, part) evaluates its n/parts gates (all three matrices, gate check
+ *  Below np = the power of two >= max(n, 2): the leaves of the interpolation tree (gates above n are empty).
+ *  - ps_qap_interp_part: rank (which, part) evaluates its np/parts gates (all three matrices, gate check
  *    a(j) b(j) = c(j) on them), and folds the subtree over those gates of polynomial `which` (0 = a,
- *    1 = b) up to one node: d_out_evals receives its 2n/parts evaluations (Montgomery); with parts = 1
+ *    1 = b) up to one node: d_out_evals receives its 2 np/parts evaluations (Montgomery); with parts = 1
  *    it receives the n coefficients directly and no finish step is needed.  d_w_nio_out (optional)
  *    receives the last n_io witness values in standard form (head of C's scalar vector).
- *  - after an all-gather of the parts, ps_qap_interp_finish runs the top log2(parts) levels on the 2n
+ *  - after an all-gather of the parts, ps_qap_interp_finish runs the top log2(parts) levels on the 2 np
  *    gathered evaluations and emits the n coefficients (Montgomery).
  *  - ps_g16_scalars_ab (every rank, from the broadcast a and b): scA = [a | r | 1], scB = [b | s | 1],
  *    scC_tail = [s a + r b | s | r | r s] (standard form; C's scalar vector is [w_nio | h | tail]), so

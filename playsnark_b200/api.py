@@ -379,13 +379,12 @@ class R1CS:
 def ToQAP(circuit: R1CS) -> "SparseQAP":
     """ToQAP, qap.go:35-65.  The per-variable polynomials are not materialised (that costs O(m n^3)
     field operations and 3*m*n*32 bytes in the reference): the result keeps the gate matrices in CSR
-    form and the device interpolates on {1..n} when proving.  nbGates must be a power of two; for
-    other sizes build the dense QAP (qap.go's layout) and pass it as `QAP`."""
+    form and the device interpolates on {1..n} when proving.  Any nbGates >= 2 (the interpolation tree is built over
+    the next power of two with dummy leaves, csrc/interp.cuh)."""
     left, right, out = circuit.rows()
     n = len(left)
-    if n < 2 or n & (n - 1):
-        raise NotImplementedError("ToQAP on the device needs a power-of-two number of gates (got %d); "
-                                  "use the dense QAP form for other sizes" % n)
+    if n < 2:
+        raise ValueError("a QAP needs at least two gates (got %d)" % n)
 
     def csr(m):
         rp, col, val = [0], [], []
@@ -442,8 +441,7 @@ class SparseQAP:
     """The same object as QAP for circuits whose dense polynomials cannot be materialised
     (3*nbVars*nbGates*32 bytes): the R1CS gate matrices in CSR form (r1cs.go:96-101 holds them
     dense); the per-variable polynomials stay implicit as interpolants on {1..nbGates}
-    (qap.go:67-93).  nbGates must be a power of two.  Each matrix is (row_ptr, col, val) with
-    val as Fr integers."""
+    (qap.go:67-93).  Any nbGates >= 2.  Each matrix is (row_ptr, col, val) with val as Fr integers."""
     nbVars: int
     nbIO: int
     nbGates: int

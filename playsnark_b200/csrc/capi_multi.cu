@@ -236,13 +236,13 @@ std::vector<double> shard_weights(const ps_mctx* m) {
   return w;
 }
 
-int ws_prepare(ps_mctx* m, int d, size_t n, size_t mvars, size_t nio, const KeySlice& sl, size_t parts) {
+int ws_prepare(ps_mctx* m, int d, size_t n, size_t np, size_t mvars, size_t nio, const KeySlice& sl, size_t parts) {
   ProveWs& w = m->ws[d];
   const size_t nx = sl.x_hi - sl.x_lo, nt = sl.t_hi - sl.t_lo, nn = sl.n_hi - sl.n_lo;
   if (w.n == n && w.m == mvars && w.parts == parts && w.nx == nx && w.nt == nt && w.nn == nn) return PS_OK;
   w.release();
   const size_t chunk = (mvars + m->ndev - 1) / m->ndev;
-  const size_t rows = parts > 1 ? 2 * n / parts : n;
+  const size_t rows = parts > 1 ? 2 * np / parts : n;
   PS_TRY(dev_alloc((void**)&w.wfull, chunk * m->ndev * sizeof(Fr)));
   PS_TRY(dev_alloc((void**)&w.e_all, (parts > 1 ? parts : 1) * rows * sizeof(Fr)));
   PS_TRY(dev_alloc((void**)&w.coef[0], n * sizeof(Fr)));
@@ -526,12 +526,14 @@ int ps_mg16_prove(ps_mctx* m, const ps_mg16_key* key, const ps_mqap* qap, const 
   const int N = m->ndev;
   const size_t n = qap->n, mv = qap->m, nio = qap->n_io, diff = mv - nio;
   const size_t parts = (size_t)N / 2;
-  const bool pipelined = !qap->dense && N >= 2 && N % 2 == 0 && (parts & (parts - 1)) == 0 && parts <= n / 2;
-  const size_t rows = parts > 1 ? 2 * n / parts : n;
+  size_t np = 2;                       // leaves of the interpolation tree (sparse QAP): the power of two >= n
+  while (np < n) np <<= 1;
+  const bool pipelined = !qap->dense && N >= 2 && N % 2 == 0 && (parts & (parts - 1)) == 0 && parts <= np / 2;
+  const size_t rows = parts > 1 ? 2 * np / parts : n;
   const size_t chunk = (mv + N - 1) / N;
   m->tl_count = 0;
 
-  int rc = run_all(m, [&](int d) -> int { return ws_prepare(m, d, n, mv, nio, key->slice[d], pipelined ? parts : 1); });
+  int rc = run_all(m, [&](int d) -> int { return ws_prepare(m, d, n, np, mv, nio, key->slice[d], pipelined ? parts : 1); });
   if (rc != PS_OK) return rc;
 
   rc = run_all(m, [&](int d) -> int {

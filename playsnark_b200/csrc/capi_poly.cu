@@ -58,24 +58,24 @@ int stage_scalars(ps_ctx* ctx, const uint8_t* scalars_be, size_t n, int mont, ui
 
 int run_quotient_sparse(ps_ctx* ctx, const ps_qap* q, const uint8_t* witness_be, QuotientBufs* o, bool want_c) {
   const SparseQap* sq = (const SparseQap*)q->sparse;
-  const uint32_t n = (uint32_t)q->n;
+  const uint32_t n = (uint32_t)q->n, np = sq->np;   // real gates; tree leaves (rows above n are empty, their evaluations 0)
   ps_stream_t st = ctx->stream;
   uint32_t* d_w = nullptr;
   PS_TRY(stage_scalars(ctx, witness_be, q->m, 1, &d_w, &o->enc_err));
   o->w = (Fr*)d_w;
-  Fr* ev = ctx->arena.take<Fr>((size_t)3 * n);
-  Fr* coef = ctx->arena.take<Fr>((size_t)3 * n);
-  o->h = ctx->arena.take<Fr>(n);
+  Fr* ev = ctx->arena.take<Fr>((size_t)3 * np);
+  Fr* coef = ctx->arena.take<Fr>((size_t)3 * np);
+  o->h = ctx->arena.take<Fr>(np);
   o->flag = ctx->arena.take<uint32_t>(1);
   if (!ev || !coef || !o->h || !o->flag) return PS_ERR_ALLOC;
   PS_TRY(dev_memset(o->flag, 0, 4, st));
-  PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, 0u, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
+  PS_LAUNCH(SpmvK, st, (size_t)3 * np, np, 0u, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
             (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
             (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, (const Fr*)o->w, ev);
-  PS_LAUNCH(GateCheckK, st, n, n, (const Fr*)ev, o->flag);
+  PS_LAUNCH(GateCheckK, st, np, np, (const Fr*)ev, o->flag);
   // only a and b are interpolated: c = a*b mod z never has to exist for the proof
-  PS_TRY(interpolate_ap(ctx, sq, n, q->log_np, 2, ev, coef));
-  o->a = coef; o->b = coef + n; o->c = coef + 2 * (size_t)n;
+  PS_TRY(interpolate_ap(ctx, sq, np, q->log_np, 2, ev, coef));
+  o->a = coef; o->b = coef + np; o->c = coef + 2 * (size_t)np;   // np entries each, zero from n on
   PS_TRY(quotient_series(ctx, sq, n, q->log_np, o->a, o->b, o->h, want_c ? o->c : (Fr*)nullptr));
   return PS_OK;
 }
@@ -153,7 +153,7 @@ struct StatusMergeK {
 int interp_part_run(ps_ctx* ctx, const ps_qap* qap, const Fr* d_w, const uint32_t* d_err, int which, size_t part, size_t parts,
                     int lp, void* d_out_evals, void* d_w_nio_out, void* d_status) {
   const SparseQap* sq = (const SparseQap*)qap->sparse;
-  const uint32_t n = (uint32_t)qap->n, ns = (uint32_t)(qap->n / parts), lo = (uint32_t)part * ns;
+  const uint32_t n = sq->np, ns = (uint32_t)(sq->np / parts), lo = (uint32_t)part * ns;   // n: leaves of the tree
   ps_stream_t st = ctx->stream;
   if (d_w_nio_out) PS_LAUNCH(FrStdCopyK, st, qap->n_io, d_w + (qap->m - qap->n_io), (Fr*)d_w_nio_out);
   Fr* ev = ctx->arena.take<Fr>((size_t)3 * ns);
@@ -164,9 +164,12 @@ int interp_part_run(ps_ctx* ctx, const ps_qap* qap, const Fr* d_w, const uint32_
             (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
             (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, d_w, ev);
   PS_LAUNCH(GateCheckK, st, ns, ns, (const Fr*)ev, flag);   // this rank's gates; every gate is checked by some rank
-  // parts == 1: the whole tree, d_out_evals receives the n coefficients
+  // parts == 1: the whole tree, d_out_evals receives the qap->n coefficients (the tree produces np, zero from n on)
+  Fr* coef = lp ? (Fr*)nullptr : ctx->arena.take<Fr>(n);
+  if (!lp && !coef) return PS_ERR_ALLOC;
   PS_TRY(interpolate_from_leaves(ctx, sq, n, qap->log_np, 1, lo, ns, qap->log_np - lp, (const Fr*)(ev + (size_t)which * ns),
-                                 lp ? (Fr*)d_out_evals : (Fr*)nullptr, lp ? (Fr*)nullptr : (Fr*)d_out_evals));
+                                 lp ? (Fr*)d_out_evals : (Fr*)nullptr, coef));
+  if (!lp) PS_TRY(dev_d2d(d_out_evals, coef, qap->n * sizeof(Fr), st));
   PS_LAUNCH(StatusMergeK, st, 1, d_err, (const uint32_t*)flag, (uint32_t*)d_status);
   return PS_OK;
 }
@@ -360,7 +363,6 @@ int ps_qap_load_r1cs(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, co
                      const uint8_t* l_val, const uint32_t* r_row_ptr, const uint32_t* r_col, const uint8_t* r_val,
                      const uint32_t* o_row_ptr, const uint32_t* o_col, const uint8_t* o_val, ps_qap** qap) {
   if (!qap || !l_row_ptr || !r_row_ptr || !o_row_ptr || n_gates < 2 || n_vars < 1 || n_io > n_vars) return PS_ERR_ARG;
-  if (n_gates & (n_gates - 1)) return PS_ERR_UNSUPPORTED;  // the interpolation tree needs n = 2^k
   if (n_gates > (1u << 26) || n_vars > (1u << 28)) return PS_ERR_UNSUPPORTED;
   PS_TRY(begin_call(ctx));
   ps_stream_t st = ctx->stream;
@@ -368,8 +370,10 @@ int ps_qap_load_r1cs(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, co
   SparseQap* sq = new (std::nothrow) SparseQap();
   if (!q || !sq) { delete q; delete sq; return PS_ERR_ALLOC; }
   q->n = n_gates; q->m = n_vars; q->n_io = n_io; q->dense = false; q->sparse = sq;
-  int k = 0;
+  int k = 1;
   while (((size_t)1 << k) < n_gates) k++;
+  const size_t np = (size_t)1 << k;   // leaves of the interpolation tree; gates n..np-1 are empty rows
+  sq->np = (uint32_t)np;
   const uint32_t* rps[3] = {l_row_ptr, r_row_ptr, o_row_ptr};
   const uint32_t* cols[3] = {l_col, r_col, o_col};
   const uint8_t* vals[3] = {l_val, r_val, o_val};
@@ -385,10 +389,13 @@ int ps_qap_load_r1cs(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, co
     if (rc != PS_OK) break;
     CsrDev& m = sq->mat[i];
     m.nnz = nnz;
-    rc = dev_alloc((void**)&m.row_ptr, (n_gates + 1) * 4);
+    std::vector<uint32_t> rp_pad(np + 1, (uint32_t)nnz);
+    std::copy(rps[i], rps[i] + n_gates + 1, rp_pad.begin());
+    rc = dev_alloc((void**)&m.row_ptr, (np + 1) * 4);
     if (rc == PS_OK) rc = dev_alloc((void**)&m.col, nnz * 4);
     if (rc == PS_OK) rc = dev_alloc((void**)&m.val, nnz * sizeof(Fr));
-    if (rc == PS_OK) rc = dev_h2d(m.row_ptr, rps[i], (n_gates + 1) * 4, st);
+    if (rc == PS_OK) rc = dev_h2d(m.row_ptr, rp_pad.data(), (np + 1) * 4, st);
+    if (rc == PS_OK) rc = dev_sync(st);   // rp_pad goes out of scope
     if (rc == PS_OK && nnz) rc = dev_h2d(m.col, cols[i], nnz * 4, st);
     uint8_t* d_bytes = ctx->arena.take<uint8_t>(nnz * 32);
     if (rc == PS_OK && !d_bytes) rc = PS_ERR_ALLOC;
@@ -423,10 +430,10 @@ int ps_qap_load_r1cs(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, co
   }
   Fr* d_z = ctx->arena.take<Fr>(n_gates + 1);
   if (rc == PS_OK && !d_z) rc = PS_ERR_ALLOC;
-  if (rc == PS_OK) rc = inv_zprime_build(ctx, sq, (uint32_t)n_gates);
-  if (rc == PS_OK) rc = ztree_build(ctx, sq, (uint32_t)n_gates, k, d_z);
-  if (rc == PS_OK) rc = twist_tables_build(ctx, sq, (uint32_t)n_gates, k);
-  if (rc == PS_OK) rc = series_tables_build(ctx, sq, (uint32_t)n_gates, k, d_z);
+  if (rc == PS_OK) rc = inv_zprime_build(ctx, sq, (uint32_t)n_gates, (uint32_t)np);
+  if (rc == PS_OK) rc = ztree_build(ctx, sq, (uint32_t)n_gates, (uint32_t)np, k, d_z);
+  if (rc == PS_OK) rc = twist_tables_build(ctx, sq, (uint32_t)np, k);
+  if (rc == PS_OK) rc = series_tables_build(ctx, sq, (uint32_t)n_gates, (uint32_t)np, k, d_z);
   q->log_np = k;
   if (rc == PS_OK) rc = check_err_flag(ctx, d_err, PS_ERR_ENCODING);
   if (rc != PS_OK) { ps_qap_free(q); return rc; }
@@ -461,16 +468,18 @@ int ps_qap_aggregate_one(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_
   if (qap->dense) return PS_ERR_UNSUPPORTED;
   PS_TRY(begin_call(ctx));
   const SparseQap* sq = (const SparseQap*)qap->sparse;
-  const uint32_t n = (uint32_t)qap->n;
+  const uint32_t n = sq->np;   // leaves of the tree (the caller's buffer takes the first qap->n coefficients)
   ps_stream_t st = ctx->stream;
   uint32_t *d_w = nullptr, *d_err = nullptr;
   PS_TRY(stage_scalars(ctx, witness_be, qap->m, 1, &d_w, &d_err));
   Fr* ev = ctx->arena.take<Fr>((size_t)3 * n);
-  if (!ev) return PS_ERR_ALLOC;
+  Fr* coef = ctx->arena.take<Fr>(n);
+  if (!ev || !coef) return PS_ERR_ALLOC;
   PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, 0u, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
             (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
             (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, (const Fr*)d_w, ev);
-  PS_TRY(interpolate_ap(ctx, sq, n, qap->log_np, 1, ev + (size_t)which * n, (Fr*)d_out_coef));
+  PS_TRY(interpolate_ap(ctx, sq, n, qap->log_np, 1, ev + (size_t)which * n, coef));
+  PS_TRY(dev_d2d(d_out_coef, coef, qap->n * sizeof(Fr), st));
   return check_err_flag(ctx, d_err, PS_ERR_ENCODING);
 }
 
@@ -484,20 +493,20 @@ int ps_g16_scalars_from_ab(ps_ctx* ctx, const ps_g16_key* key, const ps_qap* qap
   PS_TRY(begin_call(ctx));
   ps_stream_t st = ctx->stream;
   const SparseQap* sq = (const SparseQap*)qap->sparse;
-  const uint32_t n = (uint32_t)qap->n;
+  const uint32_t n = (uint32_t)qap->n, np = sq->np;
   const size_t nio = qap->n_io, diff = qap->m - qap->n_io;
   uint32_t *d_w = nullptr, *d_err = nullptr;
   PS_TRY(stage_scalars(ctx, witness_be, qap->m, 1, &d_w, &d_err));
   Fr* w = (Fr*)d_w;
-  Fr* ev = ctx->arena.take<Fr>((size_t)3 * n);
+  Fr* ev = ctx->arena.take<Fr>((size_t)3 * np);
   Fr* h = ctx->arena.take<Fr>(n);
   uint32_t* flag = ctx->arena.take<uint32_t>(1);
   if (!ev || !h || !flag) return PS_ERR_ALLOC;
   PS_TRY(dev_memset(flag, 0, 4, st));
-  PS_LAUNCH(SpmvK, st, (size_t)3 * n, n, 0u, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
+  PS_LAUNCH(SpmvK, st, (size_t)3 * np, np, 0u, (const uint32_t*)sq->mat[0].row_ptr, (const uint32_t*)sq->mat[0].col, (const Fr*)sq->mat[0].val,
             (const uint32_t*)sq->mat[1].row_ptr, (const uint32_t*)sq->mat[1].col, (const Fr*)sq->mat[1].val,
             (const uint32_t*)sq->mat[2].row_ptr, (const uint32_t*)sq->mat[2].col, (const Fr*)sq->mat[2].val, (const Fr*)w, ev);
-  PS_LAUNCH(GateCheckK, st, n, n, (const Fr*)ev, flag);
+  PS_LAUNCH(GateCheckK, st, np, np, (const Fr*)ev, flag);
   const Fr* a = (const Fr*)d_a;
   const Fr* b = (const Fr*)d_b;
   PS_TRY(quotient_series(ctx, sq, n, qap->log_np, a, b, h, (Fr*)nullptr));
@@ -526,7 +535,7 @@ int ps_qap_interp_part(ps_ctx* ctx, const ps_qap* qap, const uint8_t* witness_be
   if (!ctx || !qap || !witness_be || !d_out_evals || !d_status || which < 0 || which > 1) return PS_ERR_ARG;
   if (qap->dense) return PS_ERR_UNSUPPORTED;
   const int lp = log2_exact(parts);
-  if (lp < 0 || parts > qap->n / 2 || part >= parts) return PS_ERR_ARG;
+  if (lp < 0 || parts > ((size_t)1 << qap->log_np) / 2 || part >= parts) return PS_ERR_ARG;
   PS_TRY(begin_call(ctx));
   uint32_t *d_w = nullptr, *d_err = nullptr;
   PS_TRY(stage_scalars(ctx, witness_be, qap->m, 1, &d_w, &d_err));
@@ -538,7 +547,7 @@ int ps_qap_interp_part_dev(ps_ctx* ctx, const ps_qap* qap, const void* d_witness
   if (!ctx || !qap || !d_witness_mont || !d_out_evals || !d_status || which < 0 || which > 1) return PS_ERR_ARG;
   if (qap->dense) return PS_ERR_UNSUPPORTED;
   const int lp = log2_exact(parts);
-  if (lp < 0 || parts > qap->n / 2 || part >= parts) return PS_ERR_ARG;
+  if (lp < 0 || parts > ((size_t)1 << qap->log_np) / 2 || part >= parts) return PS_ERR_ARG;
   PS_TRY(begin_call(ctx));
   return interp_part_run(ctx, qap, (const Fr*)d_witness_mont, (const uint32_t*)nullptr, which, part, parts, lp, d_out_evals,
                          d_w_nio_out, d_status);
@@ -561,14 +570,16 @@ int ps_qap_interp_finish(ps_ctx* ctx, const ps_qap* qap, size_t parts, const voi
   if (!ctx || !qap || !d_evals_all || !d_out_coef) return PS_ERR_ARG;
   if (qap->dense) return PS_ERR_UNSUPPORTED;
   const int lp = log2_exact(parts);
-  if (lp < 1 || parts > qap->n / 2) return PS_ERR_ARG;
+  if (lp < 1 || parts > ((size_t)1 << qap->log_np) / 2) return PS_ERR_ARG;
   PS_TRY(begin_call(ctx));
   const SparseQap* sq = (const SparseQap*)qap->sparse;
-  const uint32_t n = (uint32_t)qap->n;
+  const uint32_t n = sq->np;   // leaves of the tree: d_evals_all holds 2 np values, the output the first qap->n coefficients
   Fr* E0 = ctx->arena.take<Fr>((size_t)2 * n);
-  if (!E0) return PS_ERR_ALLOC;
+  Fr* coef = ctx->arena.take<Fr>(n);
+  if (!E0 || !coef) return PS_ERR_ALLOC;
   PS_TRY(dev_d2d(E0, d_evals_all, (size_t)2 * n * sizeof(Fr), ctx->stream));
-  return interpolate_levels(ctx, sq, n, qap->log_np, 1, 0, n, qap->log_np - lp, qap->log_np, E0, (Fr*)nullptr, (Fr*)d_out_coef);
+  PS_TRY(interpolate_levels(ctx, sq, n, qap->log_np, 1, 0, n, qap->log_np - lp, qap->log_np, E0, (Fr*)nullptr, coef));
+  return dev_d2d(d_out_coef, coef, qap->n * sizeof(Fr), ctx->stream);
 }
 
 int ps_g16_h_from_ab(ps_ctx* ctx, const ps_qap* qap, const void* d_a, const void* d_b, void* d_h_out) {

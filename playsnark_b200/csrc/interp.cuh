@@ -15,7 +15,12 @@
 //      reversed, times the power-series inverse of rev(z) (precomputed per QAP by Newton iteration)
 //      -- so c never has to be interpolated.
 // The coefficient vectors are identical to Interpolate's (algebra.go:254-280) and Div2's
-// (algebra.go:140-159): interpolant and quotient are unique.  n must be a power of two in this path.
+// (algebra.go:140-159): interpolant and quotient are unique.
+// Any n >= 2: the tree is built over np = 2^k >= n leaves; the leaves above n are DUMMIES with node polynomial 1
+// and weight 0 (so every node is the product over its real leaves only, the root is z of degree n, and the
+// interpolant has degree < n with exact zeros above).  The matrices are padded with empty rows up to np, so
+// every per-gate kernel simply runs over np gates; only the factorials in 1/z'(j), the leaf / lift / root
+// kernels of the Z-tree and the reversals of the series division know the real n.
 #pragma once
 #include "poly.cuh"
 
@@ -36,6 +41,7 @@ struct SparseQap {
   Fr* twist = nullptr;           // level l at offset 2s - 2 (s = 2^l): (1/2s) * omega_{4s}^t, t < 2s; l < k - 1
   Fr* s_hat = nullptr;           // NTT_{2n} of the series inverse of rev(z) mod x^(n-1)   (bit-reversed)
   Fr* z_hat = nullptr;           // NTT_{2n} of z                                          (bit-reversed)
+  uint32_t np = 0;               // leaves of the tree: the power of two >= n (all the sizes "n" above are np)
   void release() {
     for (auto& m : mat) { dev_free(m.row_ptr); dev_free(m.col); dev_free(m.val); }
     for (auto& m : matT) { dev_free(m.row_ptr); dev_free(m.col); dev_free(m.val); }
@@ -67,10 +73,11 @@ struct GateCheckK {
     if ((ev[j] * ev[n + j]) != ev[2 * (size_t)n + j]) ps_atomic_or(flag, 1u);
   }
 };
-// leaves of the Z-tree: node i is (x - (i+1)) -> [-(i+1), 1]
+// leaves of the Z-tree: node i < n is (x - (i+1)) -> [-(i+1), 1]; the dummy leaves above are the polynomial 1
 struct TreeLeafK {
   static constexpr int BLOCK = 256;
-  PS_DEV static void run(uint32_t i, Fr* W) {
+  PS_DEV static void run(uint32_t i, uint32_t n, Fr* W) {
+    if (i >= n) { W[2 * (size_t)i] = Fr::one(); W[2 * (size_t)i + 1] = Fr::zero(); return; }
     Fr v = Fr::zero();
     v.v[0] = i + 1;
     W[2 * (size_t)i] = v.to_mont().neg();
@@ -86,59 +93,64 @@ struct TreeZMulK {
     T[idx] = L[e] * L[two_s + e] * scale;
   }
 };
-// cyclic product coefficients c[p][0..2s) of a monic degree-2s polynomial: c0 has the wrapped leading 1.
-// Writes W[p][0..4s) = [c0 - 1, c1, ..., c_{2s-1}, 1, 0, ...]                      (thread over 2n)
+// cyclic product coefficients c[p][0..2s) of a node polynomial of degree <= 2s.  A FULL node (all its 2s leaves are
+// real: p < n_full) is monic of degree exactly 2s and c0 carries the wrapped leading 1:
+//   W[p][0..4s) = [c0 - 1, c1, ..., c_{2s-1}, 1, 0, ...];
+// a node with dummy leaves has degree < 2s, nothing wraps: W[p] = [c0, ..., c_{2s-1}, 0, ...]       (thread over 2 np)
 struct TreeZLiftK {
   static constexpr int BLOCK = 256;
-  PS_DEV static void run(uint32_t idx, uint32_t two_s, const Fr* T, Fr* W) {
+  PS_DEV static void run(uint32_t idx, uint32_t two_s, uint32_t n_full, const Fr* T, Fr* W) {
     uint32_t four_s = 2 * two_s;
     uint32_t p = idx / four_s, e = idx % four_s;
+    const bool full = p < n_full;
     Fr v = Fr::zero();
-    if (e < two_s) { v = T[(size_t)p * two_s + e]; if (e == 0) v = v - Fr::one(); }
-    else if (e == two_s) v = Fr::one();
+    if (e < two_s) { v = T[(size_t)p * two_s + e]; if (e == 0 && full) v = v - Fr::one(); }
+    else if (e == two_s && full) v = Fr::one();
     W[idx] = v;
   }
 };
-// root: z[0..n) = c - [1,0,...], z[n] = 1                                         (thread over n+1)
+// root: n == np: z[0..n) = c - [1,0,...], z[n] = 1; n < np: the degree-n product did not wrap, z[0..n] = c[0..n]
+//                                                                                  (thread over n+1)
 struct TreeRootK {
   static constexpr int BLOCK = 256;
-  PS_DEV static void run(uint32_t e, uint32_t n, const Fr* T, Fr* z) {
+  PS_DEV static void run(uint32_t e, uint32_t n, uint32_t np, const Fr* T, Fr* z) {
+    if (n < np) { z[e] = T[e]; return; }
     if (e == n) { z[e] = Fr::one(); return; }
     Fr v = T[e];
     if (e == 0) v = v - Fr::one();
     z[e] = v;
   }
 };
-// Builds the Z-tree for n = 2^k (device), writes z (n+1 coefficients, Montgomery) to d_z.
-inline int ztree_build(ps_ctx* ctx, SparseQap* sq, uint32_t n, int k, Fr* d_z) {
+// Builds the Z-tree over np = 2^k leaves, the first n of them real (device); writes z (n+1 coefficients, Montgomery) to d_z.
+inline int ztree_build(ps_ctx* ctx, SparseQap* sq, uint32_t n, uint32_t np, int k, Fr* d_z) {
   ps_stream_t st = ctx->stream;
   const NttTables* tabs = nullptr;
   PS_TRY(ctx_ntt_tables(ctx, k + 1, &tabs));
-  const uint32_t n_tw = 2 * n;
-  Fr* T = ctx->arena.take<Fr>(n);
+  const uint32_t n_tw = 2 * np;
+  Fr* T = ctx->arena.take<Fr>(np);
   if (!T) return PS_ERR_ALLOC;
   sq->ztree.assign(k, nullptr);
-  for (int l = 0; l < k; l++) PS_TRY(dev_alloc((void**)&sq->ztree[l], (size_t)2 * n * sizeof(Fr)));
-  PS_LAUNCH(TreeLeafK, st, n, sq->ztree[0]);
-  PS_TRY(ntt_forward_blocks(st, sq->ztree[0], (size_t)2 * n, 1, tabs->tw, n_tw));
+  for (int l = 0; l < k; l++) PS_TRY(dev_alloc((void**)&sq->ztree[l], (size_t)2 * np * sizeof(Fr)));
+  PS_LAUNCH(TreeLeafK, st, np, n, sq->ztree[0]);
+  PS_TRY(ntt_forward_blocks(st, sq->ztree[0], (size_t)2 * np, 1, tabs->tw, n_tw));
   for (int l = 0; l < k; l++) {
     const uint32_t two_s = 2u << l;
     Fr scale = fr_inv(fr_host_from_u64(two_s));
-    PS_LAUNCH(TreeZMulK, st, n, two_s, (const Fr*)sq->ztree[l], scale, T);
-    PS_TRY(ntt_inverse_blocks_unscaled(st, T, n, l + 1, tabs->tw_inv, n_tw));
+    PS_LAUNCH(TreeZMulK, st, np, two_s, (const Fr*)sq->ztree[l], scale, T);
+    PS_TRY(ntt_inverse_blocks_unscaled(st, T, np, l + 1, tabs->tw_inv, n_tw));
     if (l + 1 == k) {
-      PS_LAUNCH(TreeRootK, st, (size_t)n + 1, n, (const Fr*)T, d_z);
+      PS_LAUNCH(TreeRootK, st, (size_t)n + 1, n, np, (const Fr*)T, d_z);
     } else {
-      PS_LAUNCH(TreeZLiftK, st, (size_t)2 * n, two_s, (const Fr*)T, sq->ztree[l + 1]);
-      PS_TRY(ntt_forward_blocks(st, sq->ztree[l + 1], (size_t)2 * n, l + 2, tabs->tw, n_tw));
+      PS_LAUNCH(TreeZLiftK, st, (size_t)2 * np, two_s, n / two_s, (const Fr*)T, sq->ztree[l + 1]);
+      PS_TRY(ntt_forward_blocks(st, sq->ztree[l + 1], (size_t)2 * np, l + 2, tabs->tw, n_tw));
     }
   }
   return PS_OK;
 }
 
-// 1 / z'(j) for j = 1..n, computed on the host (once per QAP) and uploaded
-inline int inv_zprime_build(ps_ctx* ctx, SparseQap* sq, uint32_t n) {
-  std::vector<Fr> fact(n + 1), invfact(n + 1), out(n);
+// 1 / z'(j) for j = 1..n (zero for the dummy leaves n < j <= np), computed on the host (once per QAP) and uploaded
+inline int inv_zprime_build(ps_ctx* ctx, SparseQap* sq, uint32_t n, uint32_t np) {
+  std::vector<Fr> fact(n + 1), invfact(n + 1), out(np, Fr::zero());
   fact[0] = Fr::one();
   for (uint32_t i = 1; i <= n; i++) fact[i] = fact[i - 1] * fr_host_from_u64(i);
   invfact[n] = fr_inv(fact[n]);
@@ -147,8 +159,8 @@ inline int inv_zprime_build(ps_ctx* ctx, SparseQap* sq, uint32_t n) {
     Fr v = invfact[j - 1] * invfact[n - j];
     out[j - 1] = ((n - j) & 1) ? v.neg() : v;
   }
-  PS_TRY(dev_alloc((void**)&sq->inv_zprime, (size_t)n * sizeof(Fr)));
-  PS_TRY(dev_h2d(sq->inv_zprime, out.data(), (size_t)n * sizeof(Fr), ctx->stream));
+  PS_TRY(dev_alloc((void**)&sq->inv_zprime, (size_t)np * sizeof(Fr)));
+  PS_TRY(dev_h2d(sq->inv_zprime, out.data(), (size_t)np * sizeof(Fr), ctx->stream));
   return dev_sync(ctx->stream);
 }
 
@@ -419,11 +431,11 @@ struct FrSubK {
   PS_DEV static void run(uint32_t i, const Fr* Pc, const Fr* Q, Fr* c) { c[i] = Pc[i] - Q[i]; }
 };
 
-// Precomputes s_hat and z_hat from z (n+1 coefficients on the device).
-inline int series_tables_build(ps_ctx* ctx, SparseQap* sq, uint32_t n, int k, const Fr* d_z) {
+// Precomputes s_hat and z_hat from z (n+1 coefficients on the device); transforms of size 2 np = 2^(k+1) >= 2n.
+inline int series_tables_build(ps_ctx* ctx, SparseQap* sq, uint32_t n, uint32_t np, int k, const Fr* d_z) {
   ps_stream_t st = ctx->stream;
   Arena& ar = ctx->arena;
-  const size_t N2 = (size_t)2 * n;
+  const size_t N2 = (size_t)2 * np;
   Fr* S[2] = {ar.take<Fr>(N2), ar.take<Fr>(N2)};
   Fr* F = ar.take<Fr>(2 * N2); Fr* G = ar.take<Fr>(2 * N2); Fr* E = ar.take<Fr>(2 * N2);
   if (!S[0] || !S[1] || !F || !G || !E) return PS_ERR_ALLOC;
@@ -461,10 +473,11 @@ inline int series_tables_build(ps_ctx* ctx, SparseQap* sq, uint32_t n, int k, co
 
 // h = floor(a*b / z): a, b have n coefficients (device); h receives n entries (h[n-1] = 0).
 // c_out (optional, n entries) = a*b - h*z, the polynomial computeAggregatePoly would have returned.
+// Transforms of size 2 np = 2^(k+1) >= 2n (np = sq->np).
 inline int quotient_series(ps_ctx* ctx, const SparseQap* sq, uint32_t n, int k, const Fr* a, const Fr* b, Fr* h, Fr* c_out) {
   ps_stream_t st = ctx->stream;
   Arena& ar = ctx->arena;
-  const size_t N2 = (size_t)2 * n;
+  const size_t N2 = (size_t)2 * sq->np;
   const NttTables* t = nullptr;
   PS_TRY(ctx_ntt_tables(ctx, k + 1, &t));
   Fr* A = ar.take<Fr>(N2); Fr* B = ar.take<Fr>(N2); Fr* Pc = ar.take<Fr>(N2); Fr* T = ar.take<Fr>(N2);

@@ -112,7 +112,8 @@ def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_s
     bufA, bufC, bufB = new(nA), new(nC), new(nB)
     status = torch.zeros(1, dtype=torch.int32, device=device)
     rb, sb = _fr_bytes([r]), _fr_bytes([s])
-    e_rows = 2 * n // parts if parts > 1 else n
+    np_ = _tree_leaves(n)                                # leaves of the interpolation tree (power of two >= n)
+    e_rows = 2 * np_ // parts if parts > 1 else n
     e_part = new(e_rows)
     m = q.nbVars
     if gather_witness:
@@ -187,6 +188,14 @@ def _groth16_pipelined(be, tr, q, witness, r: int, s: int, dist, device, rank0_s
     return oA.raw, oB.raw, oC.raw
 
 
+def _tree_leaves(n: int) -> int:
+    """leaves of the device's interpolation tree for n gates (csrc/interp.cuh): the power of two >= max(n, 2)"""
+    np_ = 2
+    while np_ < n:
+        np_ <<= 1
+    return np_
+
+
 def load_key_sharded(be, tr, world: int):
     """proving key resident on this rank with MSM windows sized for a 1/world share of every base set"""
     be.set_option("msm_shards", max(1, world))
@@ -219,7 +228,7 @@ def groth16_prove_sharded(be, tr, q, witness, r: int, s: int, dist=None, device=
         # size so that it reaches the h broadcast together with the others; 0.4 measured best on 8 GPUs
         rank0_share = max(0.2, 1.0 - 0.075 * world)
     if (split_quotient and world >= 2 and world % 2 == 0 and parts & (parts - 1) == 0 and type(q).__name__ == "SparseQAP"
-            and parts <= q.nbGates // 2):
+            and parts <= _tree_leaves(q.nbGates) // 2):
         return _groth16_pipelined(be, tr, q, witness, r, s, dist, device, rank0_share, trace, gather_witness)
     kh = load_key_sharded(be, tr, world)
     counts = [int(lib.ps_g16_scalar_count(kh, w)) for w in (0, 1, 2)]

@@ -376,7 +376,7 @@ def groth16_sparse_exponent_check(be, log_n, seed):
         api.Groth16Prove(tr, sq, bad, r, s, backend=be)
 
 
-def sharded_steps_recombine(be, log_n, parts, fake_world, seed, device="cpu"):
+def sharded_steps_recombine(be, log_n, parts, fake_world, seed, device="cpu", n=None):
     """The entry points of the multi-GPU Groth16 flow (dist.py), driven from ONE process: the subtrees
     of ps_qap_interp_part + ps_qap_interp_finish must reproduce ps_qap_aggregate_one's coefficients,
     ps_g16_scalars_ab / ps_g16_h_from_ab the scalar vectors of ps_g16_scalars, and the partial MSMs of
@@ -385,7 +385,8 @@ def sharded_steps_recombine(be, log_n, parts, fake_world, seed, device="cpu"):
     import torch
     from playsnark_b200 import dist as D
     lib = be.lib
-    n = 1 << log_n
+    n = n or (1 << log_n)
+    n_leaves = D._tree_leaves(n)       # the subtree roots are sized by the tree's leaves (power of two >= n)
     sq, wit = H.sparse_circuit(n, seed, n // 2)
     tr, tw = H.sparse_groth16_setup(be, sq, seed)
     smp = O.Sampler(seed + 77)
@@ -411,7 +412,7 @@ def sharded_steps_recombine(be, log_n, parts, fake_world, seed, device="cpu"):
             got = new(n)
             be._check(lib.ps_qap_interp_part(be.ctx, qh, wb, which, 0, 1, ptr(got), ptr(bufC), ptr(status)))
         else:
-            rows = 2 * n // parts
+            rows = 2 * n_leaves // parts
             e_all = new(parts * rows)
             for part in range(parts):
                 be._check(lib.ps_qap_interp_part(be.ctx, qh, wb, which, part, parts, ptr(e_all[part * rows:(part + 1) * rows]),
@@ -427,7 +428,7 @@ def sharded_steps_recombine(be, log_n, parts, fake_world, seed, device="cpu"):
     half = m // 2
     be._check(lib.ps_fr_upload(be.ctx, wb[:32 * half], half, ptr(wdev), ptr(status)))
     be._check(lib.ps_fr_upload(be.ctx, wb[32 * half:], m - half, ptr(wdev[half:]), ptr(status)))
-    rows = 2 * n // parts if parts > 1 else n
+    rows = 2 * n_leaves // parts if parts > 1 else n
     via_host, via_dev, nio_dev = new(rows), new(rows), new(max(1, nio))
     be._check(lib.ps_qap_interp_part(be.ctx, qh, wb, 1, parts - 1, parts, ptr(via_host), None, ptr(status)))
     be._check(lib.ps_qap_interp_part_dev(be.ctx, qh, ptr(wdev), 1, parts - 1, parts, ptr(via_dev), ptr(nio_dev), ptr(status)))
@@ -468,7 +469,7 @@ def sharded_steps_recombine(be, log_n, parts, fake_world, seed, device="cpu"):
     hit = 0
     for part in range(parts):
         st2.zero_()
-        rows = 2 * n // parts if parts > 1 else n
+        rows = 2 * n_leaves // parts if parts > 1 else n
         sink = new(rows)                                       # kept alive across the call
         be._check(lib.ps_qap_interp_part(be.ctx, qh, api._fr_bytes(bad), 0, part, parts, ptr(sink), None, ptr(st2)))
         be.sync()
@@ -590,12 +591,12 @@ def phgr13_sparse_exponent_check(be, log_n, seed):
     assert len(pp.h) == n - 1
 
 
-def multi_groth16_case(lib, be, ndev, log_n, seed, devices=None, rank0_share=None):
+def multi_groth16_case(lib, be, ndev, log_n, seed, devices=None, rank0_share=None, n=None):
     """ps_mg16_prove on `ndev` devices (one host call, key sharded, sparse QAP replicated) must return the proof
     of ps_g16_prove on one device bit for bit; a broken witness must raise "apocalypse" from whichever device
     owns the gate; a witness of the wrong length the sanityCheck error (qap.go:177-189)."""
     import pytest
-    n = 1 << log_n
+    n = n or (1 << log_n)      # any n >= 2: the interpolation tree pads to the next power of two with dummy leaves
     sq, wit = H.sparse_circuit(n, seed, n // 2)
     tr, tw = H.sparse_groth16_setup(be, sq, seed)
     smp = O.Sampler(seed + 5)
@@ -676,9 +677,7 @@ def device_setups_vs_oracle(be, n=12, seed=3):
     r, w = H.mixed_circuit(n, seed, max(1, n // 2)) if n & (n - 1) == 0 else H.mixed_circuit(n, seed, max(1, n // 2))
     oq = O.to_qap(r)
     dense = H.mirror_qap(oq)
-    forms = [dense]
-    if n & (n - 1) == 0:
-        forms.append(api.SparseQAP.from_dense_rows(len(r.vars), r.nb_io(), r.left, r.right, r.out))
+    forms = [dense, api.SparseQAP.from_dense_rows(len(r.vars), r.nb_io(), r.left, r.right, r.out)]
     g1, g2 = O.g1_compress, O.g2_compress
     otr = O.groth16_setup(oq, O.Sampler(seed))
     toxic = tuple(otr.tw[k] for k in ("Alpha", "Beta", "Delta", "X", "Gamma"))

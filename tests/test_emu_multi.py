@@ -31,6 +31,11 @@ def test_mg16_prove_matches_single_device(lib, be, ndev):
     P.multi_groth16_case(lib, be, ndev, log_n=4, seed=ndev)
 
 
+@pytest.mark.parametrize("ndev,n", [(2, 11), (4, 19)])
+def test_mg16_prove_any_gate_count(lib, be, ndev, n):
+    P.multi_groth16_case(lib, be, ndev, log_n=0, seed=n, n=n)
+
+
 def test_mg16_prove_dense_qap(lib, be):
     P.multi_groth16_dense_case(lib, be, 2)
 

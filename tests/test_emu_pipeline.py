@@ -65,8 +65,10 @@ def test_groth16_chain_negative_witness(be): P.groth16_circuit(be, 8, seed=4, ci
 def test_phgr13_mixed(be): P.phgr13_circuit(be, 9, seed=6)
 
 
-@pytest.mark.parametrize("n", [4, 16])
-def test_sparse_quotient(be, n): P.sparse_quotient_vs_dense(be, n, seed=n)
+@pytest.mark.parametrize("n", [4, 16, 2, 3, 7, 13])
+def test_sparse_quotient(be, n):
+    # the reference accepts any gate count; 3, 7, 13: interpolation tree over the next power of two with dummy leaves
+    P.sparse_quotient_vs_dense(be, n, seed=n)
 
 
 def test_sparse_groth16_exponent_check(be): P.groth16_sparse_exponent_check(be, 5, seed=8)
@@ -87,6 +89,10 @@ def test_device_setups_vs_oracle(be, n): P.device_setups_vs_oracle(be, n, seed=n
 
 @pytest.mark.parametrize("parts,world", [(1, 2), (2, 3), (4, 5)])
 def test_sharded_steps_recombine(be, parts, world): P.sharded_steps_recombine(be, 4, parts, world, seed=21 + parts)
+
+
+@pytest.mark.parametrize("n,parts,world", [(11, 2, 3), (21, 4, 4)])
+def test_sharded_steps_recombine_any_n(be, n, parts, world): P.sharded_steps_recombine(be, 0, parts, world, seed=n, n=n)
 
 
 @pytest.mark.parametrize("wb,tables,kind", [(16, 16, "rand"), (16, 1, "edge"), (20, -1, "rand"), (17, 3, "ones")])

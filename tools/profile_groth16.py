@@ -7,13 +7,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import playsnark_b200 as ps  # noqa: E402
 from oracle import ps_oracle as O  # noqa: E402
-from tests import helpers as H  # noqa: E402
+from playsnark_b200 import synth  # noqa: E402
 
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 18
 n = 1 << k
 be = ps.Backend(0)
-sq, wit = H.sparse_circuit(n, 7, n // 2)
-tr, tw = H.sparse_groth16_setup(be, sq, 7)
+sq, wit = synth.sparse_circuit(n, 7, n // 2)
+smp0 = O.Sampler(7)
+tr = ps.NewGroth16TrustedSetup(sq, backend=be, toxic=tuple(smp0.fr() for _ in range(5)), export=False)   # key made on the device
 wb = ps.HostBuffer(be, b"".join(v.to_bytes(32, "big") for v in wit))
 smp = O.Sampler(99)
 r, s = smp.fr(), smp.fr()
