@@ -356,11 +356,11 @@ def sparse_quotient_vs_dense(be, n, seed):
     assert p2.A == O.g1_compress(want["A"]) and p2.B == O.g2_compress(want["B"]) and p2.C == O.g1_compress(want["C"])
 
 
-def groth16_sparse_exponent_check(be, log_n, seed):
+def groth16_sparse_exponent_check(be, log_n, seed, n=None):
     """full Groth16 prove on a sparse synthetic circuit of 2^log_n gates (configs C3/C5): the proof
     must equal the exponent-level recomputation from the toxic waste, and h must satisfy
     h(x) z(x) = a(x) b(x) - c(x) at the toxic point."""
-    n = 1 << log_n
+    n = n or (1 << log_n)
     sq, wit = H.sparse_circuit(n, seed, n // 2)
     tr, tw = H.sparse_groth16_setup(be, sq, seed)
     smp = O.Sampler(seed + 1000)
@@ -578,10 +578,10 @@ def readme_flow_through_api(be):
         api.ToQAP(c5)
 
 
-def phgr13_sparse_exponent_check(be, log_n, seed):
+def phgr13_sparse_exponent_check(be, log_n, seed, n=None):
     """PHGR13 prove on a sparse synthetic circuit of 2^log_n gates: all eight proof elements must equal
     their exponent-level recomputation from the toxic waste (pinocchio_test.go:23-196 at scale)."""
-    n = 1 << log_n
+    n = n or (1 << log_n)
     sq, wit = H.sparse_circuit(n, seed, n // 2)
     ek, tw = H.sparse_phgr13_setup(be, sq, seed)
     pp = api.PHGR13Prove(ek, sq, wit, backend=be, want_h=True)

@@ -117,7 +117,7 @@ def test_groth16_chain_negative_witness(be): P.groth16_circuit(be, 32, seed=4, c
 def test_phgr13_mixed(be): P.phgr13_circuit(be, 20, seed=6)
 
 
-@pytest.mark.parametrize("n", [4, 16, 64])
+@pytest.mark.parametrize("n", [4, 16, 64, 2, 3, 13, 100])
 def test_sparse_quotient(be, n): P.sparse_quotient_vs_dense(be, n, seed=n)
 
 
@@ -129,6 +129,14 @@ def test_sparse_groth16_exponent_check(be, log_n):
 
 @pytest.mark.parametrize("log_n", [6, 12, 16])
 def test_sparse_phgr13_exponent_check(be, log_n): P.phgr13_sparse_exponent_check(be, log_n, seed=log_n)
+
+
+@pytest.mark.parametrize("n", [1000, 100000])
+def test_sparse_any_gate_count(be, n):
+    # the reference takes any number of gates: tree over the next power of two with dummy leaves (fused low levels included)
+    P.groth16_sparse_exponent_check(be, 0, seed=n % 97, n=n)
+    if n <= 1000:
+        P.phgr13_sparse_exponent_check(be, 0, seed=n % 89, n=n)
 
 
 def test_config_c2_dense_2p10(be):
