@@ -3,6 +3,7 @@
 // loaders and the assembly of Groth16 / PHGR13 proofs.  Host orchestration only: the group kernels are
 // reached through GroupOps<F> (group_ops.cuh; instantiated in group_g1.cu / group_g2.cu), the Fr
 // polynomial side through poly_api.cuh (capi_poly.cu).
+#include <cstdlib>
 #include "group_ops.cuh"
 #include "microbench.cuh"
 #include "multi_api.cuh"
@@ -310,8 +311,15 @@ int ps_ctx_create(int device, ps_ctx** out) {
     PS_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     ctx->stream = st;
     ctx->own_stream = true;
+    // The secondary stream carries the G2 sum of a proof next to the G1 batch.  At HIGH priority its blocks are placed
+    // first: the G2 accumulation runs ahead and its latency-bound tail (tiny grids) then slips in between the blocks of
+    // the G1 accumulation instead of queueing behind them.  PLAYSNARK_B200_STREAM2_PRIO=0 keeps the default priority (A/B).
     cudaStream_t st2;
-    PS_CUDA_TRY(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    PS_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    const char* pe = getenv("PLAYSNARK_B200_STREAM2_PRIO");
+    const int prio = (pe && pe[0] == '0') ? prio_lo : prio_hi;
+    PS_CUDA_TRY(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, prio));
     ctx->stream2 = st2;
     cudaEvent_t e;
     PS_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_fork = e;
@@ -373,6 +381,11 @@ int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value) {
   if (!strcmp(name, "msm_scatter")) {
     if (value < 0 || value > 2) return PS_ERR_ARG;
     ctx->msm_scatter = value;
+    return PS_OK;
+  }
+  if (!strcmp(name, "msm_wave_floor")) {
+    if (value != 0 && value != 1) return PS_ERR_ARG;
+    ctx->msm_wave_floor = value;
     return PS_OK;
   }
   if (!strcmp(name, "msm_team")) {

@@ -46,6 +46,8 @@ struct ps_ctx {
   int subgroup_check = 1;
   // lowest levels of the interpolation tree in one shared-memory kernel (interp.cuh); 0 = level by level
   int interp_fused = 1;
+  // accumulate grid of small MSMs: 1 = whole waves with the wave count rounded down (longer chunks), 0 = rounded up
+  int msm_wave_floor = 1;
   // latency-bound tail kernels of the MSM: 1 = a team of four lanes per group operation (team.cuh), 0 = one thread
   int msm_team = 1;
   // base sets loaded from now on are meant to be summed in this many index ranges (sharded proofs)

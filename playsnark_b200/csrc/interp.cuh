@@ -271,11 +271,10 @@ static __global__ void __launch_bounds__(256) k_interp_low(uint32_t ns, uint32_t
     __syncthreads();
     // inverse transforms (DIT, bit-reversed -> natural), all parents at once: blocks of two_s are multiples of 2h
     for (uint32_t h = 1; h < two_s; h <<= 1) {
-      const uint32_t step = n_tw / (2 * h);
       for (uint32_t b = tid; b < LOW_G / 2; b += T) {
         const uint32_t j = b % h, i0 = (b / h) * 2 * h + j;
         Fr u = Cb[i0], v = Cb[i0 + h];
-        if (j) v = v * fe_ld(tw_inv + (size_t)j * step);
+        if (j) v = v * ntt_twiddle(tw_inv, n_tw, 2 * h, j);
         Cb[i0] = u + v; Cb[i0 + h] = u - v;
       }
       __syncthreads();
@@ -286,13 +285,12 @@ static __global__ void __launch_bounds__(256) k_interp_low(uint32_t ns, uint32_t
     __syncthreads();
     // forward transforms (DIF, natural -> bit-reversed)
     for (uint32_t h = two_s / 2; h >= 1; h >>= 1) {
-      const uint32_t step = n_tw / (2 * h);
       for (uint32_t b = tid; b < LOW_G / 2; b += T) {
         const uint32_t j = b % h, i0 = (b / h) * 2 * h + j;
         Fr u = Cb[i0], v = Cb[i0 + h];
         Cb[i0] = u + v;
         Fr d = u - v;
-        Cb[i0 + h] = j ? d * fe_ld(tw + (size_t)j * step) : d;
+        Cb[i0 + h] = j ? d * ntt_twiddle(tw, n_tw, 2 * h, j) : d;
       }
       __syncthreads();
     }

@@ -34,6 +34,24 @@ struct FrMulTableK {
   PS_DEV static void run(uint32_t i, Fr* a, const Fr* t) { a[i] = a[i] * t[i]; }
 };
 
+// Twiddle addressing.  The flat table tw[i] = omega_n^i makes a butterfly stage on sub-transforms of size M read
+// tw[p * (n / M)]: consecutive lanes (consecutive p) then touch addresses n/M * 32 B apart -- a separate 128-byte line
+// per lane for every twiddle load of the middle passes (the radix-8 pass profiled at 71 % L1/TEX throughput next to
+// 60 % multiplier activity).  The LAYERED table stored right behind the flat one holds, for every M = 2^s <= n,
+// omega_M^p for p < M/2 contiguously (offset M/2 - 1): lanes read consecutive 32-byte entries.  Same values, same
+// products: results are bit-identical.  PS_NTT_LAYERED = 0 keeps the flat addressing (A/B builds).
+#ifndef PS_NTT_LAYERED
+#define PS_NTT_LAYERED 1
+#endif
+// twiddle omega_M^p of a table built for n: M = n / tw_mul
+PS_DEV Fr ntt_twiddle(const Fr* tw, uint32_t n, uint32_t M, uint32_t p) {
+#if PS_NTT_LAYERED
+  return fe_ld(tw + (size_t)(n >> 1) + ((M >> 1) - 1) + p);
+#else
+  return fe_ld(tw + (size_t)p * (n / M));
+#endif
+}
+
 #ifndef PS_NTT_BLOCK
 #define PS_NTT_BLOCK 128
 #endif
@@ -88,7 +106,7 @@ struct NttDifK {
 #pragma unroll
     for (int t = 0; t < R; t++) {
       const int hl = 1 << (R - 1 - t);           // half size in units of k
-      const uint32_t tw_mul = (n / B) << t;      // n / (2*half_t)
+      const uint32_t M = B >> t;                 // size of the sub-transforms of this stage
 #pragma unroll
       for (int grp = 0; grp < (1 << t); grp++) {
 #pragma unroll
@@ -98,7 +116,7 @@ struct NttDifK {
           Fr u = x[k], v = x[k2];
           x[k] = u + v;
           if (TRIV && i == 0) x[k2] = u - v;
-          else x[k2] = (u - v) * fe_ld(tw + (size_t)p * tw_mul);
+          else x[k2] = (u - v) * ntt_twiddle(tw, n, M, p);
         }
       }
     }
@@ -122,7 +140,7 @@ struct NttDitK {
 #pragma unroll
     for (int t = 0; t < R; t++) {
       const int hl = 1 << t;
-      const uint32_t tw_mul = n / ((2 * B0) << t);  // n / (2*half_t)
+      const uint32_t M = (2 * B0) << t;          // size of the sub-transforms this stage completes
 #pragma unroll
       for (int grp = 0; grp < (1 << (R - 1 - t)); grp++) {
 #pragma unroll
@@ -130,7 +148,7 @@ struct NttDitK {
           const int k = grp * 2 * hl + i, k2 = k + hl;
           uint32_t p = j + (uint32_t)i * B0;
           Fr u = x[k], v = x[k2];
-          if (!(TRIV && i == 0)) v = v * fe_ld(tw_inv + (size_t)p * tw_mul);
+          if (!(TRIV && i == 0)) v = v * ntt_twiddle(tw_inv, n, M, p);
           x[k] = u + v;
           x[k2] = u - v;
         }
@@ -229,16 +247,33 @@ inline int ntt_inverse_unscaled(ps_stream_t st, Fr* a, int log_n, const Fr* tw_i
   return ntt_inverse_blocks_unscaled(st, a, (size_t)1 << log_n, log_n, tw_inv, 1u << log_n);
 }
 
+// layered[(M/2 - 1) + p] = flat[p * (n / M)] for M = 2^s <= n, p < M/2                  (thread over n - 1 entries)
+struct TwLayerK {
+  static constexpr int BLOCK = 256;
+  PS_DEV static void run(uint32_t idx, int log_n, const Fr* flat, Fr* layered) {
+    int s = 1;
+    while ((2u << (s - 1)) - 1 <= idx) s++;        // layer s starts at 2^(s-1) - 1
+    const uint32_t p = idx - ((1u << (s - 1)) - 1);
+    layered[idx] = flat[(size_t)p << (log_n - s)];
+  }
+};
+
+// flat table omega^i (i < n/2) followed by the layered table (n - 1 entries, see PS_NTT_LAYERED), in one allocation
 inline int ntt_tables_build(ps_stream_t st, int log_n, NttTables* t) {
   if (log_n < 0 || log_n > 30) return PS_ERR_ARG;
   t->release();
-  size_t half = log_n ? (size_t)1 << (log_n - 1) : 1;
-  PS_TRY(dev_alloc((void**)&t->tw, half * sizeof(Fr)));
-  PS_TRY(dev_alloc((void**)&t->tw_inv, half * sizeof(Fr)));
+  const size_t n = (size_t)1 << log_n;
+  size_t half = log_n ? n >> 1 : 1;
+  PS_TRY(dev_alloc((void**)&t->tw, (half + n) * sizeof(Fr)));
+  PS_TRY(dev_alloc((void**)&t->tw_inv, (half + n) * sizeof(Fr)));
   Fr w = fr_root_of_unity(log_n);
   Fr wi = fr_host_pow(w, ((uint64_t)1 << log_n) - 1);  // w^-1 = w^(n-1)
   PS_LAUNCH(FrPowTableK, st, half, w, Fr::one(), t->tw);
   PS_LAUNCH(FrPowTableK, st, half, wi, Fr::one(), t->tw_inv);
+  if (log_n >= 1) {
+    PS_LAUNCH(TwLayerK, st, n - 1, log_n, (const Fr*)t->tw, t->tw + half);
+    PS_LAUNCH(TwLayerK, st, n - 1, log_n, (const Fr*)t->tw_inv, t->tw_inv + half);
+  }
   t->log_n = log_n;   // only a completely built entry is marked valid
   return PS_OK;
 }

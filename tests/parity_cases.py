@@ -574,8 +574,18 @@ def readme_flow_through_api(be):
     with pytest.raises(KeyError, match="plouf"):         # r1cs.go:27
         c.IndexOf("nope")
     c5 = api.R1CS(); c5.NewInput("x"); c5.NewOutput("o"); c5.Mul("x", "x", "o"); c5.Mul("x", "x", "o"); c5.Mul("x", "x", "o")
-    with pytest.raises(NotImplementedError):
-        api.ToQAP(c5)
+    # three gates (not a power of two): accepted like the reference's ToQAP; h z = a b - c at a random point
+    q5 = api.ToQAP(c5)
+    assert q5.nbGates == 3
+    sol5 = [0] * 3
+    for name, val in (("const", 1), ("x", 3), ("o", 9)):
+        sol5[c5.IndexOf(name)] = val
+    h5, (a5, b5, cc5) = api.Quotient(q5, sol5, backend=be, return_abc=True)
+    x0 = 0x1234567
+    z5 = (x0 - 1) * (x0 - 2) * (x0 - 3) % O.R
+    assert len(h5) == 2 and len(a5) == 3
+    assert O.poly_eval(h5, x0) * z5 % O.R == (O.poly_eval(a5, x0) * O.poly_eval(b5, x0) - O.poly_eval(cc5, x0)) % O.R
+    assert all(O.poly_eval(a5, j) * O.poly_eval(b5, j) % O.R == O.poly_eval(cc5, j) for j in (1, 2, 3))
 
 
 def phgr13_sparse_exponent_check(be, log_n, seed, n=None):
