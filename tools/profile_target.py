@@ -17,8 +17,15 @@ rng = random.Random(1)
 n = 1 << log_n
 if what in ("g1", "g2"):
     group = L.PS_G1 if what == "g1" else L.PS_G2
-    ks = b"".join(rng.randrange(1, ps.R).to_bytes(32, "big") for _ in range(n))
-    sc = b"".join(rng.randrange(ps.R).to_bytes(32, "big") for _ in range(n))
+    import numpy as np
+    g = np.random.default_rng(1)
+
+    def scalars(seed_off):       # uniform below 2^254 < r, big-endian rows (as bench.py)
+        a = g.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        a[:, 0] &= 0x3F
+        a[:, 31] |= 1
+        return a.tobytes()
+    ks, sc = scalars(0), scalars(1)
     bases = be.bases_from_scalars(group, ks, 0, -1)   # all window tables, like the keys and bench.py
     for _ in range(2):
         be.msm(bases, sc)
