@@ -639,7 +639,7 @@ def groth16_section(be, args, world):
         out["gpu_launches_per_proof_all_devices"] = int((mb.launch_count() - l0) // (reps + 2))
         pr = ps.Groth16Prove(tr, sq, wb, r, s, backend=mb)
         marks = ["witness gathered", "subtree interpolated", "roots gathered", "top levels", "a, b swapped", "slice scalars (+ division on device 0)",
-                 "early MSMs", "late MSM", "combined + encoded"]
+                 "MSMs (B_d at once, A_d + C_d after h)", "record ready", "combined + encoded"]
         out["timeline_ms"] = {"device%d" % d: dict(zip(marks, [round(x, 3) for x in mb.timeline(d)])) for d in (0, world - 1)}
         out["how"] = "ONE library call per proof (ps_mg16_prove): worker thread per GPU, exchanges over NVLink peer memory"
         wb.close()

@@ -669,10 +669,10 @@ int g16_key_load_slice(ps_ctx* ctx, const KeySlice& sl, int format, int window_g
   return PS_OK;
 }
 
-int g16_slice_msm_early(ps_ctx* ctx, const ps_g16_key* key, const KeySlice& sl, const Fr* scA, const Fr* scB, const Fr* scC,
-                        void* d_partials) {
+int g16_slice_msm_all(ps_ctx* ctx, const ps_g16_key* key, const KeySlice& sl, const Fr* scA, const Fr* scB, const Fr* scC,
+                      void* d_partials, const std::function<int()>& before_g1) {
   PS_TRY(begin_call(ctx));
-  uint8_t* out = (uint8_t*)d_partials;  // [A: 192 B | C early: 192 B | B: 384 B]
+  uint8_t* out = (uint8_t*)d_partials;  // [A: 192 B | C: 192 B | B: 384 B | 192 B left zero (infinity)]
   const size_t nx = sl.x_hi - sl.x_lo, nt = sl.t_hi - sl.t_lo, nn = sl.n_hi - sl.n_lo, k3 = sl.consts ? 3 : 0, k2 = sl.consts ? 2 : 0;
   PS_TRY(ctx_fork(ctx));
   ForkGuard fg(ctx);
@@ -680,10 +680,12 @@ int g16_slice_msm_early(ps_ctx* ctx, const ps_g16_key* key, const KeySlice& sl, 
     SecondaryScope scope(ctx);
     PS_TRY(msm_on_bases<Fp2>(ctx, key->B, 0, (const uint32_t*)scB, nx + k2, 0, (G2XYZZ*)(out + 384)));
   }
-  const SegSpec segs[3] = {{key->A, 0, (const uint32_t*)scA, nx + k2, 0, 0},
-                           {key->C, 0, (const uint32_t*)scC, nn, 0, 1},
-                           {key->C, nn + nt, (const uint32_t*)(scC + nn + nt), nx + k3, 0, 1}};
-  PS_TRY(msm_batch<Fp>(ctx, segs, 3, 2, (G1XYZZ*)out));
+  if (before_g1) PS_TRY(before_g1());   // e.g. the primary stream starts waiting for h here, with B_d already under way
+  // scC = [w_nio | h | s a + r b | s r rs] against C_d = [NioLP | XiT | Xi | Alpha Beta Delta]: one contiguous segment
+  const SegSpec segs[2] = {{key->A, 0, (const uint32_t*)scA, nx + k2, 0, 0},
+                           {key->C, 0, (const uint32_t*)scC, nn + nt + nx + k3, 0, 1}};
+  PS_TRY(msm_batch<Fp>(ctx, segs, 2, 2, (G1XYZZ*)out));
+  PS_TRY(dev_memset(out + 768, 0, 192, ctx->stream));
   return fg.join();
 }
 
@@ -696,11 +698,6 @@ int msm_partial_host_scalars(ps_ctx* ctx, const ps_bases* b, const uint8_t* scal
   return msm_on_bases<Fp2>(ctx, b, 0, d_sc, n, 0, (G2XYZZ*)d_out_xyzz);
 }
 
-int g16_slice_msm_late(ps_ctx* ctx, const ps_g16_key* key, const KeySlice& sl, const Fr* scC, void* d_partial) {
-  PS_TRY(begin_call(ctx));
-  const size_t nt = sl.t_hi - sl.t_lo, nn = sl.n_hi - sl.n_lo;
-  return msm_on_bases<Fp>(ctx, key->C, nn, (const uint32_t*)(scC + nn), nt, 0, (G1XYZZ*)d_partial);
-}
 }  // namespace ps
 }  // extern "C++"
 

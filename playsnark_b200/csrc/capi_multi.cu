@@ -14,10 +14,11 @@
 //   R  roots pushed to the devices of the same polynomial; each of them runs the top log2(parts) levels
 //      (redundantly: same latency as one leader, and no broadcast of 32 MB vectors afterwards)
 //   X  pairwise swap d <-> d + parts: afterwards every device holds a and b
-//   S  its slices of the scalar vectors; then the early MSMs: A_d, B_d (G2, second stream) and the pieces of C that
-//      do not depend on h ([w_nio] . NioLP_d and [s a + r b | s r rs] . [Xi_d | ...]) as one batched pipeline
 //   H  device 0 divides (h = floor(a b / z)) with a smaller MSM share and pushes each device its slice of h
-//   L  late MSM h_d . XiT_d;  the 960-byte records are pushed to device 0, which adds and encodes.
+//   S  its slices of the scalar vectors; B_d (G2) starts at once on the second, high-priority stream and runs while
+//      device 0 divides; when h_d has arrived, A_d and the whole of C_d ([w_nio | h | s a + r b | s r rs] against
+//      [NioLP_d | XiT_d | Xi_d | ...]) run as ONE G1 pipeline with two outputs, B_d's tail hidden beneath it
+//   L  the 976-byte records are pushed to device 0, which adds and encodes.
 // Other device counts (odd, or a dense QAP): device 0 computes all scalar vectors and pushes slices.
 // The key is SHARDED: device d holds only its index ranges of Xi, Xi2, XiT, NioLP (with all window tables).
 #include "group_ops.cuh"
@@ -598,10 +599,16 @@ int ps_mg16_prove(ps_mctx* m, const ps_mg16_key* key, const ps_mqap* qap, const 
       }
       STAGE(g16_slice_scalars(ctx, sl, r_be, s_be, w.coef[0], w.coef[1], w.wfull, diff, w.scA, w.scB, w.scC));
       STAGE(tl_mark(m, mark++, d));
-      STAGE(g16_slice_msm_early(ctx, key->part[d], sl, w.scA, w.scB, w.scC, w.rec));
+      // MSMs: B_d starts at once on the second stream; the G1 pipeline (A_d and all of C_d) is enqueued behind the
+      // arrival of h.  The host barrier (device 0 has recorded its event) sits inside the call, after B_d's launches.
+      bool arrived = false;
+      STAGE(g16_slice_msm_all(ctx, key->part[d], sl, w.scA, w.scB, w.scC, w.rec, [&]() -> int {
+        m->bar.arrive();
+        arrived = true;
+        return d != 0 ? ev_wait(m, 3, 0, d) : PS_OK;
+      }));
+      if (!arrived) m->bar.arrive();   // a failed device still meets the others
       STAGE(tl_mark(m, mark++, d));
-      m->bar.arrive();
-      if (d != 0) STAGE(ev_wait(m, 3, 0, d));
     } else {
       // device 0 computes the three scalar vectors (quotient included) and pushes every device its slices
       if (d == 0) {
@@ -636,11 +643,10 @@ int ps_mg16_prove(ps_mctx* m, const ps_mg16_key* key, const ps_mqap* qap, const 
       m->bar.arrive();
       if (d != 0) STAGE(ev_wait(m, 3, 0, d));
       STAGE(tl_mark(m, mark++, d));
-      STAGE(g16_slice_msm_early(ctx, key->part[d], sl, w.scA, w.scB, w.scC, w.rec));
+      STAGE(g16_slice_msm_all(ctx, key->part[d], sl, w.scA, w.scB, w.scC, w.rec, nullptr));
       STAGE(tl_mark(m, mark++, d));
     }
-    // L: the part of C that needs h; then the record goes to device 0
-    STAGE(g16_slice_msm_late(ctx, key->part[d], sl, w.scC, w.rec + 768));
+    // the record goes to device 0
     STAGE(dev_d2d(w.rec + 960, w.status, 16, ctx->stream));
     STAGE(tl_mark(m, mark++, d));
     STAGE(peer_copy(m, m->ws[0].recs + (size_t)d * REC_BYTES, 0, w.rec, d, REC_BYTES));

@@ -3,6 +3,8 @@
 #pragma once
 #include "poly_api.cuh"
 
+#include <functional>
+
 namespace ps {
 
 // Index ranges of the proving key one device holds: points [x_lo, x_hi) of Xi and Xi2, [t_lo, t_hi) of XiT,
@@ -24,11 +26,14 @@ int g16_key_load_slice(ps_ctx* ctx, const KeySlice& sl, int format, int window_g
 int g16_slice_scalars(ps_ctx* ctx, const KeySlice& sl, const uint8_t* r_be, const uint8_t* s_be, const Fr* d_a, const Fr* d_b,
                       const Fr* d_w, size_t diff, Fr* scA, Fr* scB, Fr* scC);
 
-// the MSMs of one device of a sharded proof.  early: A_d and C_d's [NioLP | Xi | consts] pieces as one G1 pipeline, B_d
-// on the second stream -> d_partials [A 192 B | C-early 192 B | B 384 B]; late: C_d's XiT piece -> 192 B.
-int g16_slice_msm_early(ps_ctx* ctx, const ps_g16_key* key, const KeySlice& sl, const Fr* scA, const Fr* scB, const Fr* scC,
-                        void* d_partials);
-int g16_slice_msm_late(ps_ctx* ctx, const ps_g16_key* key, const KeySlice& sl, const Fr* scC, void* d_partial);
+// The MSMs of one device of a sharded proof: B_d (G2) goes out first, on the second (high-priority) stream -- it needs
+// neither h nor the witness tail; then `before_g1` runs on the host (the pipelined prover makes the primary stream wait
+// for device 0's h there), then A_d and the WHOLE of C_d as one G1 pipeline with two outputs.  B_d's accumulation fills
+// the time device 0 spends dividing, its latency-bound tail hides under the G1 accumulation, and every device pays the
+// fixed sort / merge / reduction cost of a G1 pipeline once per proof instead of twice (early + late).
+//   d_partials: [A 192 B | C 192 B | B 384 B | 192 B zero]   (record layout of ps_g16_combine, C's late slot = infinity)
+int g16_slice_msm_all(ps_ctx* ctx, const ps_g16_key* key, const KeySlice& sl, const Fr* scA, const Fr* scB, const Fr* scC,
+                      void* d_partials, const std::function<int()>& before_g1);
 
 // Poly.BlindEval over the whole of `b` with host scalars (wire format), leaving the XYZZ partial on the device
 // (one device's share of ps_mmsm); *d_err_out points at the device flag for scalars >= r

@@ -29,7 +29,7 @@ want = E.groth16_expected(sq, wit, toxic, r, s)[:3]
 mb = ps.MultiBackend(list(range(world)))
 wb = ps.HostBuffer(be, b"".join(v.to_bytes(32, "big") for v in wit))
 marks = ["witness gathered", "subtree interpolated", "roots gathered", "top levels", "a, b swapped", "slice scalars (+ division on device 0)",
-         "early MSMs", "late MSM", "combined + encoded"]
+         "MSMs (B_d at once, A_d + C_d after h)", "record ready", "combined + encoded"]
 rows = []
 sq._resident(mb)
 for share, wave_floor in [(shares[0], 0)] + [(sh, 1) for sh in shares]:
