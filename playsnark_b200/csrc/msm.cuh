@@ -666,11 +666,14 @@ int msm_run_batch(ps_ctx* ctx, const MsmPlan& g, const Affine<F>* tab, XYZZ<F>* 
   while (L0 < 512 && L0 < avg_bucket) L0 <<= 1;
   if (L0 < 512 && max_ent / (2 * (size_t)L0) >= 400000) L0 <<= 1;
   const size_t R = (size_t)ctx->sm_count * MsmAccumK<F>::MIN_BLOCKS * MsmAccumK<F>::BLOCK;
-  // Rounding the wave count DOWN (option msm_wave_floor, default) gives chunks of L0 .. 2 L0 entries instead of
-  // L0/2 .. L0: the same accumulation work in half as many chunks, i.e. half the boundary partials, slot writes and
-  // merge items -- what the shard-sized MSMs of the multi-GPU prover (1.1 waves at L0) spend a third of their time on.
+  // With SHORT chunks (L0 <= 128: small MSMs, few entries per bucket) the wave count is rounded DOWN instead (option
+  // msm_wave_floor, default): chunks of L0 .. 2 L0 entries instead of L0/2 .. L0, i.e. the same accumulation work in
+  // half as many chunks -- half the boundary partials, slot writes and merge items, which is what the shard-sized MSMs
+  // of the multi-GPU prover spend a third of their time on (G1, 2^17 points: 2.34 -> 1.91 ms; 8-GPU proof 12.5 -> 11.6 ms).
+  // Long chunks amortise that overhead anyway and prefer the better balance of two waves (G2, 2^20 points, L0 = 256:
+  // one wave of 415 entries was 0.35 ms slower than two of 207).
   size_t waves = (max_ent + R * L0 - 1) / (R * L0);
-  if (ctx->msm_wave_floor && waves > 1 && waves < 6) waves = max_ent / (R * L0);
+  if (ctx->msm_wave_floor && L0 <= 128 && waves > 1 && waves < 6) waves = max_ent / (R * L0);
   // with many waves the last, partly filled one costs little and L0 itself is kept (more, shorter chunks
   // only add boundary partials: measured +0.2 ms of merge at 2^20, c = 20, for no gain in the accumulation)
   uint32_t L = waves >= 6 ? L0 : (uint32_t)((max_ent + waves * R - 1) / (waves * R));
