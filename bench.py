@@ -690,6 +690,38 @@ def phgr13_section(be, sizes):
     return res
 
 
+def verify_section(be, q, w, toxic, ptoxic, r, s, pr, pp):
+    """Groth16Verify / PHGR13Verify on the device for the 2^10 chain's proofs (decisions: accept the honest
+    proof, reject a wrong public input), and the throughput of the pairing-product checks for a batch of proofs."""
+    import playsnark_b200 as ps
+    from playsnark_b200 import _lib as L
+    progress("verifiers")
+    diff = q.nbVars - q.nbIO
+    tr = ps.NewGroth16TrustedSetup(q, backend=be, toxic=toxic, fmt=L.PS_FMT_COMPRESSED, export=True)
+    ek, vk, _ = ps.NewPHGR13TrustedSetup(q, backend=be, toxic=ptoxic, with_vk=True)
+    io = w[:diff]
+    bad = list(io); bad[-1] = (bad[-1] + 1) % R
+    ok = (ps.Groth16Verify(tr, q, pr, io, backend=be) and not ps.Groth16Verify(tr, q, pr, bad, backend=be)
+          and ps.PHGR13Verify(vk, q, pp, io, backend=be) and not ps.PHGR13Verify(vk, q, pp, bad, backend=be))
+    _, g_best = _time_calls(lambda: ps.Groth16Verify(tr, q, pr, io, backend=be), 3)
+    _, p_best = _time_calls(lambda: ps.PHGR13Verify(vk, q, pp, io, backend=be), 3)
+    # a batch of Groth16 equations in one call: 4 pairs each (e(-A,B) e(Alpha,Beta2) e(b1,Gamma) e(C,Delta2) == 1 with b1 = 0
+    # replaced by the honest pairs of this proof is not available host-side, so the batch repeats e(aG,bH) e(-abG,H) == 1)
+    from oracle import ps_oracle as O
+    a_, b_ = 0x1234567, 0x7654321
+    g1a, g1ab = O.g1_compress(O.g1_mul(a_)), O.g1_compress(O.g1_mul((-a_ * b_) % R))
+    g2b, g2g = O.g2_compress(O.g2_mul(b_)), O.g2_compress(O.g2_mul(1))
+    batch = 2048
+    P1, Q2 = [g1a, g1ab, g1a, g1ab] * batch, [g2b, g2g, g2b, g2g] * batch
+    res = ps.PairingCheckBatch(P1, Q2, [4] * batch, backend=be)
+    _, b_best = _time_calls(lambda: ps.PairingCheckBatch(P1, Q2, [4] * batch, backend=be), 2)
+    tr.close(); ek.close()
+    return {"decisions": "honest proofs accepted, wrong public input rejected (Groth16 and PHGR13)" if ok and all(res) else "MISMATCH",
+            "groth16_verify_ms": g_best * 1e3, "phgr13_verify_ms": p_best * 1e3,
+            "batch": {"checks": batch, "pairs_per_check": 4, "ms": b_best * 1e3, "checks_per_s": batch / b_best,
+                      "what": "ps_pairing_check_batch: one thread per Miller loop and per final exponentiation"}}
+
+
 def small_configs_section(be, cpu_flow):
     """BASELINE configs[1] and [2]: the 2^10 repeated-squaring circuit (Groth16 and PHGR13) and a 2^16-constraint sparse
     circuit (Groth16); keys from the device setups, exponent-level parity, end-to-end latency through the
@@ -724,6 +756,11 @@ def small_configs_section(be, cpu_flow):
             row["cpu_port_groth16_prove_s"] = cpu_by_n[n]["prove_s"]
             row["speedup_vs_cpu_port_prove"] = cpu_by_n[n]["prove_s"] / g_best
         out["chain_2p%d" % k] = row
+        if k == 10:
+            try:
+                out["verify"] = verify_section(be, q, w, toxic, ptoxic, r, s, pr, pp)
+            except Exception as e:
+                out["verify"] = {"error": repr(e)}
         tr.close(); ek.close(); q.close()
     k = 16
     progress("sparse circuit 2^16")

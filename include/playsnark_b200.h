@@ -237,6 +237,25 @@ int ps_phgr13_setup(ps_ctx* ctx, const ps_qap* qap, const uint8_t* toxic_be, ps_
                     uint8_t* out_vk_vs, uint8_t* out_vk_ws, uint8_t* out_vk_ys);
 int ps_phgr13_key_export(ps_ctx* ctx, const ps_phgr13_key* key, int format, uint8_t* gsi, uint8_t* vs, uint8_t* ws,
                          uint8_t* ys, uint8_t* vas, uint8_t* was, uint8_t* yas, uint8_t* vbs, uint8_t* wbs, uint8_t* ybs);
+/* ---- verifiers -----------------------------------------------------------------------------------
+ * The reference compares GT values for equality only; every such equation is decided as prod_i e(P_i, Q_i) == 1.
+ * ps_pairing_check_batch: n_checks independent products; check t covers counts[t] consecutive pairs of the flat point
+ * arrays (wire format `format`); ok[t] = 1 when its product is 1.  One thread per Miller loop and per final
+ * exponentiation: the parallelism is across pairs, checks and the proofs of a batch.  Points are validated like key
+ * material (curve, subgroup): PS_ERR_ENCODING otherwise.  Replaces Suite.Pair + Equal, curve.go:36-38.           */
+int ps_pairing_check_batch(ps_ctx* ctx, const uint8_t* g1_points, const uint8_t* g2_points, const uint32_t* counts,
+                           size_t n_checks, int format, uint8_t* ok);
+/* Groth16Verify (groth16.go:214-233): e(A, B) == e(Alpha, Beta2) e(sum_i io[i] IoLP[i], Gamma) e(C, Delta2).
+ * Compressed points; iolp = n_io points of 48 B, io_be = n_io scalars (32 B big-endian); *ok = 1 / 0.             */
+int ps_g16_verify(ps_ctx* ctx, const uint8_t* alpha, const uint8_t* beta2, const uint8_t* gamma2, const uint8_t* delta2,
+                  const uint8_t* iolp, size_t n_io, const uint8_t* io_be, const uint8_t* A, const uint8_t* B,
+                  const uint8_t* C, int* ok);
+/* PHGR13Verify (pinochio.go:281-375): division check, three CRS checks, linear check.  vk_fixed = the 576 bytes of
+ * ps_phgr13_setup; vs / ws / ys = the commitments of the first n_io (public) variables (48 / 96 / 48 B each);
+ * proof = the 432 bytes of ps_phgr13_prove.                                                                     */
+int ps_phgr13_verify(ps_ctx* ctx, const uint8_t* vk_fixed, const uint8_t* vs, const uint8_t* ws, const uint8_t* ys,
+                     size_t n_io, const uint8_t* io_be, const uint8_t* proof, int* ok);
+
 /* PHGR13Prove (pinochio.go:207-254).  out: hs, vss, yss, vass, wass, yass, gz (7 x 48 B, in this
  * order) then wss (96 B) = 432 bytes.                                                           */
 int ps_phgr13_prove(ps_ctx* ctx, const ps_phgr13_key* key, const ps_qap* qap, const uint8_t* witness_be,

@@ -70,6 +70,9 @@ SYMBOLS = [
     ("ps_phgr13_key_load", _I, [_P, _SZ, _SZ, _I] + [_B] * 10 + [C.POINTER(_P)]),
     ("ps_phgr13_key_free", None, [_P]),
     ("ps_phgr13_prove", _I, [_P, _P, _P, _P, _P, _P]),
+    ("ps_pairing_check_batch", _I, [_P, _B, _B, C.POINTER(C.c_uint32), _SZ, _I, _P]),
+    ("ps_g16_verify", _I, [_P, _B, _B, _B, _B, _B, _SZ, _B, _B, _B, _B, C.POINTER(C.c_int)]),
+    ("ps_phgr13_verify", _I, [_P, _B, _B, _B, _B, _SZ, _B, _B, C.POINTER(C.c_int)]),
     ("ps_mctx_create", _I, [C.POINTER(C.c_int), _I, C.POINTER(_P)]),
     ("ps_mctx_destroy", None, [_P]),
     ("ps_mctx_size", _I, [_P]),

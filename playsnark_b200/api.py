@@ -730,3 +730,50 @@ def PHGR13Prove(ek: PHGR13EvalKey, qap: QAP, solution: Vector, backend: Optional
     g1 = [o[i * 48:(i + 1) * 48] for i in range(7)]  # hs vss yss vass wass yass gz
     return PHGR13Proof(hs=g1[0], vss=g1[1], yss=g1[2], vass=g1[3], wass=g1[4], yass=g1[5], gz=g1[6], wss=o[336:432],
                        h=_fr_list(hb.raw[:(qap.nbGates - 1) * 32]) if want_h else None)
+
+
+# ---- verifiers: pairing-product checks on the device --------------------------------------------
+def PairingCheckBatch(g1_points: Sequence[bytes], g2_points: Sequence[bytes], counts: Sequence[int],
+                      backend: Optional[Backend] = None) -> List[bool]:
+    """For every check t: prod over its counts[t] consecutive pairs of e(P_i, Q_i) == 1 (compressed points).  What the
+    reference's `Pair(...)` / `Equal` comparisons (curve.go:36-38) decide, with one side's G1 points negated."""
+    b = backend or default_backend()
+    if len(g1_points) != len(g2_points) or sum(counts) != len(g1_points):
+        raise ValueError("pairs and counts disagree")
+    ok = C.create_string_buffer(max(1, len(counts)))
+    cnt = (C.c_uint32 * max(1, len(counts)))(*counts)
+    b._check(b.lib.ps_pairing_check_batch(b.ctx, b"".join(g1_points), b"".join(g2_points), cnt, len(counts), L.PS_FMT_COMPRESSED, ok))
+    return [ok.raw[i] == 1 for i in range(len(counts))]
+
+
+def Groth16Verify(tr: Groth16Setup, q, p: "Groth16Proof", io: Vector, backend: Optional[Backend] = None) -> bool:
+    """Groth16Verify, groth16.go:214-233.  `tr` needs its verifier side: Alpha, Beta2, Delta2 (compressed), IoLP and Gamma
+    (always compressed; NewGroth16TrustedSetup fills them).  `io` = the public part of the solution, one per IoLP."""
+    b = backend or default_backend()
+    if tr.fmt != L.PS_FMT_COMPRESSED:
+        raise ValueError("Groth16Verify takes the setup's points in compressed form (fmt = PS_FMT_COMPRESSED)")
+    n_io = len(tr.IoLP)
+    if len(io) < n_io:
+        raise ValueError("different number of public inputs than IoLP elements")
+    ok = C.c_int(0)
+    b._check(b.lib.ps_g16_verify(b.ctx, _join(tr.Alpha), _join(tr.Beta2), tr.Gamma, _join(tr.Delta2), b"".join(tr.IoLP) or b"\0", n_io,
+                                 _fr_bytes(list(io[:n_io])) or b"\0", p.A, p.B, p.C, C.byref(ok)))
+    return ok.value == 1
+
+
+def PHGR13Verify(vk: dict, qap, p: PHGR13Proof, io: Vector, backend: Optional[Backend] = None) -> bool:
+    """PHGR13Verify, pinochio.go:281-375.  `vk` = the dict NewPHGR13TrustedSetup(..., with_vk=True) returns (av, aw, ay,
+    gamma, bgamma, bgamma2, yts and the per-variable commitments vs / ws / ys); `io` = the first nbVars - nbIO values of
+    the solution (the public ones in this reference's numbering)."""
+    b = backend or default_backend()
+    diff = qap.nbVars - qap.nbIO
+    if len(io) < diff:
+        raise ValueError("different number of public inputs than verification-key elements")
+    fixed = vk["av"] + vk["aw"] + vk["ay"] + vk["gamma"] + vk["bgamma"] + vk["bgamma2"] + vk["yts"]
+    proof = p.hs + p.vss + p.yss + p.vass + p.wass + p.yass + p.gz + p.wss
+    ok = C.c_int(0)
+    j = lambda xs: b"".join(xs[:diff]) or b"\0"
+    b._check(b.lib.ps_phgr13_verify(b.ctx, fixed, j(vk["vs"]), j(vk["ws"]), j(vk["ys"]), diff, _fr_bytes(list(io[:diff])) or b"\0",
+                                    proof, C.byref(ok)))
+    return ok.value == 1
+

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libplaysnark_b200.so")
 
-CU_SOURCES = [os.path.join(CSRC, f) for f in ("capi.cu", "capi_poly.cu", "capi_multi.cu", "group_g1.cu", "group_g2.cu", "accum_g2.cu")
+CU_SOURCES = [os.path.join(CSRC, f) for f in ("capi.cu", "capi_poly.cu", "capi_multi.cu", "capi_verify.cu", "group_g1.cu", "group_g2.cu", "accum_g2.cu")
               if os.path.exists(os.path.join(CSRC, f))]
 
 NVCC_FLAGS = [

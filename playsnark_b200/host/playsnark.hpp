@@ -4,6 +4,7 @@
 // language host layer: same names, argument meaning and error behaviour as package playsnark
 //   Groth16Prove(tr, q, sol)        groth16.go:122     PHGR13Prove(ek, qap, solution)  pinochio.go:207
 //   QAP::Quotient(sol)              qap.go:151         BlindEval(p, blindedPoint)      algebra.go:348
+//   Groth16Verify(vk, p, io)        groth16.go:214     PHGR13Verify(vk, p, io)         pinochio.go:281
 // Scalars are 32-byte big-endian Elements (kyber Scalar.MarshalBinary), points their compressed
 // MarshalBinary bytes.  Go panics become C++ exceptions with the same message.  No arithmetic lives
 // here: everything is computed by libplaysnark_b200.so on the GPU.
@@ -213,5 +214,49 @@ class PHGR13Prover {
   Backend& b_;
   ps_phgr13_key* k_ = nullptr;
 };
+
+// ---- verifiers --------------------------------------------------------------------------------------------------
+// Groth16Verify, groth16.go:214-233: the verifier side of the setup (IoLP over the public variables, Gamma) and the
+// public part of the solution, io[i] for IoLP[i]
+struct Groth16VerifKey {
+  G1 Alpha{};
+  G2 Beta2{}, Gamma{}, Delta2{};
+  std::vector<G1> IoLP;
+};
+inline bool Groth16Verify(Backend& b, const Groth16VerifKey& vk, const Groth16Proof& p, const Vector& io) {
+  if (io.size() < vk.IoLP.size()) throw std::invalid_argument("different number of public inputs than IoLP elements");
+  Poly w(vk.IoLP.size());
+  for (size_t i = 0; i < w.size(); i++) w[i] = ToFieldElement(io[i]);
+  auto iolp = flatten(vk.IoLP), wb = flatten(w);
+  int ok = 0;
+  check(ps_g16_verify(b.ctx(), vk.Alpha.data(), vk.Beta2.data(), vk.Gamma.data(), vk.Delta2.data(), iolp.data(), vk.IoLP.size(), wb.data(),
+                      p.A.data(), p.B.data(), p.C.data(), &ok));
+  return ok == 1;
+}
+// PHGR13Verify, pinochio.go:281-375; vs / ws / ys = the commitments of the public variables (vk.vs[:diff] ...)
+struct PHGR13VerifKey {  // pinochio.go:66-90
+  G2 av{}, ay{}, gamma{}, bgamma2{}, yts{};
+  G1 aw{}, bgamma{};
+  std::vector<G1> vs, ys;
+  std::vector<G2> ws;
+};
+inline bool PHGR13Verify(Backend& b, const PHGR13VerifKey& vk, const PHGR13Proof& p, const Vector& io) {
+  const size_t diff = vk.vs.size();
+  if (vk.ws.size() != diff || vk.ys.size() != diff || io.size() < diff)
+    throw std::invalid_argument("different number of public inputs than verification-key elements");
+  uint8_t fixed[576], proof[432];
+  std::memcpy(fixed, vk.av.data(), 96); std::memcpy(fixed + 96, vk.aw.data(), 48); std::memcpy(fixed + 144, vk.ay.data(), 96);
+  std::memcpy(fixed + 240, vk.gamma.data(), 96); std::memcpy(fixed + 336, vk.bgamma.data(), 48);
+  std::memcpy(fixed + 384, vk.bgamma2.data(), 96); std::memcpy(fixed + 480, vk.yts.data(), 96);
+  const G1* order[7] = {&p.hs, &p.vss, &p.yss, &p.vass, &p.wass, &p.yass, &p.gz};
+  for (int i = 0; i < 7; i++) std::memcpy(proof + 48 * i, order[i]->data(), 48);
+  std::memcpy(proof + 336, p.wss.data(), 96);
+  Poly w(diff);
+  for (size_t i = 0; i < diff; i++) w[i] = ToFieldElement(io[i]);
+  auto vs = flatten(vk.vs), ws = flatten(vk.ws), ys = flatten(vk.ys), wb = flatten(w);
+  int ok = 0;
+  check(ps_phgr13_verify(b.ctx(), fixed, vs.data(), ws.data(), ys.data(), diff, wb.data(), proof, &ok));
+  return ok == 1;
+}
 
 }  // namespace playsnark

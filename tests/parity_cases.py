@@ -725,3 +725,111 @@ def device_setups_vs_oracle(be, n=12, seed=3):
         assert vk["yts"] == g2(ovk["yts"])
         assert vk["vs"] == [g1(p) for p in ovk["vs"]] and vk["ws"] == [g2(p) for p in ovk["ws"]] and vk["ys"] == [g1(p) for p in ovk["ys"]]
         ek.close(); q.close()
+
+
+# ---- verifiers: the device decides every case the way the oracle's verifier does ----------------
+def pairing_checks(be):
+    """bilinearity / non-degeneracy of the device pairing product (the only property the verifiers observe), infinity
+    on either side, several checks in one call"""
+    a, b = 0x1234567, 0x7654321
+    g1 = lambda k: O.g1_compress(O.g1_mul(k % O.R))
+    g2 = lambda k: O.g2_compress(O.g2_mul(k % O.R))
+    inf1, inf2 = O.g1_compress(None), O.g2_compress(None)
+    P1 = [g1(a), g1(-a * b), g1(a), g1(-a * b + 1), g1(1), inf1, g1(a), g1(5), g1(7), g1(-(5 * 11 + 7 * 13))]
+    Q2 = [g2(b), g2(1), g2(b), g2(1), g2(1), g2(3), inf2, g2(11), g2(13), g2(1)]
+    res = api.PairingCheckBatch(P1, Q2, [2, 2, 1, 2, 3], backend=be)
+    #      e(aG,bH)e(-abG,H)=1 | off by one | e(G,H) != 1 | two infinities -> 1 | e(5G,11H)e(7G,13H)e(-(55+91)G,H)=1
+    assert res == [True, False, False, True, True], res
+    assert res == [O.fp12_mul(O.pairing(O.g1_decompress(P1[0]), O.g2_decompress(Q2[0])),
+                              O.pairing(O.g1_decompress(P1[1]), O.g2_decompress(Q2[1]))) == O.FP12_ONE,
+                   False, False, True, True]
+    import pytest
+    from playsnark_b200._lib import PlaysnarkError
+    bad = bytearray(g1(a)); bad[-1] ^= 1                      # not on the curve
+    with pytest.raises(PlaysnarkError):
+        api.PairingCheckBatch([bytes(bad)], [g2(b)], [1], backend=be)
+
+
+def groth16_verify_cases(be, n=8, seed=9):
+    """Groth16Verify (groth16.go:214-233) on the device against the oracle's verifier: an honest proof (from the oracle's
+    prover and from the device's), a mutated A / C, a wrong public input, a wrong Gamma"""
+    r1, w = H.mixed_circuit(n, seed, max(1, n // 2))
+    oq = O.to_qap(r1)
+    smp = O.Sampler(seed)
+    otr = O.groth16_setup(oq, smp)
+    rr, ss = smp.fr(), smp.fr()
+    op = O.groth16_prove(otr, oq, w, rr, ss)
+    diff = oq.nb_vars - oq.nb_io
+    io = w[:diff]
+    assert O.groth16_verify(otr, oq, op, io)
+    tr = H.mirror_g16_setup(otr)
+    q = H.mirror_qap(oq)
+    proof = api.Groth16Proof(tp=api.Groth16ToxicProof(rr, ss), A=O.g1_compress(op["A"]), B=O.g2_compress(op["B"]), C=O.g1_compress(op["C"]))
+    assert api.Groth16Verify(tr, q, proof, io, backend=be)
+    dev = api.Groth16Prove(tr, q, w, rr, ss, backend=be)                       # the device's own proof
+    assert (dev.A, dev.B, dev.C) == (proof.A, proof.B, proof.C) and api.Groth16Verify(tr, q, dev, io, backend=be)
+    for f in ("A", "C"):
+        bad_o = dict(op); bad_o[f] = O.g1_add(op[f], O.G1_GEN)
+        bad = api.Groth16Proof(tp=proof.tp, A=O.g1_compress(bad_o["A"]), B=proof.B, C=O.g1_compress(bad_o["C"]))
+        assert not O.groth16_verify(otr, oq, bad_o, io)
+        assert not api.Groth16Verify(tr, q, bad, io, backend=be), f
+    if diff > 1:
+        io2 = list(io); io2[-1] = (io2[-1] + 1) % O.R
+        assert not O.groth16_verify(otr, oq, op, io2) and not api.Groth16Verify(tr, q, proof, io2, backend=be)
+    tr2 = H.mirror_g16_setup(otr); tr2.Gamma = O.g2_compress(O.g2_add(otr.Gamma, O.G2_GEN))
+    assert not api.Groth16Verify(tr2, q, proof, io, backend=be)
+    tr.close(); q.close()
+
+
+def phgr13_verify_cases(be, n=6, seed=4):
+    """PHGR13Verify (pinochio.go:281-375) on the device: the honest proof verifies; the five mutated proof fields and
+    the three mutated verification-key fields of pinocchio_test.go:243-276 are rejected -- the oracle's decisions"""
+    r1, w = H.mixed_circuit(n, seed, max(1, n // 2))
+    oq = O.to_qap(r1)
+    st = O.phgr13_setup(oq, O.Sampler(seed + 1))
+    pp = O.phgr13_prove(st["EK"], oq, w)
+    diff = oq.nb_vars - oq.nb_io
+    io = w[:diff]
+    assert O.phgr13_verify(st["VK"], oq, pp, io)
+    g1, g2 = O.g1_compress, O.g2_compress
+
+    def mirror_vk(vk):
+        return {"av": g2(vk["av"]), "aw": g1(vk["aw"]), "ay": g2(vk["ay"]), "gamma": g2(vk["gamma"]), "bgamma": g1(vk["bgamma"]),
+                "bgamma2": g2(vk["bgamma2"]), "yts": g2(vk["yts"]), "vs": [g1(p) for p in vk["vs"]], "ws": [g2(p) for p in vk["ws"]],
+                "ys": [g1(p) for p in vk["ys"]]}
+
+    def mirror_proof(d):
+        return api.PHGR13Proof(**{f: (g2 if f == "wss" else g1)(d[f]) for f in O.PHGR13_FIELDS})
+    q = H.mirror_qap(oq)
+    assert api.PHGR13Verify(mirror_vk(st["VK"]), q, mirror_proof(pp), io, backend=be)
+    dev = api.PHGR13Prove(H.mirror_phgr13_ek(st["EK"]), q, w, backend=be)      # the device's own proof
+    assert api.PHGR13Verify(mirror_vk(st["VK"]), q, dev, io, backend=be)
+    for f in ("hs", "vss", "vass", "wass", "yass"):
+        bad = dict(pp); bad[f] = O.g1_add(pp[f], O.G1_GEN)
+        assert not O.phgr13_verify(st["VK"], oq, bad, io)
+        assert not api.PHGR13Verify(mirror_vk(st["VK"]), q, mirror_proof(bad), io, backend=be), f
+    for f in ("yts", "gamma", "bgamma2"):
+        vk = dict(st["VK"]); vk[f] = O.g2_add(vk[f], O.G2_GEN)
+        assert not O.phgr13_verify(vk, oq, pp, io)
+        assert not api.PHGR13Verify(mirror_vk(vk), q, mirror_proof(pp), io, backend=be), f
+    io2 = list(io); io2[0] = (io2[0] + 1) % O.R
+    assert not api.PHGR13Verify(mirror_vk(st["VK"]), q, mirror_proof(pp), io2, backend=be)
+    q.close()
+
+
+def verify_device_setup_flow(be, n=16, seed=2):
+    """setup -> prove -> verify entirely through the device entry points (TestGroth16Verify groth16_test.go:22-30 and the
+    end of TestPinocchioProofValidDivision), sparse QAP"""
+    sq, wit = H.sparse_circuit(n, seed, n // 2)
+    diff = sq.nbVars - sq.nbIO
+    tr = api.NewGroth16TrustedSetup(sq, backend=be, fmt=L.PS_FMT_COMPRESSED)
+    pr = api.Groth16Prove(tr, sq, wit, 12345, 67890, backend=be)
+    assert api.Groth16Verify(tr, sq, pr, wit[:diff], backend=be)
+    bad = list(wit[:diff]); bad[0] = (bad[0] + 1) % O.R
+    assert not api.Groth16Verify(tr, sq, pr, bad, backend=be)
+    ek, vk, _ = api.NewPHGR13TrustedSetup(sq, backend=be, with_vk=True)
+    pp = api.PHGR13Prove(ek, sq, wit, backend=be)
+    assert api.PHGR13Verify(vk, sq, pp, wit[:diff], backend=be)
+    assert not api.PHGR13Verify(vk, sq, pp, bad, backend=be)
+    tr.close(); ek.close(); sq.close()
+

@@ -104,3 +104,10 @@ def test_msm_two_pass_scatter(be, wb, tables, kind):
         P.msm_exponent_check(be, L.PS_G2, 40, kind, wb, tables)
     finally:
         be.set_option("msm_scatter", 1)
+
+
+def test_pairing_checks(be): P.pairing_checks(be)
+def test_groth16_verify(be): P.groth16_verify_cases(be)
+def test_phgr13_verify(be): P.phgr13_verify_cases(be)
+def test_verify_device_setup_flow(be): P.verify_device_setup_flow(be, n=8)
+

@@ -168,6 +168,12 @@ def test_msm_two_pass_scatter(be, n, wb, tables, kind):
         be.set_option("msm_scatter", 1)
 
 
+def test_pairing_checks(be): P.pairing_checks(be)
+def test_groth16_verify(be): P.groth16_verify_cases(be, n=16)
+def test_phgr13_verify(be): P.phgr13_verify_cases(be, n=12)
+def test_verify_device_setup_flow(be): P.verify_device_setup_flow(be, n=1 << 10)
+
+
 def test_no_device_is_loud():
     lib = L.load()
     import ctypes as C
