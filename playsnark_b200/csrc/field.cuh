@@ -86,15 +86,6 @@ PS_DEV void mad_chain_mod(uint32_t* acc, uint32_t b) {
   for (int j = 2; j < N; j += 2) ptx_madc_wide_cc(acc[j], acc[j + 1], P::MOD(OFF + j), b);
 }
 
-// the same, consuming the pending carry flag at limb 0
-template <class P, int OFF>
-PS_DEV void mad_chain_mod_cin(uint32_t* acc, uint32_t b) {
-  constexpr int N = P::N;
-  ptx_madc_wide_cc(acc[0], acc[1], P::MOD(OFF), b);
-#pragma unroll
-  for (int j = 2; j < N; j += 2) ptx_madc_wide_cc(acc[j], acc[j + 1], P::MOD(OFF + j), b);
-}
-
 // ---- field element ----------------------------------------------------------------------------
 template <class P> struct Fe;
 template <class P> PS_NOINLINE Fe<P> fe_mul_call(const Fe<P>& a, const Fe<P>& b);
@@ -219,102 +210,9 @@ struct alignas(16) Fe {
   }
   PS_DEV Fe sqr() const { return (*this) * (*this); }
 
-  // Montgomery square a*a/R mod p with the symmetric products taken once (N(N-1)/2 + N wide MACs for
-  // the square instead of N^2, then the same N^2 + N for the reduction): 234 instead of 300 MACs for Fp.
-  //   1. off-diagonal products a_i a_j (i < j) at limb position i + j.  As in operator*, products whose
-  //      64-bit slots do not overlap share one carry chain: for a fixed i the j of one parity land on
-  //      consecutive slots.  Odd positions accumulate in O, even ones in E (both 2N limbs, aligned to
-  //      the true limb positions).  Rows are taken in increasing i, so the limb above a chain's top slot
-  //      only ever holds earlier carry-outs (at most a few units) and absorbs the new one without ripple.
-  //   2. T = 2 (E + O) + sum_i a_i^2 B^(2i): one 2N-limb addition, a one-bit funnel shift, one chain of
-  //      N squares on consecutive slots.
-  //   3. Montgomery reduction of T: the row loop of operator* without its a*b chains, started on the low
-  //      half (aligned accumulator = T_lo, shifted one = 0); the high half is added at the end.
-  //      T < p^2 and R > 2p give (T_lo + m p)/R <= p and T_hi < p, so one conditional subtraction.
-  // MEASURED SLOWER inside the bucket-accumulation kernel on B200 (2^24 G1 points: 82.4 vs 78.7 ms with
-  // the plain product; 168 registers either way, 88 instead of 32 bytes of spills): that kernel is bound
-  // by dependent-issue latency at 3 warps per scheduler, not by multiplier throughput, and the extra
-  // additions, shifts and the third 2N-limb array cost more than the 66 saved MACs.  Kept, tested
-  // (tests/test_host_arith.py), and not used by sqr().
-  PS_DEV Fe sqr_sos() const {
-    constexpr int M = 2 * N;
-    uint32_t E[M], O[M];
-#pragma unroll
-    for (int k = 0; k < M; k++) { E[k] = 0; O[k] = 0; }
-#pragma unroll
-    for (int i = 0; i < N - 1; i++) {
-      const uint32_t ai = v[i];
-      {  // j = i+1, i+3, ...: slots 2i+1, 2i+3, ... of O
-        const int cnt = (N - i) / 2, pos = 2 * i + 1;
-        ptx_mad_wide_cc(O[pos], O[pos + 1], v[i + 1], ai);
-#pragma unroll
-        for (int t = 1; t < cnt; t++) ptx_madc_wide_cc(O[pos + 2 * t], O[pos + 2 * t + 1], v[i + 1 + 2 * t], ai);
-        if (pos + 2 * cnt < M) O[pos + 2 * cnt] = ptx_addc(O[pos + 2 * cnt], 0);
-      }
-      {  // j = i+2, i+4, ...: slots 2i+2, 2i+4, ... of E
-        const int cnt = (N - 1 - i) / 2, pos = 2 * i + 2;
-        if (cnt > 0) {
-          ptx_mad_wide_cc(E[pos], E[pos + 1], v[i + 2], ai);
-#pragma unroll
-          for (int t = 1; t < cnt; t++) ptx_madc_wide_cc(E[pos + 2 * t], E[pos + 2 * t + 1], v[i + 2 + 2 * t], ai);
-          if (pos + 2 * cnt < M) E[pos + 2 * cnt] = ptx_addc(E[pos + 2 * cnt], 0);
-        }
-      }
-    }
-    // T = 2 (E + O) + diagonal
-    uint32_t T[M];
-    T[0] = ptx_add_cc(E[0], O[0]);
-#pragma unroll
-    for (int k = 1; k < M - 1; k++) T[k] = ptx_addc_cc(E[k], O[k]);
-    T[M - 1] = ptx_addc(E[M - 1], O[M - 1]);
-#pragma unroll
-    for (int k = M - 1; k > 0; k--) T[k] = (T[k] << 1) | (T[k - 1] >> 31);
-    T[0] <<= 1;
-    ptx_mad_wide_cc(T[0], T[1], v[0], v[0]);
-#pragma unroll
-    for (int k = 1; k < N; k++) ptx_madc_wide_cc(T[2 * k], T[2 * k + 1], v[k], v[k]);
-    // reduction
-    uint32_t X[N], Y[N];
-#pragma unroll
-    for (int k = 0; k < N; k++) { X[k] = T[k]; Y[k] = 0; }
-    uint32_t pend = 0;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-      uint32_t* A = (i & 1) ? Y : X;  // aligned
-      uint32_t* S = (i & 1) ? X : Y;  // shifted by one limb
-      uint32_t c1 = 0;
-      if (i > 0) {
-        A[0] = ptx_add_cc(A[0], pend);  // carry has the weight of S[0]
-        c1 = ptx_addc(0, 0);
-      }
-      const uint32_t m = A[0] * P::INV;
-      mad_chain_mod<P, 0>(A, m);
-      const uint32_t cx = ptx_addc(0, 0);
-      if (i > 0) {
-        (void)ptx_add_cc(c1, 0xFFFFFFFFu);  // flag := c1
-        mad_chain_mod_cin<P, 1>(S, m);
-      } else {
-        mad_chain_mod<P, 1>(S, m);
-      }
-      pend = A[1];
-#pragma unroll
-      for (int k = 0; k < N - 2; k++) A[k] = A[k + 2];
-      A[N - 2] = cx; A[N - 1] = 0;
-    }
-    uint32_t* A = (N & 1) ? Y : X;
-    uint32_t* S = (N & 1) ? X : Y;
-    Fe r;
-    r.v[0] = ptx_add_cc(A[0], pend);
-#pragma unroll
-    for (int k = 1; k < N; k++) r.v[k] = ptx_addc_cc(A[k], S[k - 1]);
-    uint32_t top = ptx_addc(S[N - 1], 0);
-    r.v[0] = ptx_add_cc(r.v[0], T[N]);
-#pragma unroll
-    for (int k = 1; k < N; k++) r.v[k] = ptx_addc_cc(r.v[k], T[N + k]);
-    top = ptx_addc(top, 0);
-    final_sub(r, top);
-    return r;
-  }
+  // (A dedicated Montgomery squaring with the symmetric products taken once -- 234 instead of 300 MACs for Fp -- was
+  // measured slower inside the bucket-accumulation kernel, 82.4 vs 78.7 ms at 2^24 G1 points, and removed in round 2:
+  // that kernel is bound by dependent-issue latency, not by multiplier throughput.)
 
   PS_DEV Fe to_mont() const { return fe_mul_call(*this, from_const<P::R2>()); }
   PS_DEV Fe from_mont() const { Fe o = zero(); o.v[0] = 1; return fe_mul_call(*this, o); }

@@ -31,11 +31,11 @@ void hc_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* o) { store_std(o,
 void hc_fr_add(const uint32_t* a, const uint32_t* b, uint32_t* o) { store_std(o, load_std<Fr>(a) + load_std<Fr>(b)); }
 void hc_fr_sub(const uint32_t* a, const uint32_t* b, uint32_t* o) { store_std(o, load_std<Fr>(a) - load_std<Fr>(b)); }
 void hc_fr_inv(const uint32_t* a, uint32_t* o) { store_std(o, fr_inv(load_std<Fr>(a))); }
-void hc_fp_sqr(const uint32_t* a, uint32_t* o) { store_std(o, load_std<Fp>(a).sqr_sos()); }
-void hc_fr_sqr(const uint32_t* a, uint32_t* o) { store_std(o, load_std<Fr>(a).sqr_sos()); }
+void hc_fp_sqr(const uint32_t* a, uint32_t* o) { store_std(o, load_std<Fp>(a).sqr()); }
+void hc_fr_sqr(const uint32_t* a, uint32_t* o) { store_std(o, load_std<Fr>(a).sqr()); }
 // raw Montgomery square on the given limbs (no domain conversion): a*a/R mod p, also for unreduced-looking inputs < p
-void hc_fp_montsqr_raw(const uint32_t* a, uint32_t* o) { Fp x; memcpy(x.v, a, 48); Fp r = x.sqr_sos(); memcpy(o, r.v, 48); }
-void hc_fr_montsqr_raw(const uint32_t* a, uint32_t* o) { Fr x; memcpy(x.v, a, 32); Fr r = x.sqr_sos(); memcpy(o, r.v, 32); }
+void hc_fp_montsqr_raw(const uint32_t* a, uint32_t* o) { Fp x; memcpy(x.v, a, 48); Fp r = x.sqr(); memcpy(o, r.v, 48); }
+void hc_fr_montsqr_raw(const uint32_t* a, uint32_t* o) { Fr x; memcpy(x.v, a, 32); Fr r = x.sqr(); memcpy(o, r.v, 32); }
 // raw Montgomery product on the given limbs (no domain conversion): a*b/R mod p
 void hc_fp_montmul_raw(const uint32_t* a, const uint32_t* b, uint32_t* o) { Fp x, y; memcpy(x.v, a, 48); memcpy(y.v, b, 48); Fp r = x * y; memcpy(o, r.v, 48); }
 void hc_fr_montmul_raw(const uint32_t* a, const uint32_t* b, uint32_t* o) { Fr x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fr r = x * y; memcpy(o, r.v, 32); }

@@ -80,9 +80,9 @@ def test_to_affine_serial_matches(host_check):
         assert list(out[:48]) == list(out[48:])
 
 
-def test_dedicated_squaring(host_check):
-    """Fe::sqr (symmetric products once + separate Montgomery reduction) against a*a mod p, on edge values
-    (carry-heavy limbs) and random ones, through the domain conversion and on raw limbs."""
+def test_squaring_edge_values(host_check):
+    """Fe::sqr against a*a mod p, on edge values (carry-heavy limbs) and random ones, through the domain conversion
+    and on raw limbs."""
     rng = random.Random(7)
     out12, out8 = (U32 * 12)(), (U32 * 8)()
     heavy_p = [O.P - 1, O.P - 2, (1 << 380) - 1, (1 << 381) - 1 - ((1 << 381) - 1 >= O.P) * (1 << 380), int("f" * 95, 16) % O.P,
