@@ -63,7 +63,11 @@ int ps_ctx_set_stream(ps_ctx* ctx, void* cuda_stream);
  * "msm_bucket_cost" = cost of one bucket (merge + reduction) in the automatic window choice, in field
  * products with a mixed addition counting 10 (default 70, fitted on B200);
  * "msm_scatter" = 0 (one-pass scatter of the counting sort) | 1 (two passes through a partitioned staging
- * array when the entry array exceeds L2) | 2 (two passes whenever the window count allows; tests) */
+ * array when the entry array exceeds L2) | 2 (two passes whenever the window count allows; tests);
+ * "msm_wave_floor" = 1 (short accumulate chunks: whole waves with the wave count rounded down, default) | 0 (rounded up);
+ * "interp_fused" = 1 (lowest nine levels of the interpolation tree in one shared-memory kernel, default) | 0 (level by
+ * level; identical coefficients).  Environment: PLAYSNARK_B200_STREAM2_PRIO=0 creates the secondary stream (G2 sums) at
+ * default instead of high priority (A/B runs). */
 int ps_ctx_set_option(ps_ctx* ctx, const char* name, int value);
 int ps_ctx_sync(ps_ctx* ctx);
 void ps_ctx_destroy(ps_ctx* ctx);
