@@ -423,6 +423,10 @@ int ps_mmsm(ps_mctx* m, const ps_mbases* b, const uint8_t* scalars_be, size_t n,
     const size_t lo = b->lo[d], cnt = b->lo[d + 1] - lo;
     uint32_t* d_err = nullptr;
     STAGE(msm_partial_host_scalars(ctx, b->part[d], scalars_be + 32 * lo, cnt, m->ws[d].rec, &d_err));
+    // the encoding flag lives in this call's arena: fetch it NOW, in stream order -- the combine below starts a new call
+    // on device 0, and a new call may merge (free) the arena blocks the flag sits in
+    uint32_t h = 0;
+    if (d_err) STAGE(dev_d2h(&h, d_err, 4, ctx->stream));
     STAGE(peer_copy(m, m->ws[0].recs + (size_t)d * pb, 0, m->ws[d].rec, d, pb));
     STAGE(ev_record(m, 4, d));
     m->bar.arrive();
@@ -430,14 +434,8 @@ int ps_mmsm(ps_mctx* m, const ps_mbases* b, const uint8_t* scalars_be, size_t n,
       for (int p = 1; p < m->ndev; p++) STAGE(ev_wait(m, 4, p, 0));
       STAGE(ps_msm_combine(ctx, b->group, m->ws[0].recs, (size_t)m->ndev, out));
     }
-    if (d_err && !m->failed.load()) {
-      uint32_t h = 0;
-      STAGE(dev_d2h(&h, d_err, 4, ctx->stream));
-      STAGE(dev_sync(ctx->stream));
-      if (h && my_rc == PS_OK) { my_rc = PS_ERR_ENCODING; m->failed.store(1); }
-    } else {
-      dev_sync(ctx->stream);
-    }
+    dev_sync(ctx->stream);
+    if (h && my_rc == PS_OK) { my_rc = PS_ERR_ENCODING; m->failed.store(1); }
     return my_rc;
   });
 }
