@@ -60,7 +60,25 @@ def _fr_bytes(vals):
         return vals.ptr
     if isinstance(vals, (bytes, bytearray, memoryview)):
         return bytes(vals)
+    if len(vals) >= 4096:
+        # long vectors of small values (matrix coefficients): one vectorised pass instead of a to_bytes per element
+        try:
+            import numpy as np
+            lo = np.array(vals, dtype=np.uint64)        # OverflowError on anything outside [0, 2^64)
+            rows = np.zeros((len(vals), 32), dtype=np.uint8)
+            rows[:, 24:] = lo.astype(">u8").view(np.uint8).reshape(-1, 8)
+            return rows.tobytes()
+        except (OverflowError, ImportError, TypeError, ValueError):
+            pass
     return b"".join((int(v) % R).to_bytes(32, "big") for v in vals)
+
+
+def _u32_array(vals):
+    """index vectors for the C ABI (array('I') converts a list in one C loop; ctypes' (*vals) unpacks it argument by argument)"""
+    import array
+    a = array.array("I", vals) if len(vals) else array.array("I", [0])
+    assert a.itemsize == 4
+    return a
 
 
 def _fr_list(buf: bytes) -> List[int]:
@@ -470,11 +488,10 @@ class SparseQAP:
             for rp, col, val in (self.left, self.right, self.out):
                 if len(rp) != self.nbGates + 1:
                     raise ValueError("row_ptr must have nbGates+1 entries")
-                a_rp = (C.c_uint32 * len(rp))(*rp)
-                a_col = (C.c_uint32 * max(1, len(col)))(*col)
+                a_rp, a_col = _u32_array(rp), _u32_array(col)
                 b_val = _fr_bytes(val) or b"\0"
                 keep += [a_rp, a_col, b_val]
-                args += [C.cast(a_rp, C.c_void_p), C.cast(a_col, C.c_void_p), C.cast(C.c_char_p(b_val), C.c_void_p)]
+                args += [C.c_void_p(a_rp.buffer_info()[0]), C.c_void_p(a_col.buffer_info()[0]), C.cast(C.c_char_p(b_val), C.c_void_p)]
             load = backend.lib.ps_mqap_load_r1cs if backend.multi else backend.lib.ps_qap_load_r1cs
             backend._check(load(backend.ctx, self.nbGates, self.nbVars, self.nbIO, *args, C.byref(h)))
             return h

@@ -8,7 +8,10 @@
 #include "multi_api.cuh"
 #include "setup.cuh"
 
+#include <algorithm>
+#include <cstdlib>
 #include <new>
+#include <vector>
 
 using namespace ps;
 
@@ -374,6 +377,7 @@ int ps_qap_load_r1cs(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, co
   while (((size_t)1 << k) < n_gates) k++;
   const size_t np = (size_t)1 << k;   // leaves of the interpolation tree; gates n..np-1 are empty rows
   sq->np = (uint32_t)np;
+  if (const char* e = getenv("PLAYSNARK_B200_SPMVT_SEG")) { long v = atol(e); if (v >= 1) sq->seg_len = (uint32_t)v; }   // tests: short segments
   const uint32_t* rps[3] = {l_row_ptr, r_row_ptr, o_row_ptr};
   const uint32_t* cols[3] = {l_col, r_col, o_col};
   const uint8_t* vals[3] = {l_val, r_val, o_val};
@@ -426,6 +430,26 @@ int ps_qap_load_r1cs(ps_ctx* ctx, size_t n_gates, size_t n_vars, size_t n_io, co
     if (rc == PS_OK && nnz) rc = dev_h2d(mt.col, gate.data(), nnz * 4, st);
     if (rc == PS_OK && nnz) rc = dev_h2d(d_src, src.data(), nnz * 4, st);
     if (rc == PS_OK) rc = ps_launch<FrGatherK>(st, nnz, (const Fr*)sq->mat[i].val, (const uint32_t*)d_src, mt.val);
+    // long rows of the transpose, cut into segments (setup.cuh: SpmvTSegK / SpmvTLongSumK)
+    std::vector<uint32_t> seg_lo, seg_hi, lrow, seg_ptr(1, 0);
+    for (size_t v = 0; v < n_vars; v++) {
+      if (cp[v + 1] - cp[v] <= sq->seg_len) continue;
+      for (uint32_t lo = cp[v]; lo < cp[v + 1]; lo += sq->seg_len) { seg_lo.push_back(lo); seg_hi.push_back(std::min(cp[v + 1], lo + sq->seg_len)); }
+      lrow.push_back((uint32_t)v);
+      seg_ptr.push_back((uint32_t)seg_lo.size());
+    }
+    LongRows& lr = sq->longT[i];
+    lr.nseg = (uint32_t)seg_lo.size(); lr.nrow = (uint32_t)lrow.size();
+    if (lr.nrow) {
+      if (rc == PS_OK) rc = dev_alloc((void**)&lr.seg_lo, lr.nseg * 4);
+      if (rc == PS_OK) rc = dev_alloc((void**)&lr.seg_hi, lr.nseg * 4);
+      if (rc == PS_OK) rc = dev_alloc((void**)&lr.row, lr.nrow * 4);
+      if (rc == PS_OK) rc = dev_alloc((void**)&lr.seg_ptr, (lr.nrow + 1) * 4);
+      if (rc == PS_OK) rc = dev_h2d(lr.seg_lo, seg_lo.data(), lr.nseg * 4, st);
+      if (rc == PS_OK) rc = dev_h2d(lr.seg_hi, seg_hi.data(), lr.nseg * 4, st);
+      if (rc == PS_OK) rc = dev_h2d(lr.row, lrow.data(), lr.nrow * 4, st);
+      if (rc == PS_OK) rc = dev_h2d(lr.seg_ptr, seg_ptr.data(), (lr.nrow + 1) * 4, st);
+    }
     if (rc == PS_OK) rc = dev_sync(st);   // the host vectors go out of scope
   }
   Fr* d_z = ctx->arena.take<Fr>(n_gates + 1);

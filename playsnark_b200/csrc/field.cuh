@@ -235,6 +235,100 @@ struct alignas(16) Fe {
   }
 };
 
+// ---- unreduced products (lazy reduction in Fp2, curve.cuh) ----------------------------------------------------
+// acc[0..N) += sum over k of MOD[OFF+2k] * b * 2^(64k), consuming the pending carry flag at limb 0
+template <class P, int OFF>
+PS_DEV void madc_chain_mod(uint32_t* acc, uint32_t b) {
+  constexpr int N = P::N;
+#pragma unroll
+  for (int j = 0; j < N; j += 2) ptx_madc_wide_cc(acc[j], acc[j + 1], P::MOD(OFF + j), b);
+}
+
+// T[0..2N) = a * b as plain integers (no reduction).  Two accumulators as in the Montgomery product: E takes the
+// 64-bit partial products that start at even limb positions, O those that start at odd positions; every row is two
+// independent carry chains of N/2 wide multiply-adds, whose carry out lands in a limb no chain has covered yet.
+template <class P>
+PS_DEV void mul_wide(uint32_t* T, const Fe<P>& a, const Fe<P>& b) {
+  constexpr int N = P::N;
+  uint32_t E[2 * N + 2], O[2 * N + 2];
+#pragma unroll
+  for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
+  mul_chain<N>(E, a.v, b.v[0]);
+  mul_chain<N>(O + 1, a.v + 1, b.v[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    const uint32_t bi = b.v[i];
+    uint32_t* ge = (i & 1) ? O : E;   // grid of the products of the even limbs of a: they start at position i + 2k
+    uint32_t* go = (i & 1) ? E : O;   // grid of the products of the odd limbs: position i + 1 + 2k
+    mad_chain<N, false>(ge + i, a.v, bi);
+    ge[i + N] = ptx_addc(ge[i + N], 0);
+    mad_chain<N, false>(go + i + 1, a.v + 1, bi);
+    go[i + 1 + N] = ptx_addc(go[i + 1 + N], 0);
+  }
+  T[0] = E[0];
+  T[1] = ptx_add_cc(E[1], O[1]);
+#pragma unroll
+  for (int k = 2; k < 2 * N - 1; k++) T[k] = ptx_addc_cc(E[k], O[k]);
+  T[2 * N - 1] = ptx_addc(E[2 * N - 1], O[2 * N - 1]);
+}
+
+// T / R mod p for T < p R (2N limbs): Montgomery-reduce the low half with the row loop of the product (its
+// multiplication rows left out), add the high half, one conditional subtraction.
+template <class P>
+PS_DEV Fe<P> redc_wide(const uint32_t* T) {
+  constexpr int N = P::N;
+  uint32_t X[N], Y[N];
+  uint32_t pend;
+#pragma unroll
+  for (int k = 0; k < N; k++) { X[k] = T[k]; Y[k] = 0; }
+  {
+    const uint32_t m = X[0] * P::INV;
+    mad_chain_mod<P, 0>(X, m);
+    uint32_t cx = ptx_addc(0, 0);
+    mad_chain_mod<P, 1>(Y, m);
+    pend = X[1];
+#pragma unroll
+    for (int k = 0; k < N - 2; k++) X[k] = X[k + 2];
+    X[N - 2] = cx; X[N - 1] = 0;
+  }
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    uint32_t* A = (i & 1) ? Y : X;  // aligned
+    uint32_t* S = (i & 1) ? X : Y;  // shifted by one limb
+    const uint32_t m = (A[0] + pend) * P::INV;
+    A[0] = ptx_add_cc(A[0], pend);   // carry -> weight 2^32 == S[0]
+    madc_chain_mod<P, 1>(S, m);      // consumes it
+    mad_chain_mod<P, 0>(A, m);
+    uint32_t cx = ptx_addc(0, 0);
+    pend = A[1];
+#pragma unroll
+    for (int k = 0; k < N - 2; k++) A[k] = A[k + 2];
+    A[N - 2] = cx; A[N - 1] = 0;
+  }
+  uint32_t* A = (N & 1) ? Y : X;
+  uint32_t* S = (N & 1) ? X : Y;
+  Fe<P> r;
+  r.v[0] = ptx_add_cc(A[0], pend);
+#pragma unroll
+  for (int k = 1; k < N; k++) r.v[k] = ptx_addc_cc(A[k], S[k - 1]);
+  uint32_t top = ptx_addc(S[N - 1], 0);   // zero: the reduced low half is at most p
+  r.v[0] = ptx_add_cc(r.v[0], T[N]);
+#pragma unroll
+  for (int k = 1; k < N; k++) r.v[k] = ptx_addc_cc(r.v[k], T[N + k]);
+  top = ptx_addc(top, 0);
+  Fe<P>::final_sub(r, top);
+  return r;
+}
+
+// a - b over n limbs, in place; returns the borrow (0 or 0xffffffff)
+template <int n>
+PS_DEV uint32_t sub_limbs(uint32_t* a, const uint32_t* b) {
+  a[0] = ptx_sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int k = 1; k < n; k++) a[k] = ptx_subc_cc(a[k], b[k]);
+  return ptx_subc(0, 0);
+}
+
 using Fp = Fe<FpParams>;
 using Fr = Fe<FrParams>;
 

@@ -33,9 +33,22 @@ struct CsrDev {
   size_t nnz = 0;
 };
 
+// Variables that occur in more than seg_len gates (the constant 1, a public input wired everywhere): their sums in the
+// transposed SpMV are cut into segments of seg_len entries -- a thread per segment, then a thread per variable over
+// its partial sums -- instead of one thread walking 2^20 entries (0.53 s at 2^20 gates, a third of the device setup).
+struct LongRows {
+  uint32_t* seg_lo = nullptr;   // nseg: first entry of the segment in matT.col / matT.val
+  uint32_t* seg_hi = nullptr;   // nseg: one past its last entry
+  uint32_t* row = nullptr;      // nrow: the variable
+  uint32_t* seg_ptr = nullptr;  // nrow + 1: its segments
+  uint32_t nseg = 0, nrow = 0;
+};
+
 struct SparseQap {
   CsrDev mat[3];                 // left, right, out
   CsrDev matT[3];                // their transposes (row_ptr over the variables, col = gate): the trusted setups sum over gates
+  LongRows longT[3];             // the long rows of the transposes
+  uint32_t seg_len = 512;
   Fr* inv_zprime = nullptr;      // 1 / z'(j), j = 1..n
   std::vector<Fr*> ztree;        // level l: NTT_{2s} of every node's Z (s = 2^l), n/s nodes x 2s
   Fr* twist = nullptr;           // level l at offset 2s - 2 (s = 2^l): (1/2s) * omega_{4s}^t, t < 2s; l < k - 1
@@ -45,6 +58,7 @@ struct SparseQap {
   void release() {
     for (auto& m : mat) { dev_free(m.row_ptr); dev_free(m.col); dev_free(m.val); }
     for (auto& m : matT) { dev_free(m.row_ptr); dev_free(m.col); dev_free(m.val); }
+    for (auto& l : longT) { dev_free(l.seg_lo); dev_free(l.seg_hi); dev_free(l.row); dev_free(l.seg_ptr); }
     dev_free(inv_zprime); dev_free(s_hat); dev_free(z_hat); dev_free(twist);
     for (auto* p : ztree) dev_free(p);
     ztree.clear();

@@ -49,17 +49,38 @@ struct FrScaleByK {
   PS_DEV static void run(uint32_t j, const Fr* s, Fr* a) { a[j] = a[j] * s[0]; }
 };
 // ev[mat][i] = sum_k valT[k] * lag[gateT[k]] over the entries of variable i              (thread = mat * m + i)
+// Variables with more than seg_len entries are left to SpmvTSegK / SpmvTLongSumK.
 struct SpmvTK {
   static constexpr int BLOCK = 128;
-  PS_DEV static void run(uint32_t tid, uint32_t m, const uint32_t* rp0, const uint32_t* g0, const Fr* v0, const uint32_t* rp1,
+  PS_DEV static void run(uint32_t tid, uint32_t m, uint32_t seg_len, const uint32_t* rp0, const uint32_t* g0, const Fr* v0, const uint32_t* rp1,
                          const uint32_t* g1, const Fr* v1, const uint32_t* rp2, const uint32_t* g2, const Fr* v2, const Fr* lag, Fr* ev) {
     uint32_t mat = tid / m, i = tid % m;
     const uint32_t* rp = mat == 0 ? rp0 : (mat == 1 ? rp1 : rp2);
     const uint32_t* gate = mat == 0 ? g0 : (mat == 1 ? g1 : g2);
     const Fr* val = mat == 0 ? v0 : (mat == 1 ? v1 : v2);
+    if (rp[i + 1] - rp[i] > seg_len) return;
     Fr acc = Fr::zero();
     for (uint32_t k = rp[i]; k < rp[i + 1]; k++) acc = acc + val[k] * lag[gate[k]];
     ev[tid] = acc;
+  }
+};
+// partial[s] = sum_k valT[k] * lag[gateT[k]] over segment s of a long row                       (thread per segment)
+struct SpmvTSegK {
+  static constexpr int BLOCK = 128;
+  PS_DEV static void run(uint32_t s, const uint32_t* seg_lo, const uint32_t* seg_hi, const uint32_t* gate, const Fr* val, const Fr* lag,
+                         Fr* partial) {
+    Fr acc = Fr::zero();
+    for (uint32_t k = seg_lo[s]; k < seg_hi[s]; k++) acc = acc + val[k] * lag[gate[k]];
+    partial[s] = acc;
+  }
+};
+// ev[row[r]] = sum of the partial sums of long row r                                            (thread per long row)
+struct SpmvTLongSumK {
+  static constexpr int BLOCK = 32;
+  PS_DEV static void run(uint32_t r, const uint32_t* row, const uint32_t* seg_ptr, const Fr* partial, Fr* ev) {
+    Fr acc = Fr::zero();
+    for (uint32_t s = seg_ptr[r]; s < seg_ptr[r + 1]; s++) acc = acc + partial[s];
+    ev[row[r]] = acc;
   }
 };
 // ev[mat][i] = polynomial i of matrix `mat` at x (dense QAP: m x n coefficients, low degree first)   (thread = mat * m + i)
@@ -114,9 +135,18 @@ inline int qap_eval_all_at(ps_ctx* ctx, const ps_qap* q, const Fr& x, Fr* ev, Fr
   if (!lag) return PS_ERR_ALLOC;
   PS_LAUNCH(LagrangeDenK, st, n, x, (const Fr*)sq->inv_zprime, lag);
   PS_LAUNCH(FrScaleByK, st, n, (const Fr*)zx, lag);
-  PS_LAUNCH(SpmvTK, st, (size_t)3 * m, m, (const uint32_t*)sq->matT[0].row_ptr, (const uint32_t*)sq->matT[0].col, (const Fr*)sq->matT[0].val,
+  PS_LAUNCH(SpmvTK, st, (size_t)3 * m, m, sq->seg_len, (const uint32_t*)sq->matT[0].row_ptr, (const uint32_t*)sq->matT[0].col, (const Fr*)sq->matT[0].val,
             (const uint32_t*)sq->matT[1].row_ptr, (const uint32_t*)sq->matT[1].col, (const Fr*)sq->matT[1].val,
             (const uint32_t*)sq->matT[2].row_ptr, (const uint32_t*)sq->matT[2].col, (const Fr*)sq->matT[2].val, (const Fr*)lag, ev);
+  for (int i = 0; i < 3; i++) {
+    const LongRows& lr = sq->longT[i];
+    if (!lr.nrow) continue;
+    Fr* partial_sums = ctx->arena.take<Fr>(lr.nseg);
+    if (!partial_sums) return PS_ERR_ALLOC;
+    PS_LAUNCH(SpmvTSegK, st, lr.nseg, (const uint32_t*)lr.seg_lo, (const uint32_t*)lr.seg_hi, (const uint32_t*)sq->matT[i].col,
+              (const Fr*)sq->matT[i].val, (const Fr*)lag, partial_sums);
+    PS_LAUNCH(SpmvTLongSumK, st, lr.nrow, (const uint32_t*)lr.row, (const uint32_t*)lr.seg_ptr, (const Fr*)partial_sums, ev + (size_t)i * m);
+  }
   return PS_OK;
 }
 

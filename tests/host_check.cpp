@@ -41,6 +41,10 @@ void hc_fp_montmul_raw(const uint32_t* a, const uint32_t* b, uint32_t* o) { Fp x
 void hc_fr_montmul_raw(const uint32_t* a, const uint32_t* b, uint32_t* o) { Fr x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fr r = x * y; memcpy(o, r.v, 32); }
 void hc_fp2_mul(const uint32_t* a, const uint32_t* b, uint32_t* o) { store2(o, load2(a) * load2(b)); }
 void hc_fp2_sqr(const uint32_t* a, uint32_t* o) { store2(o, load2(a).sqr()); }
+// the lazy-reduction product (3 wide multiplications, 2 Montgomery reductions) and its two halves on raw limbs
+void hc_fp2_mul_lazy(const uint32_t* a, const uint32_t* b, uint32_t* o) { store2(o, Fp2::mul_lazy(load2(a), load2(b))); }
+void hc_fp_mul_wide_raw(const uint32_t* a, const uint32_t* b, uint32_t* o) { Fp x, y; memcpy(x.v, a, 48); memcpy(y.v, b, 48); mul_wide(o, x, y); }
+void hc_fp_redc_wide_raw(const uint32_t* t, uint32_t* o) { Fp r = redc_wide<FpParams>(t); memcpy(o, r.v, 48); }
 void hc_fp2_inv(const uint32_t* a, uint32_t* o) { store2(o, fp2_inv(load2(a))); }
 
 // out = pre*P (pre in {1,2,3}: makes the accumulator non-trivially projective) + Q via madd

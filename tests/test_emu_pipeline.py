@@ -87,6 +87,12 @@ def test_sparse_phgr13_exponent_check(be): P.phgr13_sparse_exponent_check(be, 4,
 def test_device_setups_vs_oracle(be, n): P.device_setups_vs_oracle(be, n, seed=n)
 
 
+def test_device_setups_long_rows(be, monkeypatch):
+    """variables that occur in many gates: their transposed-SpMV sums are cut into segments (here of 2 entries)"""
+    monkeypatch.setenv("PLAYSNARK_B200_SPMVT_SEG", "2")
+    P.device_setups_vs_oracle(be, 8, seed=31)
+
+
 @pytest.mark.parametrize("parts,world", [(1, 2), (2, 3), (4, 5)])
 def test_sharded_steps_recombine(be, parts, world): P.sharded_steps_recombine(be, 4, parts, world, seed=21 + parts)
 

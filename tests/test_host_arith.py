@@ -135,6 +135,39 @@ def test_fp2_ops(host_check):
             host_check.hc_fp2_inv(f2l(a), out); assert O.F2.mul(unf2(out), a) == (1, 0)
 
 
+def test_fp2_lazy_reduction(host_check):
+    """Fp2 product with unreduced Karatsuba terms (curve.cuh mul_lazy) = the plain product, bit for bit; its two
+    building blocks on raw limbs: the full 768-bit product (operands up to 2^384 - 1, not only field elements) and the
+    Montgomery reduction of any T < p R."""
+    rng = random.Random(5)
+    P = O.P
+    edge = [(0, 0), (1, 0), (0, 1), (P - 1, P - 1), (P - 1, 0), (0, P - 1), (1, P - 1), (P - 1, 1), ((P - 1) // 2, (P + 1) // 2)]
+    vals = edge + [(rng.randrange(P), rng.randrange(P)) for _ in range(25)]
+    out, ref = (U32 * 24)(), (U32 * 24)()
+    for a in vals:
+        for b in vals:
+            host_check.hc_fp2_mul_lazy(f2l(a), f2l(b), out)
+            assert unf2(out) == O.F2.mul(a, b)
+            host_check.hc_fp2_mul(f2l(a), f2l(b), ref)
+            assert list(out) == list(ref)
+    wide = (U32 * 24)()
+    full = (1 << 384) - 1
+    ints = [0, 1, full, full - 1, 1 << 383, 2 * P - 2, P, 0xFFFFFFFF, (1 << 352) - 1] + [rng.randrange(1 << 384) for _ in range(30)]
+    for x in ints:
+        for y in ints:
+            host_check.hc_fp_mul_wide_raw(limbs(x, 12), limbs(y, 12), wide)
+            assert unl(wide) == x * y
+    rinv = pow(1 << 384, -1, P)
+    red = (U32 * 12)()
+    ts = [0, 1, P, (1 << 384) - 1, 1 << 384, P << 384, (P << 384) - 1, (P - 1) << 384, ((P - 1) << 384) | ((1 << 384) - 1), 2 * P * P - 1]
+    ts += [rng.randrange(P << 384) for _ in range(300)]
+    for t in ts:
+        if t >= P << 384:
+            continue
+        host_check.hc_fp_redc_wide_raw(limbs(t, 24), red)
+        assert unl(red) == t * rinv % P, hex(t)
+
+
 def g1l(p):
     return limbs(0 if p is None else p[0] | (p[1] << 384), 24)
 
