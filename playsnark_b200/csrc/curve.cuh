@@ -29,7 +29,9 @@ struct alignas(16) Fp2T {
   PS_DEV Fp2T neg() const { return Fp2T{c0.neg(), c1.neg()}; }
   PS_DEV Fp2T dbl() const { return Fp2T{c0.dbl(), c1.dbl()}; }
   // Karatsuba on UNREDUCED products: 3 wide multiplications and 2 Montgomery reductions (720 instead of 864
-  // multiply-adds); results identical to operator*.  a0 + a1 and b0 + b1 stay below 2p < 2^382 unreduced, the three
+  // multiply-adds); results identical to operator*.  NOT used by default: inside the G2 bucket accumulation (255
+  // registers already) it measured 21.87 ms against 19.83 ms at 2^20 points, and the schoolbook form below 21.29 ms
+  // (tools/ab_fp2.py, round 2); kept behind -DPS_FP2_LAZY[=2] with its host tests.  a0 + a1 and b0 + b1 stay below 2p < 2^382 unreduced, the three
   // products below 4 p^2 < 2^768, a0 b1 + a1 b0 < 2 p^2 < p R, and a0 b0 - a1 b1 gets p R added when it is negative.
   PS_DEV static Fp2T mul_lazy(const Fp2T& a, const Fp2T& b) {
     constexpr int N = Fp::N;
@@ -58,7 +60,11 @@ struct alignas(16) Fp2T {
   }
   // Karatsuba: 3 base-field products
   PS_DEV friend Fp2T operator*(const Fp2T& a, const Fp2T& b) {
-#ifdef PS_FP2_LAZY
+#if defined(PS_FP2_LAZY) && PS_FP2_LAZY == 2
+    // schoolbook on unreduced products: c0 = a0 b0 + (p - a1) b1, c1 = a0 b1 + a1 b0, one reduction each (the same 864
+    // multiply-adds as three Montgomery products, a third fewer reduction rows, no wide temporaries)
+    if (INLINE) return Fp2T{mul2_lazy(a.c0, b.c0, neg_lazy(a.c1), b.c1), mul2_lazy(a.c0, b.c1, a.c1, b.c0)};
+#elif defined(PS_FP2_LAZY)
     if (INLINE) return mul_lazy(a, b);
 #endif
     Fp t0 = mulp(a.c0, b.c0);
@@ -122,6 +128,33 @@ struct alignas(16) XYZZ {
   PS_DEV XYZZ neg() const { return XYZZ{x, y.neg(), zz, zzz}; }
 };
 
+// a b - c d, the shape of Y3 in every addition / doubling formula below.  The base field computes it as
+// (a b + (p - c) d) / R with ONE Montgomery reduction (432 instead of 576 multiply-adds; same value bit for bit):
+// measured on B200 inside the G1 bucket accumulation, 2^24 points: 78.98 -> 75.86 ms (tools/ab_fp2.py, round 2).
+// -DPS_NO_LAZY_Y3 restores the two separate products (A/B builds).  Fp2 keeps separate products: unreduced Fp2
+// products were measured SLOWER in the G2 kernel (Fp2T::mul_lazy below).
+PS_DEV Fp mul_sub_pair(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+#ifndef PS_NO_LAZY_Y3
+  return mul2_lazy(a, b, neg_lazy(c), d);
+#else
+  return a * b - c * d;
+#endif
+}
+// Fp2: Karatsuba on the three DIFFERENCES a0 b0 - c0 d0, a1 b1 - c1 d1, (a0 + a1)(b0 + b1) - (c0 + c1)(d0 + d1), each one
+// reduction (3 instead of 6 reductions for the two Fp2 products); only in the inlined G2 accumulation kernel.
+template <bool I>
+PS_DEV Fp2T<I> mul_sub_pair(const Fp2T<I>& a, const Fp2T<I>& b, const Fp2T<I>& c, const Fp2T<I>& d) {
+#ifdef PS_FP2_LAZY_Y3
+  if (I) {
+    Fp A = mul2_lazy(a.c0, b.c0, neg_lazy(c.c0), d.c0);
+    Fp B = mul2_lazy(a.c1, b.c1, neg_lazy(c.c1), d.c1);
+    Fp K = mul2_lazy(a.c0 + a.c1, b.c0 + b.c1, neg_lazy(c.c0 + c.c1), d.c0 + d.c1);
+    return Fp2T<I>{A - B, K - A - B};
+  }
+#endif
+  return a * b - c * d;
+}
+
 // 2*P for affine P (mdbl-2008-s-1, a = 0)
 template <class F>
 PS_DEV XYZZ<F> xyzz_dbl_affine(const Affine<F>& p) {
@@ -133,7 +166,7 @@ PS_DEV XYZZ<F> xyzz_dbl_affine(const Affine<F>& p) {
   F X2 = p.x.sqr();
   F M = X2.dbl() + X2;
   F X3 = M.sqr() - S.dbl();
-  F Y3 = M * (S - X3) - W * p.y;
+  F Y3 = mul_sub_pair(M, S - X3, W, p.y);
   return XYZZ<F>{X3, Y3, V, W};
 }
 
@@ -148,7 +181,7 @@ PS_DEV XYZZ<F> xyzz_dbl(const XYZZ<F>& p) {
   F X2 = p.x.sqr();
   F M = X2.dbl() + X2;
   F X3 = M.sqr() - S.dbl();
-  F Y3 = M * (S - X3) - W * p.y;
+  F Y3 = mul_sub_pair(M, S - X3, W, p.y);
   return XYZZ<F>{X3, Y3, V * p.zz, W * p.zzz};
 }
 
@@ -174,7 +207,7 @@ PS_DEV void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q) {
   F PPP = Pd * PP;
   F Q = acc.x * PP;
   F X3 = Rd.sqr() - PPP - Q.dbl();
-  F Y3 = Rd * (Q - X3) - acc.y * PPP;
+  F Y3 = mul_sub_pair(Rd, Q - X3, acc.y, PPP);
   acc.x = X3;
   acc.y = Y3;
   acc.zz = acc.zz * PP;
@@ -200,7 +233,7 @@ PS_DEV void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
   F PPP = Pd * PP;
   F Q = U1 * PP;
   F X3 = Rd.sqr() - PPP - Q.dbl();
-  F Y3 = Rd * (Q - X3) - S1 * PPP;
+  F Y3 = mul_sub_pair(Rd, Q - X3, S1, PPP);
   acc.x = X3;
   acc.y = Y3;
   acc.zz = acc.zz * q.zz * PP;

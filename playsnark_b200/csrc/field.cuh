@@ -89,6 +89,7 @@ PS_DEV void mad_chain_mod(uint32_t* acc, uint32_t b) {
 // ---- field element ----------------------------------------------------------------------------
 template <class P> struct Fe;
 template <class P> PS_NOINLINE Fe<P> fe_mul_call(const Fe<P>& a, const Fe<P>& b);
+template <class P> PS_DEV Fe<P> fe_sqr_wide(const Fe<P>& a);
 
 template <class P>
 struct alignas(16) Fe {
@@ -208,7 +209,12 @@ struct alignas(16) Fe {
     final_sub(r, top);
     return r;
   }
-  PS_DEV Fe sqr() const { return (*this) * (*this); }
+  PS_DEV Fe sqr() const {
+#ifdef PS_WIDE_SQR
+    if (N == 12) return fe_sqr_wide(*this);   // unreduced square with the symmetric products taken once + one reduction
+#endif
+    return (*this) * (*this);
+  }
 
   // (A dedicated Montgomery squaring with the symmetric products taken once -- 234 instead of 300 MACs for Fp -- was
   // measured slower inside the bucket-accumulation kernel, 82.4 vs 78.7 ms at 2^24 G1 points, and removed in round 2:
@@ -244,19 +250,22 @@ PS_DEV void madc_chain_mod(uint32_t* acc, uint32_t b) {
   for (int j = 0; j < N; j += 2) ptx_madc_wide_cc(acc[j], acc[j + 1], P::MOD(OFF + j), b);
 }
 
-// T[0..2N) = a * b as plain integers (no reduction).  Two accumulators as in the Montgomery product: E takes the
+// Unreduced products a * b as plain integers of 2N limbs.  Two accumulators as in the Montgomery product: E takes the
 // 64-bit partial products that start at even limb positions, O those that start at odd positions; every row is two
-// independent carry chains of N/2 wide multiply-adds, whose carry out lands in a limb no chain has covered yet.
-template <class P>
-PS_DEV void mul_wide(uint32_t* T, const Fe<P>& a, const Fe<P>& b) {
+// independent carry chains of N/2 wide multiply-adds, whose carry out lands in a limb no chain of that accumulator has
+// covered yet.  wide_rows<FIRST = true> initialises (E, O) with a * b, FIRST = false adds another product to them
+// (sums of products below 2^(64N) in total); wide_merge adds the two accumulators up.
+template <class P, bool FIRST>
+PS_DEV void wide_rows(uint32_t* E, uint32_t* O, const Fe<P>& a, const Fe<P>& b) {
   constexpr int N = P::N;
-  uint32_t E[2 * N + 2], O[2 * N + 2];
+  if (FIRST) {
 #pragma unroll
-  for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
-  mul_chain<N>(E, a.v, b.v[0]);
-  mul_chain<N>(O + 1, a.v + 1, b.v[0]);
+    for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
+    mul_chain<N>(E, a.v, b.v[0]);
+    mul_chain<N>(O + 1, a.v + 1, b.v[0]);
+  }
 #pragma unroll
-  for (int i = 1; i < N; i++) {
+  for (int i = FIRST ? 1 : 0; i < N; i++) {
     const uint32_t bi = b.v[i];
     uint32_t* ge = (i & 1) ? O : E;   // grid of the products of the even limbs of a: they start at position i + 2k
     uint32_t* go = (i & 1) ? E : O;   // grid of the products of the odd limbs: position i + 1 + 2k
@@ -265,11 +274,81 @@ PS_DEV void mul_wide(uint32_t* T, const Fe<P>& a, const Fe<P>& b) {
     mad_chain<N, false>(go + i + 1, a.v + 1, bi);
     go[i + 1 + N] = ptx_addc(go[i + 1 + N], 0);
   }
+}
+template <int N>
+PS_DEV void wide_merge(uint32_t* T, const uint32_t* E, const uint32_t* O) {
   T[0] = E[0];
   T[1] = ptx_add_cc(E[1], O[1]);
 #pragma unroll
   for (int k = 2; k < 2 * N - 1; k++) T[k] = ptx_addc_cc(E[k], O[k]);
   T[2 * N - 1] = ptx_addc(E[2 * N - 1], O[2 * N - 1]);
+}
+template <class P>
+PS_DEV void mul_wide(uint32_t* T, const Fe<P>& a, const Fe<P>& b) {
+  constexpr int N = P::N;
+  uint32_t E[2 * N + 2], O[2 * N + 2];
+  wide_rows<P, true>(E, O, a, b);
+  wide_merge<N>(T, E, O);
+}
+// (a b + c d) / R mod p with ONE reduction; a b + c d < p R (e.g. all four below p, or p itself among them)
+template <class P>
+PS_DEV Fe<P> redc_wide(const uint32_t* T);
+template <class P>
+PS_DEV Fe<P> mul2_lazy(const Fe<P>& a, const Fe<P>& b, const Fe<P>& c, const Fe<P>& d) {
+  constexpr int N = P::N;
+  uint32_t E[2 * N + 2], O[2 * N + 2], T[2 * N];
+  wide_rows<P, true>(E, O, a, b);
+  wide_rows<P, false>(E, O, c, d);
+  wide_merge<N>(T, E, O);
+  return redc_wide<P>(T);
+}
+// T[0..2N) = a * a: the products a_i a_j, i < j, taken once (N (N - 1) / 2 wide multiply-adds in the same two
+// accumulators as wide_rows: row i is one chain over j = i + 1, i + 3, ... and one over j = i + 2, i + 4, ...),
+// doubled with funnel shifts while the N squares a_i^2 -- disjoint limb pairs, no carries -- are added.
+template <class P>
+PS_DEV void sqr_wide(uint32_t* T, const Fe<P>& a) {
+  constexpr int N = P::N;
+  uint32_t E[2 * N + 2], O[2 * N + 2];
+#pragma unroll
+  for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < N - 1; i++) {
+    const uint32_t bi = a.v[i];
+    {  // j = i + 1, i + 3, ...: positions 2i + 1, 2i + 3, ... (odd grid)
+      int pos = 2 * i + 1;
+      ptx_mad_wide_cc(O[pos], O[pos + 1], a.v[i + 1], bi);
+#pragma unroll
+      for (int j = i + 3; j < N; j += 2) { pos += 2; ptx_madc_wide_cc(O[pos], O[pos + 1], a.v[j], bi); }
+      O[pos + 2] = ptx_addc(O[pos + 2], 0);
+    }
+    if (i + 2 < N) {  // j = i + 2, i + 4, ...: positions 2i + 2, 2i + 4, ... (even grid)
+      int pos = 2 * i + 2;
+      ptx_mad_wide_cc(E[pos], E[pos + 1], a.v[i + 2], bi);
+#pragma unroll
+      for (int j = i + 4; j < N; j += 2) { pos += 2; ptx_madc_wide_cc(E[pos], E[pos + 1], a.v[j], bi); }
+      E[pos + 2] = ptx_addc(E[pos + 2], 0);
+    }
+  }
+  uint32_t Cx[2 * N], D[2 * N];
+  wide_merge<N>(Cx, E, O);
+#pragma unroll
+  for (int i = 0; i < N; i++) ptx_mul_wide(D[2 * i], D[2 * i + 1], a.v[i], a.v[i]);
+  T[0] = ptx_add_cc(Cx[0] << 1, D[0]);
+#pragma unroll
+  for (int k = 1; k < 2 * N - 1; k++) T[k] = ptx_addc_cc((Cx[k] << 1) | (Cx[k - 1] >> 31), D[k]);
+  T[2 * N - 1] = ptx_addc((Cx[2 * N - 1] << 1) | (Cx[2 * N - 2] >> 31), D[2 * N - 1]);
+}
+
+// p - a as a plain integer (a <= p): the additive inverse for use as an operand of an unreduced product (0 -> p)
+template <class P>
+PS_DEV Fe<P> neg_lazy(const Fe<P>& a) {
+  constexpr int N = P::N;
+  Fe<P> r;
+  r.v[0] = ptx_sub_cc(P::MOD(0), a.v[0]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) r.v[k] = ptx_subc_cc(P::MOD(k), a.v[k]);
+  r.v[N - 1] = ptx_subc(P::MOD(N - 1), a.v[N - 1]);
+  return r;
 }
 
 // T / R mod p for T < p R (2N limbs): Montgomery-reduce the low half with the row loop of the product (its
@@ -318,6 +397,13 @@ PS_DEV Fe<P> redc_wide(const uint32_t* T) {
   top = ptx_addc(top, 0);
   Fe<P>::final_sub(r, top);
   return r;
+}
+
+template <class P>
+PS_DEV Fe<P> fe_sqr_wide(const Fe<P>& a) {
+  uint32_t T[2 * P::N];
+  sqr_wide(T, a);
+  return redc_wide<P>(T);
 }
 
 // a - b over n limbs, in place; returns the borrow (0 or 0xffffffff)

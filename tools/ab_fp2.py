@@ -1,9 +1,15 @@
 #!/usr/bin/env python3
-"""A/B of the Fp2 product inside the G2 bucket-accumulation kernel on one B200: Karatsuba with three Montgomery products
-(product library) against Karatsuba on unreduced products with two reductions (variants/lib_fp2lazy.so, accum_g2.cu built
-with -DPS_FP2_LAZY).  G2 MSMs at 2^18 and 2^20 points with all window tables, every result checked against
-(sum k_i s_i mod r) * G2 from the oracle.  Each library runs in its own process (PLAYSNARK_B200_LIB).
-    python -c "from playsnark_b200 import build as B; B.build_variant('fp2lazy', ['-DPS_FP2_LAZY'], tus=('accum_g2.cu',))"   # here
+"""A/B of lazy reduction inside the bucket-accumulation kernels on one B200, against the product library:
+  fp2lazy    G2: Fp2 product = Karatsuba on unreduced products, 2 reductions (accum_g2.cu with -DPS_FP2_LAZY)
+  fp2lazy2   G2: Fp2 product = schoolbook on unreduced products, 2 reductions (-DPS_FP2_LAZY=2)
+  fp2y3      G2: Y3 of the mixed addition = Karatsuba on three differences of products, 3 reductions instead of 6
+             (-DPS_FP2_LAZY_Y3)
+  g1nolazyy3 G1: Y3 = R (Q - X3) - Y1 PPP of the mixed addition as two Montgomery products (group_g1.cu with
+             -DPS_NO_LAZY_Y3; the product library computes it with one reduction)
+  g1sqr      G1: squarings as unreduced squares with the symmetric products taken once (-DPS_WIDE_SQR)
+G2 MSMs at 2^18 / 2^20 points, G1 at 2^24, all window tables, every result checked against (sum k_i s_i mod r) * G from
+the oracle.  Each library runs in its own process (PLAYSNARK_B200_LIB).
+    python tools/ab_fp2.py --build    # here: the variants into playsnark_b200/variants/
     python tools/ab_fp2.py            # on the GPU box
 """
 import ctypes as C
@@ -27,39 +33,60 @@ def child():
     lib = be.lib
     dev = torch.device("cuda:0")
     res = {}
-    for k in (18, 20):
+    cases = [(L.PS_G2, 18), (L.PS_G2, 20), (L.PS_G1, 24)]
+    only = os.environ.get("AB_ONLY")
+    if only:
+        cases = [c for c in cases if c[0] == int(only)]
+    for group, k in cases:
         n = 1 << k
         ks, sc = B.random_scalars_be(n, 3000 + 16 * k), B.random_scalars_be(n, 4000 + 16 * k)
-        bases = be.bases_from_scalars(L.PS_G2, ks.tobytes(), 0, -1)
+        bases = be.bases_from_scalars(group, ks.tobytes(), 0, -1)
         d_sc = torch.from_numpy(B.be_to_le_limbs(sc).view(np.int32)).to(dev)
         d_part = torch.zeros(384, dtype=torch.uint8, device=dev)
         step = lambda: be._check(lib.ps_msm_device(be.ctx, bases.handle, 0, C.c_void_p(d_sc.data_ptr()), n, C.c_void_p(d_part.data_ptr())))
         for _ in range(3):
             step()
         be.sync()
-        out = C.create_string_buffer(96)
-        be._check(lib.ps_msm_combine(be.ctx, L.PS_G2, C.c_void_p(d_part.data_ptr()), 1, out))
-        ok = out.raw == B.expected_point(L.PS_G2, B.expected_exponent(ks, sc))
+        out = C.create_string_buffer(96 if group == L.PS_G2 else 48)
+        be._check(lib.ps_msm_combine(be.ctx, group, C.c_void_p(d_part.data_ptr()), 1, out))
+        ok = out.raw == B.expected_point(group, B.expected_exponent(ks, sc))
         best, acc = 1e9, 1e9
         for _ in range(7):
             step()
             be.sync()
             t = be.msm_timing()
             best, acc = min(best, t["total_ms"]), min(acc, t["accumulate_ms"])
-        res["2p%d" % k] = {"total_ms": best, "accumulate_ms": acc, "parity": ok, "point": out.raw.hex()[:16]}
+        res["g%d_2p%d" % (group, k)] = {"total_ms": best, "accumulate_ms": acc, "parity": ok, "point": out.raw.hex()[:16]}
         bases.close()
+        del d_sc
+        torch.cuda.empty_cache()
     print("AB_RESULT " + json.dumps(res), flush=True)
 
 
 def main():
     if "--child" in sys.argv:
         return child()
+    if "--build" in sys.argv:
+        from playsnark_b200 import build as B
+        if "--all" in sys.argv:
+            B.build_variant("fp2lazy", ["-DPS_FP2_LAZY"], tus=("accum_g2.cu",))
+            B.build_variant("fp2lazy2", ["-DPS_FP2_LAZY=2"], tus=("accum_g2.cu",))
+        if "--all" in sys.argv:
+            B.build_variant("g1nolazyy3", ["-DPS_NO_LAZY_Y3"], tus=("group_g1.cu",))
+            B.build_variant("g1sqr", ["-DPS_WIDE_SQR"], tus=("group_g1.cu",))
+        B.build_variant("fp2y3", ["-DPS_FP2_LAZY_Y3"], tus=("accum_g2.cu",))
+        return
     libs = [("product", os.path.join(ROOT, "playsnark_b200", "libplaysnark_b200.so"))]
-    for p in sorted(glob.glob(os.path.join(ROOT, "playsnark_b200", "variants", "lib_fp2*.so"))):
+    for p in sorted(glob.glob(os.path.join(ROOT, "playsnark_b200", "variants", "lib_fp2*.so")) +
+                    glob.glob(os.path.join(ROOT, "playsnark_b200", "variants", "lib_g1*.so"))):
         libs.append((os.path.basename(p)[4:-3], p))
     rows = {}
     for name, path in libs:
         env = dict(os.environ, PLAYSNARK_B200_LIB=path)
+        if name.startswith("fp2"):
+            env["AB_ONLY"] = "2"     # the variant only changes the G2 kernel
+        elif name.startswith("g1"):
+            env["AB_ONLY"] = "1"
         out = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=env, capture_output=True, text=True, timeout=600)
         line = [l for l in out.stdout.splitlines() if l.startswith("AB_RESULT ")]
         rows[name] = json.loads(line[0][10:]) if line else {"error": out.stderr[-800:]}
