@@ -28,45 +28,11 @@ struct alignas(16) Fp2T {
   PS_DEV friend Fp2T operator-(const Fp2T& a, const Fp2T& b) { return Fp2T{a.c0 - b.c0, a.c1 - b.c1}; }
   PS_DEV Fp2T neg() const { return Fp2T{c0.neg(), c1.neg()}; }
   PS_DEV Fp2T dbl() const { return Fp2T{c0.dbl(), c1.dbl()}; }
-  // Karatsuba on UNREDUCED products: 3 wide multiplications and 2 Montgomery reductions (720 instead of 864
-  // multiply-adds); results identical to operator*.  NOT used by default: inside the G2 bucket accumulation (255
-  // registers already) it measured 21.87 ms against 19.83 ms at 2^20 points, and the schoolbook form below 21.29 ms
-  // (tools/ab_fp2.py, round 2); kept behind -DPS_FP2_LAZY[=2] with its host tests.  a0 + a1 and b0 + b1 stay below 2p < 2^382 unreduced, the three
-  // products below 4 p^2 < 2^768, a0 b1 + a1 b0 < 2 p^2 < p R, and a0 b0 - a1 b1 gets p R added when it is negative.
-  PS_DEV static Fp2T mul_lazy(const Fp2T& a, const Fp2T& b) {
-    constexpr int N = Fp::N;
-    uint32_t T0[2 * N], T1[2 * N], T2[2 * N];
-    mul_wide(T0, a.c0, b.c0);
-    mul_wide(T1, a.c1, b.c1);
-    Fp sa, sb;   // plain additions, no reduction
-    sa.v[0] = ptx_add_cc(a.c0.v[0], a.c1.v[0]);
-#pragma unroll
-    for (int k = 1; k < N - 1; k++) sa.v[k] = ptx_addc_cc(a.c0.v[k], a.c1.v[k]);
-    sa.v[N - 1] = ptx_addc(a.c0.v[N - 1], a.c1.v[N - 1]);
-    sb.v[0] = ptx_add_cc(b.c0.v[0], b.c1.v[0]);
-#pragma unroll
-    for (int k = 1; k < N - 1; k++) sb.v[k] = ptx_addc_cc(b.c0.v[k], b.c1.v[k]);
-    sb.v[N - 1] = ptx_addc(b.c0.v[N - 1], b.c1.v[N - 1]);
-    mul_wide(T2, sa, sb);
-    (void)sub_limbs<2 * N>(T2, T0);
-    (void)sub_limbs<2 * N>(T2, T1);
-    Fp c1 = redc_wide<FpParams>(T2);
-    const uint32_t borrow = sub_limbs<2 * N>(T0, T1);
-    T0[N] = ptx_add_cc(T0[N], FpParams::MOD(0) & borrow);
-#pragma unroll
-    for (int k = 1; k < N - 1; k++) T0[N + k] = ptx_addc_cc(T0[N + k], FpParams::MOD(k) & borrow);
-    T0[2 * N - 1] = ptx_addc(T0[2 * N - 1], FpParams::MOD(N - 1) & borrow);
-    return Fp2T{redc_wide<FpParams>(T0), c1};
-  }
-  // Karatsuba: 3 base-field products
+  // Karatsuba: 3 base-field products.  (Products on unreduced terms -- Karatsuba with 3 wide multiplications and 2
+  // reductions, 720 instead of 864 multiply-adds, or schoolbook with 4 + 2 -- were measured SLOWER inside the G2 bucket
+  // accumulation, 21.9 / 21.3 vs 19.8 ms at 2^20 points, and removed: that kernel sits at 255 registers and 2 warps
+  // per scheduler and is bound by latency, not by the number of multiply-adds; profiles/r02_ab_lazy.md.)
   PS_DEV friend Fp2T operator*(const Fp2T& a, const Fp2T& b) {
-#if defined(PS_FP2_LAZY) && PS_FP2_LAZY == 2
-    // schoolbook on unreduced products: c0 = a0 b0 + (p - a1) b1, c1 = a0 b1 + a1 b0, one reduction each (the same 864
-    // multiply-adds as three Montgomery products, a third fewer reduction rows, no wide temporaries)
-    if (INLINE) return Fp2T{mul2_lazy(a.c0, b.c0, neg_lazy(a.c1), b.c1), mul2_lazy(a.c0, b.c1, a.c1, b.c0)};
-#elif defined(PS_FP2_LAZY)
-    if (INLINE) return mul_lazy(a, b);
-#endif
     Fp t0 = mulp(a.c0, b.c0);
     Fp t1 = mulp(a.c1, b.c1);
     Fp t2 = mulp(a.c0 + a.c1, b.c0 + b.c1);
@@ -131,8 +97,7 @@ struct alignas(16) XYZZ {
 // a b - c d, the shape of Y3 in every addition / doubling formula below.  The base field computes it as
 // (a b + (p - c) d) / R with ONE Montgomery reduction (432 instead of 576 multiply-adds; same value bit for bit):
 // measured on B200 inside the G1 bucket accumulation, 2^24 points: 78.98 -> 75.86 ms (tools/ab_fp2.py, round 2).
-// -DPS_NO_LAZY_Y3 restores the two separate products (A/B builds).  Fp2 keeps separate products: unreduced Fp2
-// products were measured SLOWER in the G2 kernel (Fp2T::mul_lazy below).
+// -DPS_NO_LAZY_Y3 restores the two separate products (A/B builds, tools/ab_lazy.py).
 PS_DEV Fp mul_sub_pair(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
 #ifndef PS_NO_LAZY_Y3
   return mul2_lazy(a, b, neg_lazy(c), d);
@@ -140,20 +105,10 @@ PS_DEV Fp mul_sub_pair(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
   return a * b - c * d;
 #endif
 }
-// Fp2: Karatsuba on the three DIFFERENCES a0 b0 - c0 d0, a1 b1 - c1 d1, (a0 + a1)(b0 + b1) - (c0 + c1)(d0 + d1), each one
-// reduction (3 instead of 6 reductions for the two Fp2 products); only in the inlined G2 accumulation kernel.
+// Fp2 keeps two plain products (the same merge over Fp2, three differences of products with one reduction each, measured
+// 20.1 vs 19.7 ms in the G2 kernel).
 template <bool I>
-PS_DEV Fp2T<I> mul_sub_pair(const Fp2T<I>& a, const Fp2T<I>& b, const Fp2T<I>& c, const Fp2T<I>& d) {
-#ifdef PS_FP2_LAZY_Y3
-  if (I) {
-    Fp A = mul2_lazy(a.c0, b.c0, neg_lazy(c.c0), d.c0);
-    Fp B = mul2_lazy(a.c1, b.c1, neg_lazy(c.c1), d.c1);
-    Fp K = mul2_lazy(a.c0 + a.c1, b.c0 + b.c1, neg_lazy(c.c0 + c.c1), d.c0 + d.c1);
-    return Fp2T<I>{A - B, K - A - B};
-  }
-#endif
-  return a * b - c * d;
-}
+PS_DEV Fp2T<I> mul_sub_pair(const Fp2T<I>& a, const Fp2T<I>& b, const Fp2T<I>& c, const Fp2T<I>& d) { return a * b - c * d; }
 
 // 2*P for affine P (mdbl-2008-s-1, a = 0)
 template <class F>

@@ -89,7 +89,6 @@ PS_DEV void mad_chain_mod(uint32_t* acc, uint32_t b) {
 // ---- field element ----------------------------------------------------------------------------
 template <class P> struct Fe;
 template <class P> PS_NOINLINE Fe<P> fe_mul_call(const Fe<P>& a, const Fe<P>& b);
-template <class P> PS_DEV Fe<P> fe_sqr_wide(const Fe<P>& a);
 
 template <class P>
 struct alignas(16) Fe {
@@ -209,16 +208,11 @@ struct alignas(16) Fe {
     final_sub(r, top);
     return r;
   }
-  PS_DEV Fe sqr() const {
-#ifdef PS_WIDE_SQR
-    if (N == 12) return fe_sqr_wide(*this);   // unreduced square with the symmetric products taken once + one reduction
-#endif
-    return (*this) * (*this);
-  }
+  PS_DEV Fe sqr() const { return (*this) * (*this); }
 
-  // (A dedicated Montgomery squaring with the symmetric products taken once -- 234 instead of 300 MACs for Fp -- was
-  // measured slower inside the bucket-accumulation kernel, 82.4 vs 78.7 ms at 2^24 G1 points, and removed in round 2:
-  // that kernel is bound by dependent-issue latency, not by multiplier throughput.)
+  // (A dedicated squaring with the symmetric products taken once was measured slower inside the bucket-accumulation
+  // kernel twice in round 2 and removed: interleaved with the reduction, 234 instead of 300 MACs, 82.4 vs 78.7 ms at
+  // 2^24 G1 points; as an unreduced square + redc_wide, 222 MACs, 75.3 vs 74.2 ms (profiles/r02_ab_lazy.md).)
 
   PS_DEV Fe to_mont() const { return fe_mul_call(*this, from_const<P::R2>()); }
   PS_DEV Fe from_mont() const { Fe o = zero(); o.v[0] = 1; return fe_mul_call(*this, o); }
@@ -241,7 +235,7 @@ struct alignas(16) Fe {
   }
 };
 
-// ---- unreduced products (lazy reduction in Fp2, curve.cuh) ----------------------------------------------------
+// ---- unreduced products (sums of two products with ONE reduction: mul_sub_pair in curve.cuh) -------------------
 // acc[0..N) += sum over k of MOD[OFF+2k] * b * 2^(64k), consuming the pending carry flag at limb 0
 template <class P, int OFF>
 PS_DEV void madc_chain_mod(uint32_t* acc, uint32_t b) {
@@ -302,43 +296,6 @@ PS_DEV Fe<P> mul2_lazy(const Fe<P>& a, const Fe<P>& b, const Fe<P>& c, const Fe<
   wide_merge<N>(T, E, O);
   return redc_wide<P>(T);
 }
-// T[0..2N) = a * a: the products a_i a_j, i < j, taken once (N (N - 1) / 2 wide multiply-adds in the same two
-// accumulators as wide_rows: row i is one chain over j = i + 1, i + 3, ... and one over j = i + 2, i + 4, ...),
-// doubled with funnel shifts while the N squares a_i^2 -- disjoint limb pairs, no carries -- are added.
-template <class P>
-PS_DEV void sqr_wide(uint32_t* T, const Fe<P>& a) {
-  constexpr int N = P::N;
-  uint32_t E[2 * N + 2], O[2 * N + 2];
-#pragma unroll
-  for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
-#pragma unroll
-  for (int i = 0; i < N - 1; i++) {
-    const uint32_t bi = a.v[i];
-    {  // j = i + 1, i + 3, ...: positions 2i + 1, 2i + 3, ... (odd grid)
-      int pos = 2 * i + 1;
-      ptx_mad_wide_cc(O[pos], O[pos + 1], a.v[i + 1], bi);
-#pragma unroll
-      for (int j = i + 3; j < N; j += 2) { pos += 2; ptx_madc_wide_cc(O[pos], O[pos + 1], a.v[j], bi); }
-      O[pos + 2] = ptx_addc(O[pos + 2], 0);
-    }
-    if (i + 2 < N) {  // j = i + 2, i + 4, ...: positions 2i + 2, 2i + 4, ... (even grid)
-      int pos = 2 * i + 2;
-      ptx_mad_wide_cc(E[pos], E[pos + 1], a.v[i + 2], bi);
-#pragma unroll
-      for (int j = i + 4; j < N; j += 2) { pos += 2; ptx_madc_wide_cc(E[pos], E[pos + 1], a.v[j], bi); }
-      E[pos + 2] = ptx_addc(E[pos + 2], 0);
-    }
-  }
-  uint32_t Cx[2 * N], D[2 * N];
-  wide_merge<N>(Cx, E, O);
-#pragma unroll
-  for (int i = 0; i < N; i++) ptx_mul_wide(D[2 * i], D[2 * i + 1], a.v[i], a.v[i]);
-  T[0] = ptx_add_cc(Cx[0] << 1, D[0]);
-#pragma unroll
-  for (int k = 1; k < 2 * N - 1; k++) T[k] = ptx_addc_cc((Cx[k] << 1) | (Cx[k - 1] >> 31), D[k]);
-  T[2 * N - 1] = ptx_addc((Cx[2 * N - 1] << 1) | (Cx[2 * N - 2] >> 31), D[2 * N - 1]);
-}
-
 // p - a as a plain integer (a <= p): the additive inverse for use as an operand of an unreduced product (0 -> p)
 template <class P>
 PS_DEV Fe<P> neg_lazy(const Fe<P>& a) {
@@ -397,22 +354,6 @@ PS_DEV Fe<P> redc_wide(const uint32_t* T) {
   top = ptx_addc(top, 0);
   Fe<P>::final_sub(r, top);
   return r;
-}
-
-template <class P>
-PS_DEV Fe<P> fe_sqr_wide(const Fe<P>& a) {
-  uint32_t T[2 * P::N];
-  sqr_wide(T, a);
-  return redc_wide<P>(T);
-}
-
-// a - b over n limbs, in place; returns the borrow (0 or 0xffffffff)
-template <int n>
-PS_DEV uint32_t sub_limbs(uint32_t* a, const uint32_t* b) {
-  a[0] = ptx_sub_cc(a[0], b[0]);
-#pragma unroll
-  for (int k = 1; k < n; k++) a[k] = ptx_subc_cc(a[k], b[k]);
-  return ptx_subc(0, 0);
 }
 
 using Fp = Fe<FpParams>;

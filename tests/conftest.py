@@ -25,6 +25,5 @@ def host_check():
             os.path.join(ROOT, "playsnark_b200", "csrc", "curve.cuh"),
             os.path.join(ROOT, "playsnark_b200", "csrc", "constants.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        # the opt-in variants of the hot kernels (A/B builds) are switched on here so that their arithmetic is checked too
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-DPS_FP2_LAZY_Y3", "-shared", "-fPIC", "-o", so, srcs[0]])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, srcs[0]])
     return ctypes.CDLL(so)

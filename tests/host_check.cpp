@@ -41,17 +41,10 @@ void hc_fp_montmul_raw(const uint32_t* a, const uint32_t* b, uint32_t* o) { Fp x
 void hc_fr_montmul_raw(const uint32_t* a, const uint32_t* b, uint32_t* o) { Fr x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fr r = x * y; memcpy(o, r.v, 32); }
 void hc_fp2_mul(const uint32_t* a, const uint32_t* b, uint32_t* o) { store2(o, load2(a) * load2(b)); }
 void hc_fp2_sqr(const uint32_t* a, uint32_t* o) { store2(o, load2(a).sqr()); }
-// the lazy-reduction product (3 wide multiplications, 2 Montgomery reductions) and its two halves on raw limbs
-void hc_fp2_mul_lazy(const uint32_t* a, const uint32_t* b, uint32_t* o) { store2(o, Fp2::mul_lazy(load2(a), load2(b))); }
+// building blocks of the unreduced products on raw limbs
 void hc_fp_mul2_lazy_raw(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* o) {
   Fp x, y, z, w; memcpy(x.v, a, 48); memcpy(y.v, b, 48); memcpy(z.v, c, 48); memcpy(w.v, d, 48);
   Fp r = mul2_lazy(x, y, neg_lazy(z), w); memcpy(o, r.v, 48); }
-void hc_fp_sqr_wide_raw(const uint32_t* a, uint32_t* o) { Fp x; memcpy(x.v, a, 48); sqr_wide(o, x); }
-void hc_fp_sqr_via_wide_raw(const uint32_t* a, uint32_t* o) { Fp x; memcpy(x.v, a, 48); Fp r = fe_sqr_wide(x); memcpy(o, r.v, 48); }
-void hc_fp2_mul_sub_pair(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* o) {
-  Fp2 x = load2(a), y = load2(b), z = load2(c), w = load2(d);
-  Fp2I r = mul_sub_pair(Fp2I{x.c0, x.c1}, Fp2I{y.c0, y.c1}, Fp2I{z.c0, z.c1}, Fp2I{w.c0, w.c1});
-  store2(o, Fp2{r.c0, r.c1}); }
 void hc_fp_mul_wide_raw(const uint32_t* a, const uint32_t* b, uint32_t* o) { Fp x, y; memcpy(x.v, a, 48); memcpy(y.v, b, 48); mul_wide(o, x, y); }
 void hc_fp_redc_wide_raw(const uint32_t* t, uint32_t* o) { Fp r = redc_wide<FpParams>(t); memcpy(o, r.v, 48); }
 void hc_fp2_inv(const uint32_t* a, uint32_t* o) { store2(o, fp2_inv(load2(a))); }

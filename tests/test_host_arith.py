@@ -135,27 +135,12 @@ def test_fp2_ops(host_check):
             host_check.hc_fp2_inv(f2l(a), out); assert O.F2.mul(unf2(out), a) == (1, 0)
 
 
-def test_fp2_lazy_reduction(host_check):
-    """Fp2 product with unreduced Karatsuba terms (curve.cuh mul_lazy) = the plain product, bit for bit; its two
-    building blocks on raw limbs: the full 768-bit product (operands up to 2^384 - 1, not only field elements) and the
-    Montgomery reduction of any T < p R."""
+def test_unreduced_products(host_check):
+    """Building blocks of mul_sub_pair (curve.cuh: Y3 = a b - c d with ONE Montgomery reduction) on raw limbs: the full
+    768-bit product (operands up to 2^384 - 1, not only field elements), the reduction of any T < p R, and
+    (a b + (p - c) d) / R against a b - c d in the Montgomery domain, edge values included."""
     rng = random.Random(5)
     P = O.P
-    edge = [(0, 0), (1, 0), (0, 1), (P - 1, P - 1), (P - 1, 0), (0, P - 1), (1, P - 1), (P - 1, 1), ((P - 1) // 2, (P + 1) // 2)]
-    vals = edge + [(rng.randrange(P), rng.randrange(P)) for _ in range(25)]
-    out, ref = (U32 * 24)(), (U32 * 24)()
-    for a in vals:
-        for b in vals:
-            host_check.hc_fp2_mul_lazy(f2l(a), f2l(b), out)
-            assert unf2(out) == O.F2.mul(a, b)
-            host_check.hc_fp2_mul(f2l(a), f2l(b), ref)
-            assert list(out) == list(ref)
-    for a in vals[:12]:
-        for b in vals[5:14]:
-            for c in vals[:6] + vals[-2:]:
-                for d in vals[3:9]:
-                    host_check.hc_fp2_mul_sub_pair(f2l(a), f2l(b), f2l(c), f2l(d), out)      # a b - c d with three reductions
-                    assert unf2(out) == O.F2.sub(O.F2.mul(a, b), O.F2.mul(c, d))
     wide = (U32 * 24)()
     full = (1 << 384) - 1
     ints = [0, 1, full, full - 1, 1 << 383, 2 * P - 2, P, 0xFFFFFFFF, (1 << 352) - 1] + [rng.randrange(1 << 384) for _ in range(30)]
@@ -163,20 +148,13 @@ def test_fp2_lazy_reduction(host_check):
         for y in ints:
             host_check.hc_fp_mul_wide_raw(limbs(x, 12), limbs(y, 12), wide)
             assert unl(wide) == x * y
-    for x in ints:
-        host_check.hc_fp_sqr_wide_raw(limbs(x, 12), wide)          # symmetric products taken once
-        assert unl(wide) == x * x
     rinv = pow(1 << 384, -1, P)
     red = (U32 * 12)()
-    for x in [0, 1, P - 1, P - 2, (1 << 380)] + [rng.randrange(P) for _ in range(40)]:
-        host_check.hc_fp_sqr_via_wide_raw(limbs(x, 12), red)
-        assert unl(red) == x * x * rinv % P
     fe = [0, 1, P - 1, P - 2, (P - 1) // 2, (1 << 380)] + [rng.randrange(P) for _ in range(12)]
     for a in fe[:8]:
         for b in fe[:8]:
             for c in fe[:6] + fe[-3:]:
                 for d in fe[:4] + fe[-3:]:
-                    # (a b + (p - c) d) / R mod p with one reduction == a b - c d in the Montgomery domain
                     host_check.hc_fp_mul2_lazy_raw(limbs(a, 12), limbs(b, 12), limbs(c, 12), limbs(d, 12), red)
                     assert unl(red) == (a * b - c * d) * rinv % P
     ts = [0, 1, P, (1 << 384) - 1, 1 << 384, P << 384, (P << 384) - 1, (P - 1) << 384, ((P - 1) << 384) | ((1 << 384) - 1), 2 * P * P - 1]

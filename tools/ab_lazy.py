@@ -1,16 +1,13 @@
 #!/usr/bin/env python3
-"""A/B of lazy reduction inside the bucket-accumulation kernels on one B200, against the product library:
-  fp2lazy    G2: Fp2 product = Karatsuba on unreduced products, 2 reductions (accum_g2.cu with -DPS_FP2_LAZY)
-  fp2lazy2   G2: Fp2 product = schoolbook on unreduced products, 2 reductions (-DPS_FP2_LAZY=2)
-  fp2y3      G2: Y3 of the mixed addition = Karatsuba on three differences of products, 3 reductions instead of 6
-             (-DPS_FP2_LAZY_Y3)
-  g1nolazyy3 G1: Y3 = R (Q - X3) - Y1 PPP of the mixed addition as two Montgomery products (group_g1.cu with
-             -DPS_NO_LAZY_Y3; the product library computes it with one reduction)
-  g1sqr      G1: squarings as unreduced squares with the symmetric products taken once (-DPS_WIDE_SQR)
+"""A/B of the merged Y3 of the group law (curve.cuh mul_sub_pair: a b - c d as ONE reduction of two unreduced products)
+inside the bucket-accumulation kernels on one B200, against the product library:
+  g1nolazyy3   G1: Y3 as two Montgomery products (group_g1.cu with -DPS_NO_LAZY_Y3)
 G2 MSMs at 2^18 / 2^20 points, G1 at 2^24, all window tables, every result checked against (sum k_i s_i mod r) * G from
-the oracle.  Each library runs in its own process (PLAYSNARK_B200_LIB).
-    python tools/ab_fp2.py --build    # here: the variants into playsnark_b200/variants/
-    python tools/ab_fp2.py            # on the GPU box
+the oracle.  Each library runs in its own process (PLAYSNARK_B200_LIB).  Round 2's other variants (unreduced Fp2
+products, Fp2 Y3 on three differences, wide squaring) were measured with this tool at commit a58c4da and removed;
+numbers in profiles/r02_ab_lazy.md.
+    python tools/ab_lazy.py --build    # here: the variants into playsnark_b200/variants/
+    python tools/ab_lazy.py            # on the GPU box
 """
 import ctypes as C
 import glob
@@ -68,17 +65,11 @@ def main():
         return child()
     if "--build" in sys.argv:
         from playsnark_b200 import build as B
-        if "--all" in sys.argv:
-            B.build_variant("fp2lazy", ["-DPS_FP2_LAZY"], tus=("accum_g2.cu",))
-            B.build_variant("fp2lazy2", ["-DPS_FP2_LAZY=2"], tus=("accum_g2.cu",))
-        if "--all" in sys.argv:
-            B.build_variant("g1nolazyy3", ["-DPS_NO_LAZY_Y3"], tus=("group_g1.cu",))
-            B.build_variant("g1sqr", ["-DPS_WIDE_SQR"], tus=("group_g1.cu",))
-        B.build_variant("fp2y3", ["-DPS_FP2_LAZY_Y3"], tus=("accum_g2.cu",))
+        B.build_variant("g1nolazyy3", ["-DPS_NO_LAZY_Y3"], tus=("group_g1.cu",))
         return
     libs = [("product", os.path.join(ROOT, "playsnark_b200", "libplaysnark_b200.so"))]
     for p in sorted(glob.glob(os.path.join(ROOT, "playsnark_b200", "variants", "lib_fp2*.so")) +
-                    glob.glob(os.path.join(ROOT, "playsnark_b200", "variants", "lib_g1*.so"))):
+                    glob.glob(os.path.join(ROOT, "playsnark_b200", "variants", "lib_g1*.so"))):   # fp2*: G2-only variants
         libs.append((os.path.basename(p)[4:-3], p))
     rows = {}
     for name, path in libs:
@@ -92,7 +83,7 @@ def main():
         rows[name] = json.loads(line[0][10:]) if line else {"error": out.stderr[-800:]}
         print(name, json.dumps(rows[name]), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "ab_fp2.json"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", "ab_lazy.json"), "w") as f:
         json.dump(rows, f, indent=1)
 
 
