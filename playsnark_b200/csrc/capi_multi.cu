@@ -119,8 +119,9 @@ struct ps_mbases {
 
 namespace {
 
-void worker_main(ps_mctx* m, int d) {
-  Worker* w = m->workers[d];
+// (the Worker is handed over by pointer: m->workers is still growing in ps_mctx_create while the first threads start,
+// and indexing it from here raced with its reallocation -- a worker could end up waiting on a stale object)
+void worker_main(ps_mctx* m, int d, Worker* w) {
 #if PS_GPU
   cudaSetDevice(m->devs[d]);
 #endif
@@ -312,11 +313,12 @@ int ps_mctx_create(const int* devices, int ndev, ps_mctx** out) {
   for (int k = 0; k < TL_MAX; k++) m->tl[k].assign(ndev, nullptr);
 #endif
   if (rc != PS_OK) { ps_mctx_destroy(m); return rc; }
+  m->workers.reserve((size_t)ndev);
   for (int d = 0; d < ndev; d++) {
     Worker* w = new (std::nothrow) Worker();
     if (!w) { ps_mctx_destroy(m); return PS_ERR_ALLOC; }
     m->workers.push_back(w);
-    w->th = std::thread(worker_main, m, d);
+    w->th = std::thread(worker_main, m, d, w);
   }
   *out = m;
   return PS_OK;

@@ -244,29 +244,41 @@ PS_DEV void madc_chain_mod(uint32_t* acc, uint32_t b) {
   for (int j = 0; j < N; j += 2) ptx_madc_wide_cc(acc[j], acc[j + 1], P::MOD(OFF + j), b);
 }
 
-// Unreduced products a * b as plain integers of 2N limbs.  Two accumulators as in the Montgomery product: E takes the
+// Unreduced products as plain integers of 2N limbs.  Two accumulators as in the Montgomery product: E takes the
 // 64-bit partial products that start at even limb positions, O those that start at odd positions; every row is two
-// independent carry chains of N/2 wide multiply-adds, whose carry out lands in a limb no chain of that accumulator has
-// covered yet.  wide_rows<FIRST = true> initialises (E, O) with a * b, FIRST = false adds another product to them
-// (sums of products below 2^(64N) in total); wide_merge adds the two accumulators up.
-template <class P, bool FIRST>
-PS_DEV void wide_rows(uint32_t* E, uint32_t* O, const Fe<P>& a, const Fe<P>& b) {
+// independent carry chains of N/2 wide multiply-adds per product.  The carry out of a chain is added into the limb just
+// above it, which no chain of that accumulator has covered yet at that row (it only ever holds such carries, so it
+// cannot overflow).  That invariant is why a SUM of two products (DUAL: a b + c d < 2^(64N)) is accumulated row by row
+// for both products together: adding the second product after the first would find every limb already full, and a
+// carry added into a full limb is lost about once per 2^32 rows -- one wrong point per 2^24-point MSM, invisible to
+// random operands (tests/test_host_arith.py drives it with saturated limbs).
+template <class P, bool DUAL>
+PS_DEV void wide_rows(uint32_t* E, uint32_t* O, const Fe<P>& a, const Fe<P>& b, const Fe<P>& c, const Fe<P>& d) {
   constexpr int N = P::N;
-  if (FIRST) {
 #pragma unroll
-    for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
-    mul_chain<N>(E, a.v, b.v[0]);
-    mul_chain<N>(O + 1, a.v + 1, b.v[0]);
+  for (int k = 0; k < 2 * N + 2; k++) { E[k] = 0; O[k] = 0; }
+  mul_chain<N>(E, a.v, b.v[0]);
+  mul_chain<N>(O + 1, a.v + 1, b.v[0]);
+  if (DUAL) {
+    mad_chain<N, false>(E, c.v, d.v[0]);
+    E[N] = ptx_addc(E[N], 0);
+    mad_chain<N, false>(O + 1, c.v + 1, d.v[0]);
+    O[N + 1] = ptx_addc(O[N + 1], 0);
   }
 #pragma unroll
-  for (int i = FIRST ? 1 : 0; i < N; i++) {
-    const uint32_t bi = b.v[i];
-    uint32_t* ge = (i & 1) ? O : E;   // grid of the products of the even limbs of a: they start at position i + 2k
+  for (int i = 1; i < N; i++) {
+    uint32_t* ge = (i & 1) ? O : E;   // grid of the products of the even limbs of a / c: they start at position i + 2k
     uint32_t* go = (i & 1) ? E : O;   // grid of the products of the odd limbs: position i + 1 + 2k
-    mad_chain<N, false>(ge + i, a.v, bi);
+    mad_chain<N, false>(ge + i, a.v, b.v[i]);
     ge[i + N] = ptx_addc(ge[i + N], 0);
-    mad_chain<N, false>(go + i + 1, a.v + 1, bi);
+    mad_chain<N, false>(go + i + 1, a.v + 1, b.v[i]);
     go[i + 1 + N] = ptx_addc(go[i + 1 + N], 0);
+    if (DUAL) {
+      mad_chain<N, false>(ge + i, c.v, d.v[i]);
+      ge[i + N] = ptx_addc(ge[i + N], 0);
+      mad_chain<N, false>(go + i + 1, c.v + 1, d.v[i]);
+      go[i + 1 + N] = ptx_addc(go[i + 1 + N], 0);
+    }
   }
 }
 template <int N>
@@ -281,19 +293,24 @@ template <class P>
 PS_DEV void mul_wide(uint32_t* T, const Fe<P>& a, const Fe<P>& b) {
   constexpr int N = P::N;
   uint32_t E[2 * N + 2], O[2 * N + 2];
-  wide_rows<P, true>(E, O, a, b);
+  wide_rows<P, false>(E, O, a, b, a, b);
   wide_merge<N>(T, E, O);
 }
 // (a b + c d) / R mod p with ONE reduction; a b + c d < p R (e.g. all four below p, or p itself among them)
 template <class P>
 PS_DEV Fe<P> redc_wide(const uint32_t* T);
+// T[0..2N) = a b + c d as a plain integer (must stay below 2^(64N))
+template <class P>
+PS_DEV void mul2_wide(uint32_t* T, const Fe<P>& a, const Fe<P>& b, const Fe<P>& c, const Fe<P>& d) {
+  constexpr int N = P::N;
+  uint32_t E[2 * N + 2], O[2 * N + 2];
+  wide_rows<P, true>(E, O, a, b, c, d);
+  wide_merge<N>(T, E, O);
+}
 template <class P>
 PS_DEV Fe<P> mul2_lazy(const Fe<P>& a, const Fe<P>& b, const Fe<P>& c, const Fe<P>& d) {
-  constexpr int N = P::N;
-  uint32_t E[2 * N + 2], O[2 * N + 2], T[2 * N];
-  wide_rows<P, true>(E, O, a, b);
-  wide_rows<P, false>(E, O, c, d);
-  wide_merge<N>(T, E, O);
+  uint32_t T[2 * P::N];
+  mul2_wide(T, a, b, c, d);
   return redc_wide<P>(T);
 }
 // p - a as a plain integer (a <= p): the additive inverse for use as an operand of an unreduced product (0 -> p)

@@ -45,6 +45,10 @@ void hc_fp2_sqr(const uint32_t* a, uint32_t* o) { store2(o, load2(a).sqr()); }
 void hc_fp_mul2_lazy_raw(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* o) {
   Fp x, y, z, w; memcpy(x.v, a, 48); memcpy(y.v, b, 48); memcpy(z.v, c, 48); memcpy(w.v, d, 48);
   Fp r = mul2_lazy(x, y, neg_lazy(z), w); memcpy(o, r.v, 48); }
+// a b + c d as a plain 768-bit integer (the unreduced sum inside mul2_lazy), operands = any 12-limb integers
+void hc_fp_mul2_wide_raw(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* o) {
+  Fp x, y, z, w; memcpy(x.v, a, 48); memcpy(y.v, b, 48); memcpy(z.v, c, 48); memcpy(w.v, d, 48);
+  mul2_wide(o, x, y, z, w); }
 void hc_fp_mul_wide_raw(const uint32_t* a, const uint32_t* b, uint32_t* o) { Fp x, y; memcpy(x.v, a, 48); memcpy(y.v, b, 48); mul_wide(o, x, y); }
 void hc_fp_redc_wide_raw(const uint32_t* t, uint32_t* o) { Fp r = redc_wide<FpParams>(t); memcpy(o, r.v, 48); }
 void hc_fp2_inv(const uint32_t* a, uint32_t* o) { store2(o, fp2_inv(load2(a))); }

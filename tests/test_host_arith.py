@@ -148,8 +148,33 @@ def test_unreduced_products(host_check):
         for y in ints:
             host_check.hc_fp_mul_wide_raw(limbs(x, 12), limbs(y, 12), wide)
             assert unl(wide) == x * y
+    # a b + c d unreduced, limbs drawn from saturating values: every carry out of a row's chain lands in a limb that
+    # the FIRST product has already filled (a carry lost there shows up about once per 2^32 random rows: one wrong
+    # point per 2^24-point MSM, invisible to random operands)
+    sat = [0, 1, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, 0x7FFFFFFF, 2]
+    def sat_int(top):
+        v = 0
+        for i in range(12):
+            v |= rng.choice(sat) << (32 * i)
+        return v % top
+    for _ in range(20000):
+        a, b = sat_int(1 << 383), sat_int(1 << 384)
+        c, d = sat_int(1 << 383), sat_int(1 << 384)
+        host_check.hc_fp_mul2_wide_raw(limbs(a, 12), limbs(b, 12), limbs(c, 12), limbs(d, 12), wide)
+        assert unl(wide) == a * b + c * d, (hex(a), hex(b), hex(c), hex(d))
+        host_check.hc_fp_mul_wide_raw(limbs(b, 12), limbs(d, 12), wide)
+        assert unl(wide) == b * d
     rinv = pow(1 << 384, -1, P)
     red = (U32 * 12)()
+    for _ in range(3000):
+        t = (sat_int(P) << 384) | sat_int(1 << 384)                  # any T < p R with saturated limbs
+        host_check.hc_fp_redc_wide_raw(limbs(t, 24), red)
+        assert unl(red) == t * rinv % P, hex(t)
+        a, b, c, d = sat_int(P), sat_int(P), sat_int(P), sat_int(P)
+        host_check.hc_fp_mul2_lazy_raw(limbs(a, 12), limbs(b, 12), limbs(c, 12), limbs(d, 12), red)
+        assert unl(red) == (a * b - c * d) * rinv % P
+        host_check.hc_fp_montmul_raw(limbs(a, 12), limbs(b, 12), red)   # the plain product under the same operands
+        assert unl(red) == a * b * rinv % P
     fe = [0, 1, P - 1, P - 2, (P - 1) // 2, (1 << 380)] + [rng.randrange(P) for _ in range(12)]
     for a in fe[:8]:
         for b in fe[:8]:

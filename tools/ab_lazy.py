@@ -53,7 +53,16 @@ def child():
             be.sync()
             t = be.msm_timing()
             best, acc = min(best, t["total_ms"]), min(acc, t["accumulate_ms"])
-        res["g%d_2p%d" % (group, k)] = {"total_ms": best, "accumulate_ms": acc, "parity": ok, "point": out.raw.hex()[:16]}
+        # rare-event check: more scalar vectors over the same bases, each against the oracle's expectation
+        extra = 0
+        for rnd in range(int(os.environ.get("AB_EXTRA_PARITY", "4")) if k >= 22 else 0):
+            sc_x = B.random_scalars_be(n, 9000 + 7 * rnd + k)
+            d_sc.copy_(torch.from_numpy(B.be_to_le_limbs(sc_x).view(np.int32)).to(dev))
+            step()
+            be._check(lib.ps_msm_combine(be.ctx, group, C.c_void_p(d_part.data_ptr()), 1, out))
+            ok = ok and out.raw == B.expected_point(group, B.expected_exponent(ks, sc_x))
+            extra += 1
+        res["g%d_2p%d" % (group, k)] = {"extra_parity_rounds": extra, "total_ms": best, "accumulate_ms": acc, "parity": ok, "point": out.raw.hex()[:16]}
         bases.close()
         del d_sc
         torch.cuda.empty_cache()
