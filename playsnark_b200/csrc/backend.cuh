@@ -76,6 +76,10 @@ inline std::atomic<uint64_t>& launch_counter() { static std::atomic<uint64_t> c{
 // optional K::MIN_BLOCKS (resident blocks per SM the register allocator must allow)
 template <class K, class = void> struct MinBlocks { static constexpr int V = 1; };
 template <class K> struct MinBlocks<K, decltype((void)K::MIN_BLOCKS)> { static constexpr int V = K::MIN_BLOCKS; };
+// optional K::SMEM_PAD: bytes of (unused) dynamic shared memory requested per block, to hold the number of resident
+// blocks per SM BELOW what the registers alone would allow (wave-count tuning of multiplier-bound kernels); <= 48 KB
+template <class K, class = void> struct SmemPad { static constexpr int V = 0; };
+template <class K> struct SmemPad<K, decltype((void)K::SMEM_PAD)> { static constexpr int V = K::SMEM_PAD; };
 
 #if PS_GPU
 template <class K, class... Args>
@@ -88,15 +92,52 @@ inline int ps_launch(ps_stream_t st, size_t n, Args... args) {
   if (n == 0) return PS_OK;
   if (n > 0xFFFFFFFFull) return PS_ERR_ARG;
   uint32_t blocks = (uint32_t)((n + K::BLOCK - 1) / K::BLOCK);
-  ps_kernel<K, Args...><<<blocks, K::BLOCK, 0, st>>>((uint32_t)n, args...);
+  ps_kernel<K, Args...><<<blocks, K::BLOCK, SmemPad<K>::V, st>>>((uint32_t)n, args...);
   PS_CUDA_TRY(cudaGetLastError());
   launch_counter()++;
   return PS_OK;
 }
 #else
+// Host emulation (tests only).  Kernels whose threads write disjoint outputs and use no atomics may be marked
+// EmuParallel (specialisations next to the kernels, inside #if !PS_GPU): their serial loop is cut over the host's
+// cores, which is what keeps the CPU suite at a few minutes (the fixed-base tables alone are 16 320 scalar
+// multiplications per context).  PS_EMU_PROFILE=1 prints the seconds spent per kernel at exit.
+}  // namespace ps
+#include <chrono>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <typeinfo>
+namespace ps {
+template <class K> struct EmuParallel { static constexpr bool V = false; };
+struct EmuProfile {
+  std::map<std::string, double> secs;
+  std::mutex mu;
+  bool on = getenv("PS_EMU_PROFILE") != nullptr;
+  ~EmuProfile() {
+    if (on) for (auto& kv : secs) if (kv.second > 0.2) fprintf(stderr, "[emu] %8.2f s  %s\n", kv.second, kv.first.c_str());
+  }
+};
+inline EmuProfile& emu_profile() { static EmuProfile p; return p; }
 template <class K, class... Args>
 inline int ps_launch(ps_stream_t, size_t n, Args... args) {
-  for (size_t t = 0; t < n; t++) K::run((uint32_t)t, args...);
+  auto t0 = std::chrono::steady_clock::now();
+  unsigned hw = std::thread::hardware_concurrency();
+  if (EmuParallel<K>::V && n >= 64 && hw > 1) {
+    const size_t parts = hw < 16 ? hw : 16;
+    std::vector<std::thread> th;
+    for (size_t p = 0; p < parts; p++)
+      th.emplace_back([=]() { for (size_t t = n * p / parts; t < n * (p + 1) / parts; t++) K::run((uint32_t)t, args...); });
+    for (auto& x : th) x.join();
+  } else {
+    for (size_t t = 0; t < n; t++) K::run((uint32_t)t, args...);
+  }
+  EmuProfile& pr = emu_profile();
+  if (pr.on) {
+    std::lock_guard<std::mutex> g(pr.mu);
+    pr.secs[typeid(K).name()] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
   return PS_OK;
 }
 #endif

@@ -28,6 +28,9 @@ struct FixedBaseTableK {
     table[tid] = xyzz_to_affine_c(r);
   }
 };
+#if !PS_GPU
+template <class F> struct EmuParallel<FixedBaseTableK<F>> { static constexpr bool V = true; };   // host emulation only (backend.cuh)
+#endif
 // out[i] = scalar[i] * generator  (scalars: standard-form limbs), left in XYZZ form
 template <class F>
 struct FixedBaseMulK {

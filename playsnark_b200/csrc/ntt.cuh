@@ -58,6 +58,9 @@ PS_DEV Fr ntt_twiddle(const Fr* tw, uint32_t n, uint32_t M, uint32_t p) {
 #ifndef PS_NTT_MINB
 #define PS_NTT_MINB 4
 #endif
+#ifndef PS_NTT_SMEM_PAD
+#define PS_NTT_SMEM_PAD 0      // A/B builds only: see SmemPad in backend.cuh
+#endif
 
 // How the LAST pass of a batched transform writes its outputs (compile-time mode, so that every variant
 // stays as lean as the plain kernel).  The interpolation tree (interp.cuh) fuses its element-wise steps
@@ -95,6 +98,7 @@ template <int R, int MODE = NTT_ST_PLAIN, bool TRIV = false>
 struct NttDifK {
   static constexpr int BLOCK = PS_NTT_BLOCK;
   static constexpr int MIN_BLOCKS = PS_NTT_MINB;   // 8 field elements per thread: cap registers for 4 warps / scheduler
+  static constexpr int SMEM_PAD = PS_NTT_SMEM_PAD;
   // one launch = R stages on sub-transforms of size B (B >= 2^R); n/2^R threads
   PS_DEV static void run(uint32_t tid, Fr* a, uint32_t n, uint32_t B, const Fr* tw, NttIO io) {
     const uint32_t q = B >> R;
@@ -130,6 +134,7 @@ template <int R, int MODE = NTT_ST_PLAIN, bool TRIV = false>
 struct NttDitK {
   static constexpr int BLOCK = PS_NTT_BLOCK;
   static constexpr int MIN_BLOCKS = PS_NTT_MINB;
+  static constexpr int SMEM_PAD = PS_NTT_SMEM_PAD;
   // one launch = R stages that grow finished sub-transforms of size B0 to B0 * 2^R
   PS_DEV static void run(uint32_t tid, Fr* a, uint32_t n, uint32_t B0, const Fr* tw_inv, NttIO io) {
     const uint32_t blk = tid / B0, j = tid % B0;
