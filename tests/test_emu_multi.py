@@ -3,13 +3,11 @@ emulation: N "devices" are N contexts with one worker thread each, exchanging th
 on the GPU box (peer copies degrade to memmove, events to no-ops, the host barriers stay).  Every result must
 equal the single-context one bit for bit."""
 import os
-import random
 
 import pytest
 
-from oracle import ps_oracle as O
 from playsnark_b200 import _lib as L, api, build as B
-from tests import helpers as H, parity_cases as P
+from tests import parity_cases as P
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

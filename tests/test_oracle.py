@@ -1,7 +1,5 @@
 """Pins the oracle: public constants, the reference's integer-level known answers, algebraic
 self-checks of its own tests, and the committed golden fixtures (tools/make_golden.py)."""
-import json
-import os
 import random
 from fractions import Fraction
 
