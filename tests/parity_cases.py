@@ -175,6 +175,19 @@ def codec_roundtrip(be, n=24):
     assert [x.hex() for x in g.export()] == [c["g2_generator_compressed"], c["g2_two_g"], c["g2_infinity_compressed"]]
 
 
+def msm_linearity(be, n):
+    """MSM(s+t) = MSM(s) + MSM(t), MSM(k*s) = k*MSM(s) on a fixed base set."""
+    rng = random.Random(42)
+    bases = be.bases_from_scalars(L.PS_G1, [rng.randrange(1, O.R) for _ in range(n)])
+    s = [rng.randrange(O.R) for _ in range(n)]
+    t = [rng.randrange(O.R) for _ in range(n)]
+    k = rng.randrange(O.R)
+    ms, mt = O.g1_decompress(be.msm(bases, s)), O.g1_decompress(be.msm(bases, t))
+    mst = O.g1_decompress(be.msm(bases, [(a + b) % O.R for a, b in zip(s, t)]))
+    assert mst == O.g1_add(ms, mt)
+    assert O.g1_decompress(be.msm(bases, [a * k % O.R for a in s])) == O.g1_mul(k, ms)
+
+
 def ntt_cases(be, max_log=7):
     g = gold("ntt")
     v = [int(x, 16) for x in g["input"]]

@@ -24,6 +24,7 @@ def be():
 def test_codec(be): P.codec_roundtrip(be, 6)
 def test_msm_golden(be): P.msm_golden(be)
 def test_msm_errors(be): P.msm_errors(be)
+def test_msm_linearity(be): P.msm_linearity(be, 40)
 
 
 @pytest.mark.parametrize("kind", ["rand", "ones", "neg", "small", "zero", "edge"])
