@@ -1,10 +1,8 @@
 """Parity tests proper: the CUDA path, called through the product C ABI (libplaysnark_b200.so),
 against the oracle / golden fixtures, plus size-independent properties at BASELINE.json's sizes."""
-import random
 
 import pytest
 
-from oracle import ps_oracle as O
 from playsnark_b200 import _lib as L, api
 from tests import parity_cases as P
 
